@@ -1,0 +1,107 @@
+/*
+ * stamp_b200 -- C ABI of the B200 (sm_100a) hot path behind STAMP's plugin interfaces.
+ *
+ * The reference (KatherLab/STAMP v2.5.0) has no FFI: its boundary is three Python plugin
+ * interfaces (Extractor, MIL backbone, Encoder).  This header is the native boundary a
+ * maintainer binds from Python with ctypes; every entry point cites the
+ * reference call site whose arithmetic it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - the callee never allocates: callers pass outputs and workspaces;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value: 0 = OK, negative = error (stamp_b200_strerror); nothing throws;
+ *   - re-entrant per stream; one CUDA context per process (one process per GPU).
+ *   - "16-bit" matrices are IEEE fp16 unless a `bf16` flag says otherwise.
+ */
+#ifndef STAMP_B200_H
+#define STAMP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STAMP_B200_ABI_VERSION 1
+
+enum {
+    STAMP_OK = 0,
+    STAMP_ERR_BAD_ARG = -1,
+    STAMP_ERR_CUDA = -2,
+    STAMP_ERR_DRIVER = -3,
+    STAMP_ERR_UNSUPPORTED = -4,
+    STAMP_ERR_WORKSPACE = -5
+};
+
+int stamp_b200_abi_version(void);
+const char* stamp_b200_strerror(int code);
+/* kernels launched by this library since load / since the last reset (bench.py "gpu_launches") */
+long long stamp_b200_launch_count(void);
+void stamp_b200_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense layers: C[M,N] = epilogue(A[M,K] . W[N,K]^T), tcgen05/TMEM, TMA-fed.
+ * replaces: every nn.Linear / Conv2d(patch) on the path --
+ *   timm ViT blocks called from src/stamp/preprocessing/__init__.py:325;
+ *   src/stamp/modeling/models/vision_tranformer.py:137-139 (per-head Q/K/V, packed to one GEMM),
+ *   :153 (fc), :163-167 (feed_forward), :314-318 (project_features);
+ *   src/stamp/encoding/encoder/chief.py:45,257-266 (fc + gated attention branches).
+ * act:   0 none, 1 GELU(erf), 2 ReLU                         applied to acc + bias
+ * store: 0 out16[row,n] = v          1 out32[row,n] = v (+ table[m % gin, n])
+ *        2 out32[row,n] += gamma[n]*v (residual + LayerScale; gamma NULL = 1)
+ *        3 out16[row,n/2] = silu(v[n]) * v[n+1]   (SwiGLU, weight rows interleaved x1,x2)
+ *        4 out16[row,n/2] = tanh(v[n]) * sigmoid(v[n+1])   (gated attention)
+ * row remap (prefix tokens): row = (m / gin) * gout + goff + m % gin; gin = 0 -> row = m.
+ * lda/ldw/ldo/ldt in elements; lda, ldw multiples of 8; A, W 16-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+int stamp_gemm_tn(const void* A, long long lda, const void* W, long long ldw, void* out,
+                  long long ldo, int M, int N, int K, const float* bias, const float* gamma,
+                  int act, int store, int bf16, const float* table, long long ldt, int gin,
+                  int gout, int goff, void* stream);
+
+/* LayerNorm over the last dim of an fp32 matrix; out_kind 0 fp16, 1 bf16, 2 fp32.
+ * replaces: timm Block.norm1/norm2/norm (eps 1e-6); nn.LayerNorm in
+ *   src/stamp/modeling/models/vision_tranformer.py:161,186,277 (eps 1e-5). */
+int stamp_layernorm(const float* x, long long ldx, const float* weight, const float* bias,
+                    void* out, long long ldo, int rows, int cols, float eps, int out_kind,
+                    void* stream);
+
+/* x[g*rows_per_group + row_off + r, :] = src[r, :] (+ add[r, :]);  class / register token rows.
+ * replaces: timm VisionTransformer._pos_embed (cls/reg token concat);
+ *   src/stamp/modeling/models/vision_tranformer.py:347-348 (class token concat). */
+int stamp_fill_rows(float* x, long long ldx, int groups, int rows_per_group, int row_off,
+                    const float* src, long long lds, const float* add, long long lda, int nrows,
+                    int cols, void* stream);
+
+/* uint8 HWC tiles [B,img,img,3] -> 16-bit patch matrix [B*(img/P)^2, Kpad], columns (c,ky,kx),
+ * values ((x/255) - mean[c]) / std[c]; columns >= 3*P*P are zero.  host_mean/host_std: 3 floats.
+ * replaces: Extractor.transform (ToTensor + Normalize) applied per tile at
+ *   src/stamp/preprocessing/__init__.py:94 and the H2D of fp32 tiles at :325, plus the im2col
+ *   of timm PatchEmbed's Conv2d. */
+int stamp_tiles_to_patches(const uint8_t* tiles, void* patches, int B, int img, int P, int Kpad,
+                           const float* host_mean, const float* host_std, int bf16, void* stream);
+
+/* Fused attention forward, fp16 in/out, O(S) memory.
+ *   q,k,v: element pointers to (bag 0, token 0, head 0); head h at +h*head_dim;
+ *   coords NULL  -> O = softmax(QK^T*scale) V                       (timm Attention / SDPA)
+ *   coords given -> O = (softmax(QK^T*scale) - slope[h]*Dist) V     (reference ALiBi)
+ *   mask [B,S] (1 = masked) with mask_mode 1 reproduces the reference's masked branch
+ *   (attn_mask = m_q&m_k | (q>=1 & k==0) applied after the softmax, no ALiBi on row/col 0);
+ *   mask_mode 2 = -inf before the softmax (nn.MultiheadAttention semantics).
+ * replaces: src/stamp/modeling/models/vision_tranformer.py:42-74,123-154,218-228,354-379
+ *   and timm Attention.forward's F.scaled_dot_product_attention.
+ * dscale: [B,2] scratch filled by stamp_alibi_dist_scale (power-of-two range scale per bag). */
+int stamp_attention_fwd(const void* q, const void* k, const void* v, long long row_stride,
+                        long long batch_stride, void* out, long long out_row_stride,
+                        long long out_batch_stride, int B, int S, int H, int head_dim,
+                        float scale, const float* coords, const float* slope,
+                        const float* dscale, const uint8_t* mask, int mask_mode, void* stream);
+int stamp_alibi_dist_scale(const float* coords, const float* slope, int B, int S, int H,
+                           float* dscale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STAMP_B200_H */

@@ -1,0 +1,32 @@
+// Fused attention forward (attention.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+struct AttnParams {
+    const __half* q;  // head 0 of token 0 of bag 0; head h at +h*head_dim
+    const __half* k;
+    const __half* v;
+    long long row_stride;    // elements between consecutive tokens
+    long long batch_stride;  // elements between consecutive bags / tiles
+    __half* out;             // [B, S, H*head_dim], head-major concat
+    long long out_row_stride;
+    long long out_batch_stride;
+    int B, S, H;
+    float scale_log2;        // softmax scale * log2(e)
+    const float* coords;     // [B, S, 2] fp32 or null (no ALiBi)
+    const float* slope;      // [H]   bias_scale_h / running_mean_h
+    const float* dscale;     // [B, 2] {2^-e, 2^e} from alibi_dist_scale
+    const uint8_t* mask;     // [B, S] 1 = masked token, or null
+    int mask_mode;           // 1: reference ALiBi masked branch (post-softmax), 2: -inf before softmax
+};
+
+int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
+
+int alibi_dist_scale(const float* coords, const float* slope, int B, int S, int H, float* dscale,
+                     cudaStream_t stream);
+
+}  // namespace sb

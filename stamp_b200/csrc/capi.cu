@@ -1,0 +1,102 @@
+// extern "C" surface of libstamp_b200.so (declared in include/stamp_b200.h): argument checks,
+// status codes and launch accounting around the kernels; no torch types, no allocation.
+#include "stamp_b200.h"
+
+#include <atomic>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "rowops.cuh"
+
+namespace sb {
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace sb
+
+extern "C" {
+
+int stamp_b200_abi_version(void) { return STAMP_B200_ABI_VERSION; }
+
+const char* stamp_b200_strerror(int code) {
+    switch (code) {
+    case STAMP_OK: return "ok";
+    case STAMP_ERR_BAD_ARG: return "bad argument (null pointer, misaligned or non-positive size)";
+    case STAMP_ERR_CUDA: return "CUDA runtime error at launch";
+    case STAMP_ERR_DRIVER: return "CUDA driver entry point unavailable (cuTensorMapEncodeTiled)";
+    case STAMP_ERR_UNSUPPORTED: return "unsupported shape for the sm_100a kernels";
+    case STAMP_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown error";
+    }
+}
+
+long long stamp_b200_launch_count(void) { return sb::g_launches.load(std::memory_order_relaxed); }
+void stamp_b200_reset_launch_count(void) { sb::g_launches.store(0, std::memory_order_relaxed); }
+
+int stamp_gemm_tn(const void* A, long long lda, const void* W, long long ldw, void* out,
+                  long long ldo, int M, int N, int K, const float* bias, const float* gamma,
+                  int act, int store, int bf16, const float* table, long long ldt, int gin,
+                  int gout, int goff, void* stream) {
+    if (act < 0 || act > 2 || store < 0 || store > 4) return STAMP_ERR_BAD_ARG;
+    sb::GemmParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.act = act; p.store = store; p.bf16 = bf16;
+    p.out = out; p.ldo = ldo;
+    p.bias = bias; p.gamma = gamma;
+    p.table = table; p.ldt = ldt;
+    p.gin = gin; p.gout = gout; p.goff = goff;
+    return sb::gemm_tn(A, lda, W, ldw, p, static_cast<cudaStream_t>(stream));
+}
+
+int stamp_layernorm(const float* x, long long ldx, const float* weight, const float* bias,
+                    void* out, long long ldo, int rows, int cols, float eps, int out_kind,
+                    void* stream) {
+    if (x == nullptr || weight == nullptr || bias == nullptr || out == nullptr) return STAMP_ERR_BAD_ARG;
+    return sb::layernorm(x, ldx, weight, bias, out, ldo, rows, cols, eps, out_kind,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int stamp_fill_rows(float* x, long long ldx, int groups, int rows_per_group, int row_off,
+                    const float* src, long long lds, const float* add, long long lda, int nrows,
+                    int cols, void* stream) {
+    if (x == nullptr || src == nullptr) return STAMP_ERR_BAD_ARG;
+    return sb::fill_rows(x, ldx, groups, rows_per_group, row_off, src, lds, add, lda, nrows, cols,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int stamp_tiles_to_patches(const uint8_t* tiles, void* patches, int B, int img, int P, int Kpad,
+                           const float* host_mean, const float* host_std, int bf16, void* stream) {
+    if (tiles == nullptr || patches == nullptr || host_mean == nullptr || host_std == nullptr)
+        return STAMP_ERR_BAD_ARG;
+    return sb::tiles_to_patches(tiles, patches, B, img, P, Kpad, host_mean, host_std, bf16,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int stamp_attention_fwd(const void* q, const void* k, const void* v, long long row_stride,
+                        long long batch_stride, void* out, long long out_row_stride,
+                        long long out_batch_stride, int B, int S, int H, int head_dim,
+                        float scale, const float* coords, const float* slope,
+                        const float* dscale, const uint8_t* mask, int mask_mode, void* stream) {
+    if (q == nullptr || k == nullptr || v == nullptr || out == nullptr) return STAMP_ERR_BAD_ARG;
+    if (mask != nullptr && mask_mode != 1 && mask_mode != 2) return STAMP_ERR_BAD_ARG;
+    sb::AttnParams p;
+    p.q = static_cast<const __half*>(q);
+    p.k = static_cast<const __half*>(k);
+    p.v = static_cast<const __half*>(v);
+    p.row_stride = row_stride; p.batch_stride = batch_stride;
+    p.out = static_cast<__half*>(out);
+    p.out_row_stride = out_row_stride; p.out_batch_stride = out_batch_stride;
+    p.B = B; p.S = S; p.H = H;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    p.coords = coords; p.slope = slope; p.dscale = dscale;
+    p.mask = mask; p.mask_mode = mask_mode;
+    return sb::attention_fwd(p, head_dim, static_cast<cudaStream_t>(stream));
+}
+
+int stamp_alibi_dist_scale(const float* coords, const float* slope, int B, int S, int H,
+                           float* dscale, void* stream) {
+    if (coords == nullptr || slope == nullptr || dscale == nullptr) return STAMP_ERR_BAD_ARG;
+    return sb::alibi_dist_scale(coords, slope, B, S, H, dscale, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,232 @@
+// Row-wise HBM-bound kernels: LayerNorm (fp32 residual stream -> 16-bit GEMM operand or fp32),
+// token-row fills, and the uint8 tile -> normalised patch-matrix transform.
+//
+// reference: LayerNorm = timm Block.norm1/norm2/norm (eps 1e-6) and the MIL aggregator's
+// nn.LayerNorm (src/stamp/modeling/models/vision_tranformer.py:161,186,277, eps 1e-5);
+// tile transform = ToTensor + Normalize applied per tile in
+// src/stamp/preprocessing/__init__.py:94 (Extractor.transform).
+#include "rowops.cuh"
+
+#include "common.cuh"
+
+namespace sb {
+
+namespace {
+
+// One warp per row; row cached in registers (cols <= 32 * 4 * MAXV), two-pass variance
+// (mean first, then sum of squared deviations) to match torch's numerics.
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w,
+                 const float* __restrict__ b, void* __restrict__ out, long long ldo, int rows,
+                 int cols, float eps, int out_kind /*0 fp16, 1 bf16, 2 fp32*/) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const float* xr = x + static_cast<long long>(warp) * ldx;
+    const int nvec = cols >> 2;  // cols % 4 == 0 enforced by the launcher
+    float4 v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < nvec) {
+            v[i] = *reinterpret_cast<const float4*>(xr + idx * 4);
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    s = warp_sum(s);
+    const float mean = s / static_cast<float>(cols);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < nvec) {
+            float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+            q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        }
+    }
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q / static_cast<float>(cols) + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int idx = lane + i * 32;
+        if (idx < nvec) {
+            float4 ww = __ldg(reinterpret_cast<const float4*>(w) + idx);
+            float4 bb = __ldg(reinterpret_cast<const float4*>(b) + idx);
+            float y0 = (v[i].x - mean) * rstd * ww.x + bb.x;
+            float y1 = (v[i].y - mean) * rstd * ww.y + bb.y;
+            float y2 = (v[i].z - mean) * rstd * ww.z + bb.z;
+            float y3 = (v[i].w - mean) * rstd * ww.w + bb.w;
+            if (out_kind == 2) {
+                float* o = reinterpret_cast<float*>(out) + static_cast<long long>(warp) * ldo;
+                *reinterpret_cast<float4*>(o + idx * 4) = make_float4(y0, y1, y2, y3);
+            } else {
+                uint16_t* o = reinterpret_cast<uint16_t*>(out) + static_cast<long long>(warp) * ldo;
+                uint2 pk;
+                pk.x = pack_16(y0, y1, out_kind == 1);
+                pk.y = pack_16(y2, y3, out_kind == 1);
+                *reinterpret_cast<uint2*>(o + idx * 4) = pk;
+            }
+        }
+    }
+}
+
+// x[g * rows_per_group + row_off + r, :] = src[r, :] (+ add[r, :])     fp32 rows
+__global__ void fill_rows_kernel(float* __restrict__ x, long long ldx, int groups,
+                                 int rows_per_group, int row_off, const float* __restrict__ src,
+                                 long long lds, const float* __restrict__ add, long long lda,
+                                 int nrows, int cols) {
+    const long long total = static_cast<long long>(groups) * nrows * (cols >> 2);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c4 = static_cast<int>(i % (cols >> 2));
+        const long long t = i / (cols >> 2);
+        const int r = static_cast<int>(t % nrows);
+        const int g = static_cast<int>(t / nrows);
+        float4 v = __ldg(reinterpret_cast<const float4*>(src + r * lds) + c4);
+        if (add != nullptr) {
+            float4 a = __ldg(reinterpret_cast<const float4*>(add + r * lda) + c4);
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        }
+        float* o = x + (static_cast<long long>(g) * rows_per_group + row_off + r) * ldx;
+        reinterpret_cast<float4*>(o)[c4] = v;
+    }
+}
+
+// uint8 tiles [B, img, img, 3] (HWC) -> 16-bit patch matrix [B * (img/P)^2, 3 * P * P] with
+// column order (c, ky, kx), i.e. the flattening of a Conv2d(3, D, P, stride=P) weight, after
+// x/255 -> (x - mean) / std.  One thread handles 8 consecutive kx of one (patch, c, ky) row:
+// 24 bytes of input (3 channels interleaved), one 16-byte store.
+__global__ void __launch_bounds__(256)
+tiles_to_patches_kernel(const uint8_t* __restrict__ tiles, uint16_t* __restrict__ patches, int B,
+                        int img, int P, float3 scale, float3 shift, int bf16) {
+    const int gp = img / P;           // patches per side
+    const int kx8 = P / 8;            // 8-pixel groups per patch row (P = 16 -> 2; P = 14 handled below)
+    const long long total = static_cast<long long>(B) * gp * gp * P * kx8;
+    const int K = 3 * P * P;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        long long t = i;
+        const int xg = static_cast<int>(t % kx8); t /= kx8;
+        const int ky = static_cast<int>(t % P); t /= P;
+        const int px = static_cast<int>(t % gp); t /= gp;
+        const int py = static_cast<int>(t % gp); t /= gp;
+        const int b = static_cast<int>(t);
+        const int y = py * P + ky;
+        const int x0 = px * P + xg * 8;
+        const uint8_t* src = tiles + ((static_cast<long long>(b) * img + y) * img + x0) * 3;
+        uint8_t px24[24];
+        // 24 bytes, 8-byte aligned because x0 % 8 == 0 and row pitch img*3 is a multiple of 8 for img % 8 == 0
+        const uint2* s2 = reinterpret_cast<const uint2*>(src);
+        uint2 a0 = __ldg(s2), a1 = __ldg(s2 + 1), a2 = __ldg(s2 + 2);
+        *reinterpret_cast<uint2*>(px24) = a0;
+        *reinterpret_cast<uint2*>(px24 + 8) = a1;
+        *reinterpret_cast<uint2*>(px24 + 16) = a2;
+        const long long prow = (static_cast<long long>(b) * gp + py) * gp + px;
+        const float sc[3] = {scale.x, scale.y, scale.z};
+        const float sh[3] = {shift.x, shift.y, shift.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(static_cast<float>(px24[j * 3 + c]), sc[c], sh[c]);
+            uint4 w;
+            w.x = pack_16(f[0], f[1], bf16);
+            w.y = pack_16(f[2], f[3], bf16);
+            w.z = pack_16(f[4], f[5], bf16);
+            w.w = pack_16(f[6], f[7], bf16);
+            uint16_t* o = patches + prow * K + (c * P + ky) * P + xg * 8;
+            *reinterpret_cast<uint4*>(o) = w;
+        }
+    }
+}
+
+// generic (any P, e.g. 14): one thread per output element pair; slower but only used for P % 8 != 0
+__global__ void __launch_bounds__(256)
+tiles_to_patches_generic_kernel(const uint8_t* __restrict__ tiles, uint16_t* __restrict__ patches,
+                                int B, int img, int P, int Kpad, float3 scale, float3 shift,
+                                int bf16) {
+    const int gp = img / P;
+    const int K = 3 * P * P;
+    const long long total = static_cast<long long>(B) * gp * gp * Kpad;
+    const float sc[3] = {scale.x, scale.y, scale.z};
+    const float sh[3] = {shift.x, shift.y, shift.z};
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i % Kpad);
+        const long long prow = i / Kpad;
+        float f = 0.f;
+        if (k < K) {
+            const int kx = k % P, ky = (k / P) % P, c = k / (P * P);
+            const int px = static_cast<int>(prow % gp);
+            const int py = static_cast<int>((prow / gp) % gp);
+            const long long b = prow / (gp * gp);
+            const uint8_t v = __ldg(tiles + ((b * img + py * P + ky) * img + px * P + kx) * 3 + c);
+            f = fmaf(static_cast<float>(v), sc[c], sh[c]);
+        }
+        uint32_t w = pack_16(f, 0.f, bf16);
+        patches[i] = static_cast<uint16_t>(w & 0xFFFF);
+    }
+}
+
+inline int grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    const long long cap = 148LL * 16;
+    return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+int layernorm(const float* x, long long ldx, const float* w, const float* b, void* out,
+              long long ldo, int rows, int cols, float eps, int out_kind, cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0 || (cols % 4) != 0 || (ldx % 4) != 0 || (ldo % 4) != 0 ||
+        out_kind < 0 || out_kind > 2)
+        return SB_ERR_BAD_ARG;
+    const int threads = 256;
+    const int blocks = (rows * 32 + threads - 1) / threads;
+    if (cols <= 512)
+        layernorm_kernel<4><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, ldo, rows, cols, eps, out_kind);
+    else if (cols <= 1024)
+        layernorm_kernel<8><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, ldo, rows, cols, eps, out_kind);
+    else if (cols <= 2048)
+        layernorm_kernel<16><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, ldo, rows, cols, eps, out_kind);
+    else
+        return SB_ERR_UNSUPPORTED;
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+int fill_rows(float* x, long long ldx, int groups, int rows_per_group, int row_off,
+              const float* src, long long lds, const float* add, long long lda, int nrows, int cols,
+              cudaStream_t stream) {
+    if (groups <= 0 || nrows <= 0 || (cols % 4) != 0) return SB_ERR_BAD_ARG;
+    const long long total = static_cast<long long>(groups) * nrows * (cols / 4);
+    fill_rows_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, ldx, groups, rows_per_group,
+                                                              row_off, src, lds, add, lda, nrows, cols);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+int tiles_to_patches(const uint8_t* tiles, void* patches, int B, int img, int P, int Kpad,
+                     const float mean[3], const float stdv[3], int bf16, cudaStream_t stream) {
+    if (B <= 0 || img <= 0 || P <= 0 || (img % P) != 0 || Kpad < 3 * P * P) return SB_ERR_BAD_ARG;
+    float3 scale = make_float3(1.f / (255.f * stdv[0]), 1.f / (255.f * stdv[1]), 1.f / (255.f * stdv[2]));
+    float3 shift = make_float3(-mean[0] / stdv[0], -mean[1] / stdv[1], -mean[2] / stdv[2]);
+    const int gp = img / P;
+    if ((P % 8) == 0 && (img % 8) == 0 && Kpad == 3 * P * P &&
+        (reinterpret_cast<uintptr_t>(tiles) & 7) == 0) {
+        const long long total = static_cast<long long>(B) * gp * gp * P * (P / 8);
+        tiles_to_patches_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+            tiles, reinterpret_cast<uint16_t*>(patches), B, img, P, scale, shift, bf16);
+    count_launch();
+    } else {
+        const long long total = static_cast<long long>(B) * gp * gp * Kpad;
+        tiles_to_patches_generic_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+            tiles, reinterpret_cast<uint16_t*>(patches), B, img, P, Kpad, scale, shift, bf16);
+    count_launch();
+    }
+    return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+}  // namespace sb

@@ -1,0 +1,21 @@
+// Row-wise HBM-bound kernels (rowops.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+// out_kind: 0 fp16, 1 bf16, 2 fp32
+int layernorm(const float* x, long long ldx, const float* w, const float* b, void* out,
+              long long ldo, int rows, int cols, float eps, int out_kind, cudaStream_t stream);
+
+// x[g * rows_per_group + row_off + r, :] = src[r, :] (+ add[r, :]) for g < groups, r < nrows
+int fill_rows(float* x, long long ldx, int groups, int rows_per_group, int row_off,
+              const float* src, long long lds, const float* add, long long lda, int nrows, int cols,
+              cudaStream_t stream);
+
+// uint8 HWC tiles -> normalised 16-bit patch matrix [B * (img/P)^2, Kpad], columns (c, ky, kx)
+int tiles_to_patches(const uint8_t* tiles, void* patches, int B, int img, int P, int Kpad,
+                     const float mean[3], const float stdv[3], int bf16, cudaStream_t stream);
+
+}  // namespace sb
