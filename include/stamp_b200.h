@@ -54,11 +54,13 @@ void stamp_b200_reset_launch_count(void);
  *        3 out16[row,n/2] = silu(v[n]) * v[n+1]   (SwiGLU, weight rows interleaved x1,x2)
  *        4 out16[row,n/2] = tanh(v[n]) * sigmoid(v[n+1])   (gated attention)
  * row remap (prefix tokens): row = (m / gin) * gout + goff + m % gin; gin = 0 -> row = m.
- * lda/ldw/ldo/ldt in elements; lda, ldw multiples of 8; A, W 16-byte aligned.
+ * dtype: operand type 0 fp16, 1 bf16, 2 fp32 consumed as TF32 (kind::tf32; pre-round operands
+ *        to TF32 to avoid the hardware's truncation); 16-bit outputs are fp16 (bf16 if dtype 1).
+ * lda/ldw/ldo/ldt in elements; A, W 16-byte aligned with 16-byte row pitch.
  * ------------------------------------------------------------------------------------------- */
 int stamp_gemm_tn(const void* A, long long lda, const void* W, long long ldw, void* out,
                   long long ldo, int M, int N, int K, const float* bias, const float* gamma,
-                  int act, int store, int bf16, const float* table, long long ldt, int gin,
+                  int act, int store, int dtype, const float* table, long long ldt, int gin,
                   int gout, int goff, void* stream);
 
 /* LayerNorm over the last dim of an fp32 matrix; out_kind 0 fp16, 1 bf16, 2 fp32.
@@ -92,11 +94,13 @@ int stamp_tiles_to_patches(const uint8_t* tiles, void* patches, int B, int img, 
  *   mask_mode 2 = -inf before the softmax (nn.MultiheadAttention semantics).
  * replaces: src/stamp/modeling/models/vision_tranformer.py:42-74,123-154,218-228,354-379
  *   and timm Attention.forward's F.scaled_dot_product_attention.
+ * out_f32: 0 -> fp16 output; 1 -> fp32 output rounded to TF32 (the ALiBi term of the reference is
+ *   unscaled distances, |O| easily exceeds the fp16 range; it then feeds a dtype-2 GEMM).
  * dscale: [B,2] scratch filled by stamp_alibi_dist_scale (power-of-two range scale per bag). */
 int stamp_attention_fwd(const void* q, const void* k, const void* v, long long row_stride,
                         long long batch_stride, void* out, long long out_row_stride,
-                        long long out_batch_stride, int B, int S, int H, int head_dim,
-                        float scale, const float* coords, const float* slope,
+                        long long out_batch_stride, int out_f32, int B, int S, int H,
+                        int head_dim, float scale, const float* coords, const float* slope,
                         const float* dscale, const uint8_t* mask, int mask_mode, void* stream);
 int stamp_alibi_dist_scale(const float* coords, const float* slope, int B, int S, int H,
                            float* dscale, void* stream);

@@ -32,7 +32,7 @@ SIGNATURES: dict[str, tuple] = {
     "stamp_tiles_to_patches": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_fp, c_fp,
                                        c_int, c_void_p]),
     "stamp_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll,
-                                    c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                                    c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_int, c_void_p]),
     "stamp_alibi_dist_scale": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
 }

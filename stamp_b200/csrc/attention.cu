@@ -296,7 +296,7 @@ flash_attn_kernel(const AttnParams p) {
     l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
     l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
     const float inv_a = 1.0f / l_a, inv_b = 1.0f / l_b;
-    __half* ob = p.out + b * p.out_batch_stride + h * HD;
+    const long long obase = b * p.out_batch_stride + h * HD;
 #pragma unroll
     for (int nt = 0; nt < ONT; ++nt) {
         float ya0 = o1[nt][0] * inv_a, ya1 = o1[nt][1] * inv_a;
@@ -308,10 +308,23 @@ flash_attn_kernel(const AttnParams p) {
             yb1 = fmaf(-descale, o2[nt][3], yb1);
         }
         const int col = nt * 8 + 2 * t4;
-        if (row_a < S)
-            *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(row_a) * p.out_row_stride + col) = pack_f16(ya0, ya1);
-        if (row_b < S)
-            *reinterpret_cast<uint32_t*>(ob + static_cast<long long>(row_b) * p.out_row_stride + col) = pack_f16(yb0, yb1);
+        if (p.out_f32) {
+            // fp32 output pre-rounded (round-to-nearest) to TF32: it is the A operand of a
+            // kind::tf32 GEMM, whose hardware conversion would otherwise truncate
+            float* of = reinterpret_cast<float*>(p.out) + obase;
+            if (row_a < S)
+                *reinterpret_cast<float2*>(of + static_cast<long long>(row_a) * p.out_row_stride + col) =
+                    make_float2(round_tf32(ya0), round_tf32(ya1));
+            if (row_b < S)
+                *reinterpret_cast<float2*>(of + static_cast<long long>(row_b) * p.out_row_stride + col) =
+                    make_float2(round_tf32(yb0), round_tf32(yb1));
+        } else {
+            __half* oh = reinterpret_cast<__half*>(p.out) + obase;
+            if (row_a < S)
+                *reinterpret_cast<uint32_t*>(oh + static_cast<long long>(row_a) * p.out_row_stride + col) = pack_f16(ya0, ya1);
+            if (row_b < S)
+                *reinterpret_cast<uint32_t*>(oh + static_cast<long long>(row_b) * p.out_row_stride + col) = pack_f16(yb0, yb1);
+        }
     }
 }
 

@@ -12,7 +12,8 @@ struct AttnParams {
     const __half* v;
     long long row_stride;    // elements between consecutive tokens
     long long batch_stride;  // elements between consecutive bags / tiles
-    __half* out;             // [B, S, H*head_dim], head-major concat
+    void* out;               // [B, S, H*head_dim], head-major concat; fp16, or fp32 (TF32-rounded) if out_f32
+    int out_f32;
     long long out_row_stride;
     long long out_batch_stride;
     int B, S, H;

@@ -35,12 +35,12 @@ void stamp_b200_reset_launch_count(void) { sb::g_launches.store(0, std::memory_o
 
 int stamp_gemm_tn(const void* A, long long lda, const void* W, long long ldw, void* out,
                   long long ldo, int M, int N, int K, const float* bias, const float* gamma,
-                  int act, int store, int bf16, const float* table, long long ldt, int gin,
+                  int act, int store, int dtype, const float* table, long long ldt, int gin,
                   int gout, int goff, void* stream) {
-    if (act < 0 || act > 2 || store < 0 || store > 4) return STAMP_ERR_BAD_ARG;
+    if (act < 0 || act > 2 || store < 0 || store > 4 || dtype < 0 || dtype > 2) return STAMP_ERR_BAD_ARG;
     sb::GemmParams p;
     p.M = M; p.N = N; p.K = K;
-    p.act = act; p.store = store; p.bf16 = bf16;
+    p.act = act; p.store = store; p.bf16 = (dtype == 1); p.tf32 = (dtype == 2);
     p.out = out; p.ldo = ldo;
     p.bias = bias; p.gamma = gamma;
     p.table = table; p.ldt = ldt;
@@ -74,8 +74,8 @@ int stamp_tiles_to_patches(const uint8_t* tiles, void* patches, int B, int img, 
 
 int stamp_attention_fwd(const void* q, const void* k, const void* v, long long row_stride,
                         long long batch_stride, void* out, long long out_row_stride,
-                        long long out_batch_stride, int B, int S, int H, int head_dim,
-                        float scale, const float* coords, const float* slope,
+                        long long out_batch_stride, int out_f32, int B, int S, int H,
+                        int head_dim, float scale, const float* coords, const float* slope,
                         const float* dscale, const uint8_t* mask, int mask_mode, void* stream) {
     if (q == nullptr || k == nullptr || v == nullptr || out == nullptr) return STAMP_ERR_BAD_ARG;
     if (mask != nullptr && mask_mode != 1 && mask_mode != 2) return STAMP_ERR_BAD_ARG;
@@ -84,7 +84,8 @@ int stamp_attention_fwd(const void* q, const void* k, const void* v, long long r
     p.k = static_cast<const __half*>(k);
     p.v = static_cast<const __half*>(v);
     p.row_stride = row_stride; p.batch_stride = batch_stride;
-    p.out = static_cast<__half*>(out);
+    p.out = out;
+    p.out_f32 = out_f32;
     p.out_row_stride = out_row_stride; p.out_batch_stride = out_batch_stride;
     p.B = B; p.S = S; p.H = H;
     p.scale_log2 = scale * 1.4426950408889634f;

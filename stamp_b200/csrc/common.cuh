@@ -145,6 +145,16 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, ui
         : "memory");
 }
 
+__device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread retire
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile(
@@ -211,6 +221,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool bf16, b
            (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// kind::tf32: fp32 storage, a/b_format TF32 = 2, K-major both, fp32 accumulate
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+           (static_cast<uint32_t>(M >> 4) << 24);
+}
+
 // ----------------------------------------------------------------------------
 // legacy tensor path (mma.sync) helpers for the small attention tiles
 // ----------------------------------------------------------------------------
@@ -261,6 +277,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 __device__ __forceinline__ uint32_t pack_16(float a, float b, bool bf16) {
     return bf16 ? pack_bf16(a, b) : pack_f16(a, b);
+}
+
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
 }
 
 // erf with |abs err| < 1.5e-7 (Abramowitz-Stegun 7.1.26): cheap enough to sit in a

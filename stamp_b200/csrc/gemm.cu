@@ -23,16 +23,16 @@ namespace sb {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 64;  // 64 x 2 B = one 128-byte swizzle row
-constexpr int UMMA_K = 16;
+constexpr int BK_BYTES = 128;  // one 128-byte swizzle row of K per tile row: 64 x 16-bit or 32 x tf32
+constexpr int UMMA_K_BYTES = 32;  // K extent of one tcgen05.mma: 16 x 16-bit or 8 x tf32
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 
 template <int BN>
 struct Cfg {
     static constexpr int STAGES = (BN == 256) ? 4 : 6;
-    static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int A_BYTES = BM * BK_BYTES;
+    static constexpr int B_BYTES = BN * BK_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
     static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;
@@ -178,7 +178,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     }
 }
 
-template <int BN>
+template <int BN, bool TF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
@@ -226,6 +226,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int num_m = (p.M + BM - 1) / BM;
     const int num_n = (p.N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
+    constexpr int BK = TF32 ? 32 : 64;  // elements of K per pipeline stage
     const int num_kb = (p.K + BK - 1) / BK;
 
     if (warp == 0) {
@@ -247,7 +248,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // ------------------------------ MMA issuer --------------------------------
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_f16(BM, BN, p.bf16 != 0, false, false);
+            const uint32_t idesc = TF32 ? umma_idesc_tf32(BM, BN) : umma_idesc_f16(BM, BN, p.bf16 != 0, false, false);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -262,11 +263,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t a_desc = umma_desc_k128(smem_u32(sA + stage * C::A_BYTES));
                     const uint64_t b_desc = umma_desc_k128(smem_u32(sB + stage * C::B_BYTES));
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advancing 16 elements (32 B) along K inside the swizzle row: +2 in the
+                    for (int k = 0; k < BK_BYTES / UMMA_K_BYTES; ++k) {
+                        // advancing 32 B along K inside the swizzle row: +2 in the
                         // 16-byte-granular start-address field
-                        umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                                    (kb | k) != 0 ? 1u : 0u);
+                        if constexpr (TF32)
+                            umma_tf32_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else
+                            umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
                     if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
@@ -339,14 +342,18 @@ EncodeTiledFn get_encode_fn() {
 }
 
 int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, long long ld, int box_rows,
-              bool bf16) {
+              int kind /*0 fp16, 1 bf16, 2 fp32(tf32)*/) {
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) return SB_ERR_DRIVER;
     cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    const int esz = (kind == 2) ? 4 : 2;
+    cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * esz};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK_BYTES / esz), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+    const CUtensorMapDataType dt = (kind == 2)   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                   : (kind == 1) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = fn(tm, dt, 2,
                     const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -355,18 +362,18 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, long long ld
 
 int g_num_sms = 0;
 
-template <int BN>
+template <int BN, bool TF32>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int tiles,
            cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(gemm_tn_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg<BN>::SMEM_BYTES) != cudaSuccess)
             return SB_ERR_CUDA;
         configured = true;
     }
     int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_tn_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    gemm_tn_kernel<BN, TF32><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, p);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
@@ -387,7 +394,8 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, const Ge
             cudaStream_t stream) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0 || A == nullptr || B == nullptr || p.out == nullptr)
         return SB_ERR_BAD_ARG;
-    if ((lda % 8) != 0 || (ldb % 8) != 0 || (reinterpret_cast<uintptr_t>(A) & 15) != 0 ||
+    const int ealign = p.tf32 ? 4 : 8;  // 16-byte row pitch
+    if ((lda % ealign) != 0 || (ldb % ealign) != 0 || (reinterpret_cast<uintptr_t>(A) & 15) != 0 ||
         (reinterpret_cast<uintptr_t>(B) & 15) != 0)
         return SB_ERR_BAD_ARG;
     if ((p.store == ST_SWIGLU16 || p.store == ST_GATED16) && (p.N % 2) != 0) return SB_ERR_BAD_ARG;
@@ -400,13 +408,15 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, const Ge
     const int bn = use256 ? 256 : 128;
 
     CUtensorMap tmA, tmB;
-    int rc = make_tmap(&tmA, A, p.M, p.K, lda, BM, p.bf16 != 0);
+    const int kind = p.tf32 ? 2 : (p.bf16 ? 1 : 0);
+    int rc = make_tmap(&tmA, A, p.M, p.K, lda, BM, kind);
     if (rc != SB_OK) return rc;
-    rc = make_tmap(&tmB, B, p.N, p.K, ldb, bn, p.bf16 != 0);
+    rc = make_tmap(&tmB, B, p.N, p.K, ldb, bn, kind);
     if (rc != SB_OK) return rc;
 
-    if (use256) return launch<256>(tmA, tmB, p, tiles256, stream);
-    return launch<128>(tmA, tmB, p, num_m * ((p.N + 127) / 128), stream);
+    const int tiles128 = num_m * ((p.N + 127) / 128);
+    if (p.tf32) return use256 ? launch<256, true>(tmA, tmB, p, tiles256, stream) : launch<128, true>(tmA, tmB, p, tiles128, stream);
+    return use256 ? launch<256, false>(tmA, tmB, p, tiles256, stream) : launch<128, false>(tmA, tmB, p, tiles128, stream);
 }
 
 }  // namespace sb

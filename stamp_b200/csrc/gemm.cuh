@@ -22,7 +22,8 @@ struct GemmParams {
     int M, N, K;
     int act;
     int store;
-    int bf16;            // operands and 16-bit outputs are bf16 instead of fp16
+    int bf16;            // 16-bit operands and 16-bit outputs are bf16 instead of fp16
+    int tf32;            // operands are fp32 read as TF32 (kind::tf32); 16-bit outputs follow bf16
     void* out;           // fp16/bf16 or fp32 matrix
     long long ldo;       // leading dimension of out, elements
     const float* bias;   // [N] or null
@@ -35,7 +36,7 @@ struct GemmParams {
 };
 
 // C[M,N] = A[M,K] . B[N,K]^T, A and B K-major 16-bit, fp32 accumulate in TMEM.
-// lda/ldb in elements (multiples of 8); pointers 16-byte aligned.
+// lda/ldb in elements with a 16-byte row pitch; pointers 16-byte aligned.
 int gemm_tn(const void* A, long long lda, const void* B, long long ldb, const GemmParams& p,
             cudaStream_t stream);
 

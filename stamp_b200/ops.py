@@ -54,15 +54,15 @@ def gemm_tn(
 ) -> Tensor:
     """out = epilogue(a @ w.T).  a [M,K], w [N,K] fp16/bf16 (last dim contiguous)."""
     _require_cuda(a, w, out, bias, gamma, table)
-    if a.dtype != w.dtype or a.dtype not in (torch.float16, torch.bfloat16):
-        raise TypeError("a and w must both be float16 or both bfloat16")
+    if a.dtype != w.dtype or a.dtype not in (torch.float16, torch.bfloat16, torch.float32):
+        raise TypeError("a and w must share one dtype: float16, bfloat16 or float32 (consumed as TF32)")
     if a.dim() != 2 or w.dim() != 2 or a.shape[1] != w.shape[1]:
         raise ValueError(f"shape mismatch: a {tuple(a.shape)} w {tuple(w.shape)}")
     if a.stride(1) != 1 or w.stride(1) != 1 or out.stride(-1) != 1:
         raise ValueError("innermost dimensions must be contiguous")
     M, K = a.shape
     N = w.shape[0]
-    want = torch.float32 if store in (ST_32, ST_RESID32) else a.dtype
+    want = torch.float32 if store in (ST_32, ST_RESID32) else (torch.float16 if a.dtype == torch.float32 else a.dtype)
     if out.dtype != want:
         raise TypeError(f"out must be {want} for store mode {store}")
     _f32(bias, "bias"), _f32(gamma, "gamma")
@@ -72,7 +72,8 @@ def gemm_tn(
         ldt = table.stride(0)
     code = _lib.load().stamp_gemm_tn(
         a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(-2),
-        M, N, K, _ptr(bias), _ptr(gamma), act, store, int(a.dtype == torch.bfloat16),
+        M, N, K, _ptr(bias), _ptr(gamma), act, store,
+        {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}[a.dtype],
         _ptr(table), ldt, gin, gout, goff, _stream(),
     )
     _lib.check(code, "stamp_gemm_tn")
@@ -134,15 +135,21 @@ def tiles_to_patches(tiles: Tensor, patch: int, mean, std, dtype=torch.float16,
 def attention(qkv: Tensor, n_heads: int, *, out: Tensor | None = None, coords: Tensor | None = None,
               slope: Tensor | None = None, mask: Tensor | None = None, mask_mode: int = 1,
               scale: float | None = None) -> Tensor:
-    """Fused attention over a packed fp16 [B, S, 3, H, hd] (= [B, S, 3*H*hd]) projection."""
+    """Fused attention over a packed fp16 [B, S, 3, H, hd] (= [B, S, 3*H*hd]) projection.
+
+    Plain attention returns fp16; the ALiBi variant returns fp32 values rounded to TF32 (the
+    reference's distance term is unscaled and overflows fp16)."""
     _require_cuda(qkv, coords, slope, mask)
     if qkv.dtype != torch.float16 or qkv.dim() != 3 or not qkv.is_contiguous():
         raise TypeError("qkv must be a contiguous float16 [B, S, 3*D] tensor")
     B, S, D3 = qkv.shape
     D = D3 // 3
     hd = D // n_heads
+    out_dtype = torch.float32 if coords is not None else torch.float16
     if out is None:
-        out = torch.empty((B, S, D), dtype=torch.float16, device=qkv.device)
+        out = torch.empty((B, S, D), dtype=out_dtype, device=qkv.device)
+    if out.dtype != out_dtype or not out.is_contiguous():
+        raise TypeError(f"out must be a contiguous {out_dtype} tensor")
     dscale = None
     lib = _lib.load()
     if coords is not None:
@@ -161,7 +168,7 @@ def attention(qkv: Tensor, n_heads: int, *, out: Tensor | None = None, coords: T
     base = qkv.data_ptr()
     code = lib.stamp_attention_fwd(
         base, base + 2 * D, base + 4 * D, D3 * esz, S * D3 * esz, out.data_ptr(), D, S * D,
-        B, S, n_heads, hd, float(scale if scale is not None else 1.0 / math.sqrt(hd)),
+        int(out_dtype == torch.float32), B, S, n_heads, hd, float(scale if scale is not None else 1.0 / math.sqrt(hd)),
         _ptr(coords), _ptr(slope), _ptr(dscale), _ptr(mask), mask_mode, _stream(),
     )
     _lib.check(code, "stamp_attention_fwd")

@@ -35,6 +35,24 @@ def test_gemm_store16(cuda_device, M, N, K, dtype):
     assert (out.float() - ref).abs().max().item() < 0.05 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 512, 512), (4097, 512, 512), (130, 72, 100)])
+def test_gemm_tf32(cuda_device, M, N, K):
+    """kind::tf32 path: fp32 operands pre-rounded to TF32, huge dynamic range (ALiBi outputs)."""
+    from stamp_b200 import ops
+
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g) * 1e5).to(cuda_device)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda_device)
+    # round-to-nearest to 10 explicit mantissa bits
+    rnd = lambda t: ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    a, w = rnd(a), rnd(w)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    x = torch.zeros(M, N, device=cuda_device)
+    ops.gemm_tn(a, w, out=x, bias=bias, store=ops.ST_RESID32)
+    ref = (a.double() @ w.double().T + bias.double())
+    assert _rel(x, ref) < 1e-5
+
+
 def test_gemm_epilogues(cuda_device):
     from stamp_b200 import ops
 
@@ -180,7 +198,7 @@ def test_attention_alibi(cuda_device, S, masked):
         mask[:, 0] = False
     out = ops.attention(qkv, H, coords=coords, slope=slope, mask=mask, mask_mode=1)
     ref = _attn_ref(qkv, H, coords, slope, mask, 1)
-    assert torch.isfinite(out).all()
+    assert out.dtype == torch.float32 and torch.isfinite(out).all()
     # the ALiBi term dominates (|out| ~ 1e5): fp16 Dist operand (2^-11 rel) + fp16 V + fp16 output
     assert _rel(out.float(), ref) < 1e-3
 
