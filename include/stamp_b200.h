@@ -105,6 +105,53 @@ int stamp_attention_fwd(const void* q, const void* k, const void* v, long long r
 int stamp_alibi_dist_scale(const float* coords, const float* slope, int B, int S, int H,
                            float* dscale, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Tile-encoder ViT forward for one batch of uint8 tiles (UNI ViT-L/16, Virchow2 ViT-H/14, ...).
+ * replaces: `model(tiles.to(device))` at src/stamp/preprocessing/__init__.py:322-327 == timm
+ *   VisionTransformer.forward as built in src/stamp/preprocessing/extractor/uni.py:26-31 and
+ *   virchow2.py:24-42 (incl. the wrapper's [:, 0]) together with Extractor.transform's
+ *   ToTensor+Normalize.  Output: fp16 class-token features [B, dim] (the reference's `.half()`).
+ * All structs are HOST structs holding DEVICE pointers; 16-bit weights are fp16, K-major [out,in].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int img, patch, dim, depth, heads;
+    int mlp_hidden;   /* fc1 output width (x1|x2 packed width for SwiGLU) */
+    int mlp_kind;     /* 0: fc1-GELU(erf)-fc2   1: SwiGLUPacked (fc1 rows interleaved x1,x2) */
+    int reg_tokens;
+    int kpad;         /* patch vector length 3*patch^2 rounded up to a multiple of 8 */
+    float ln_eps;
+    float mean[3], std[3];
+} StampVitConfig;
+
+typedef struct {
+    const void* patch_w;   /* fp16 [dim, kpad], Conv2d weight flattened (c,ky,kx), zero padded */
+    const float* patch_b;  /* [dim] */
+    const float* prefix;   /* [1+reg_tokens, dim]: cat(cls_token, reg_token) + pos_embed[:1+reg] */
+    const float* pos;      /* [n_patches, dim]: pos_embed rows of the patch tokens */
+    const float* norm_w;   /* final LayerNorm */
+    const float* norm_b;
+} StampVitWeights;
+
+typedef struct {
+    const float *ln1_w, *ln1_b;
+    const void* qkv_w;  const float* qkv_b;   /* [3*dim, dim] */
+    const void* proj_w; const float* proj_b;  /* [dim, dim] */
+    const float* ls1;                         /* LayerScale gamma or NULL */
+    const float *ln2_w, *ln2_b;
+    const void* fc1_w;  const float* fc1_b;   /* [mlp_hidden, dim] */
+    const void* fc2_w;  const float* fc2_b;   /* [dim, mlp_hidden (/2 for SwiGLU)] */
+    const float* ls2;
+} StampVitBlock;
+
+/* bytes of 256-byte-aligned device workspace stamp_vit_forward needs for a batch of B tiles
+ * (0 = invalid config) */
+size_t stamp_vit_workspace_bytes(const StampVitConfig* cfg, int B);
+
+int stamp_vit_forward(const StampVitConfig* cfg, const StampVitWeights* w,
+                      const StampVitBlock* blocks /* [depth] */, const uint8_t* tiles /* [B,img,img,3] */,
+                      void* feats16 /* [B, dim] */, int B, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,76 @@
+"""Tile-encoder parity on the GPU: stamp_vit_forward (through the TileEncoder module) against the
+fp32 CPU oracle on identical seeded synthetic tiles and weights.
+
+Tolerance (north_star): feature vectors within 1e-3 relative, per tile: ||f - f_ref|| / ||f_ref||."""
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _per_tile_rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm(dim=1) / b.norm(dim=1)).max().item()
+
+
+def _run(cfg_o, n_tiles, device, seed=3, max_batch=256):
+    from oracle import vit_oracle as vo
+    from stamp_b200.vit import TileEncoder, VitArch
+
+    w = vo.make_weights(cfg_o, seed=1234)
+    tiles = vo.synthetic_tiles(n_tiles, seed=seed, img=cfg_o.img)
+    with torch.no_grad():
+        ref = vo.forward(w, cfg_o, tiles)
+    arch = VitArch(cfg_o.name, img=cfg_o.img, patch=cfg_o.patch, dim=cfg_o.dim, depth=cfg_o.depth,
+                   heads=cfg_o.heads, mlp_hidden=cfg_o.mlp_hidden, mlp=cfg_o.mlp,
+                   reg_tokens=cfg_o.reg_tokens, ln_eps=cfg_o.ln_eps)
+    enc = TileEncoder(arch, w, max_batch=max_batch).to(device).eval()
+    out = enc(tiles.to(device))
+    assert out.dtype == torch.float16 and out.shape == ref.shape
+    assert torch.isfinite(out).all()
+    return _per_tile_rel(out.float(), ref)
+
+
+@pytest.mark.parametrize("mlp,reg,patch", [("gelu", 0, 16), ("swiglu", 4, 14), ("gelu", 2, 14)])
+def test_tiny_vit_matches_oracle(cuda_device, mlp, reg, patch):
+    from oracle import vit_oracle as vo
+
+    err = _run(vo.tiny_config(mlp=mlp, reg_tokens=reg, patch=patch, depth=3), 5, cuda_device)
+    assert err < 1e-3, err
+
+
+def test_tiny_vit_batch_chunking(cuda_device):
+    from oracle import vit_oracle as vo
+
+    err = _run(vo.tiny_config(depth=2), 7, cuda_device, max_batch=3)
+    assert err < 1e-3, err
+
+
+def test_uni_vit_l16_matches_oracle(cuda_device):
+    """Full UNI architecture (ViT-L/16, 24 blocks) on 4 synthetic H&E-like tiles."""
+    from oracle import vit_oracle as vo
+
+    err = _run(vo.UNI, 4, cuda_device)
+    print("ViT-L/16 max per-tile relative error:", err)
+    assert err < 1e-3, err
+
+
+def test_virchow2_vit_h14_matches_oracle(cuda_device):
+    """Full Virchow2 architecture (ViT-H/14, 32 blocks, SwiGLU, 4 register tokens) on 2 tiles."""
+    from oracle import vit_oracle as vo
+
+    err = _run(vo.VIRCHOW2, 2, cuda_device)
+    print("ViT-H/14 max per-tile relative error:", err)
+    assert err < 1e-3, err
+
+
+def test_tile_encoder_refuses_cpu():
+    from oracle import vit_oracle as vo
+    from stamp_b200.vit import TileEncoder, VitArch
+
+    cfg = vo.tiny_config(depth=1)
+    enc = TileEncoder(VitArch("t", dim=cfg.dim, depth=1, heads=cfg.heads, mlp_hidden=cfg.mlp_hidden),
+                      vo.make_weights(cfg))
+    with pytest.raises(RuntimeError):
+        enc(torch.zeros(1, 224, 224, 3, dtype=torch.uint8))
