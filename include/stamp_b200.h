@@ -40,6 +40,11 @@ const char* stamp_b200_strerror(int code);
 /* kernels launched by this library since load / since the last reset (bench.py "gpu_launches") */
 long long stamp_b200_launch_count(void);
 void stamp_b200_reset_launch_count(void);
+/* Optional CUDA-event timing of the library's own launches, on the launching stream, by category
+ * (0 GEMM, 1 attention, 2 row ops, 3 Macenko, 4 pooling/top-k).  summary() synchronises, fills
+ * host arrays ms[c] / work[c] (algorithmic FLOPs for 0-1, bytes otherwise) / count[c], clears. */
+void stamp_b200_profile_enable(int on);
+int stamp_b200_profile_summary(double* host_ms, double* host_work, long long* host_count, int ncat);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense layers: C[M,N] = epilogue(A[M,K] . W[N,K]^T), tcgen05/TMEM, TMA-fed.
@@ -151,6 +156,50 @@ int stamp_vit_forward(const StampVitConfig* cfg, const StampVitWeights* w,
                       const StampVitBlock* blocks /* [depth] */, const uint8_t* tiles /* [B,img,img,3] */,
                       void* feats16 /* [B, dim] */, int B, void* workspace, size_t workspace_bytes,
                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ALiBi Transformer-MIL aggregator forward (inference) for a batch of feature bags.
+ * replaces: VisionTransformer.forward, src/stamp/modeling/models/vision_tranformer.py:332-384 and
+ *   everything it calls (:15-295), as used by LitTileClassifier.predict_step/validation_step
+ *   (src/stamp/modeling/models/__init__.py:288-313), deploy._predict (src/stamp/modeling/deploy.py:390-456)
+ *   and heatmaps_ (src/stamp/heatmaps/__init__.py:392,419).
+ * bags fp32 [B,N,F], coords fp32 [B,N,2], mask uint8 [B,N] (1 = masked tile) or NULL,
+ * logits fp32 [B,C].  mask == NULL takes the reference's mask=None branch (padding tiles attend and
+ * are attended, ALiBi applies to the class token's (0,0) coordinate); a mask reproduces :359-379.
+ * HOST structs holding DEVICE pointers.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int dim_input, dim_model, n_layers, n_heads, dim_ff, dim_output;
+    int use_alibi;   /* 1: MultiHeadALiBi, 0: nn.MultiheadAttention */
+} StampMilConfig;
+
+typedef struct {
+    const void* proj_w;          /* fp16 [dim_model, dim_input]   project_features.0.weight */
+    const float* proj_b;
+    const float* class_token;    /* [dim_model] */
+    const float* norm_w;         /* transformer.norm */
+    const float* norm_b;
+    const float* head_w;         /* fp32 [dim_output, dim_model]  mlp_head.0 */
+    const float* head_b;
+} StampMilWeights;
+
+typedef struct {
+    const float *ln1_w, *ln1_b;              /* layers.l.0.norm */
+    const void* qkv_w; const float* qkv_b;   /* fp16 [3d, d]: rows = q heads | k heads | v heads */
+    const float* slope;                      /* [H] bias_scale_h / running_mean_h (ALiBi only) */
+    const void* fc_w;  const float* fc_b;    /* ALiBi: fp32 [d,d] rounded to TF32 (mhsa.fc);
+                                                else fp16 [d,d] (mhsa.out_proj) */
+    const float *ln2_w, *ln2_b;              /* layers.l.1.0 */
+    const void* ff1_w; const float* ff1_b;   /* fp16 [ff, d]  layers.l.1.1 */
+    const void* ff2_w; const float* ff2_b;   /* fp16 [d, ff]  layers.l.1.4 */
+} StampMilLayer;
+
+size_t stamp_mil_workspace_bytes(const StampMilConfig* cfg, int B, int N);
+
+int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w,
+                      const StampMilLayer* layers /* [n_layers] */, const float* bags,
+                      const float* coords, const uint8_t* mask, float* logits, int B, int N,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -147,7 +147,11 @@ def forward(sd: dict[str, Tensor], bags: Tensor, coords: Tensor, mask: Tensor | 
             q, k, v = qkv.view(B, S, 3, n_heads, hd).permute(2, 0, 3, 1, 4)
             logits = q @ k.transpose(-1, -2) / math.sqrt(hd)
             if attn_mask is not None:
-                logits = logits.masked_fill(attn_mask[:, None], float("-inf"))
+                # Reference quirk kept on purpose (vision_tranformer.py:222-226): the [B,S,S] mask is
+                # expanded with .repeat(H,1,1) -> rows ordered (head, bag), but nn.MultiheadAttention
+                # reads its [B*H,S,S] mask as (bag, head): bag b / head h gets the mask of bag (b*H+h) % B.
+                idx = (torch.arange(B)[:, None] * n_heads + torch.arange(n_heads)[None, :]) % B
+                logits = logits.masked_fill(attn_mask[idx], float("-inf"))
             o = (torch.softmax(logits, -1) @ v).permute(0, 2, 1, 3).reshape(B, S, d)
             att = F.linear(o, sd[p + "0.mhsa.out_proj.weight"], sd[p + "0.mhsa.out_proj.bias"])
         x = att + x

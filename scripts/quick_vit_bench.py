@@ -1,6 +1,10 @@
 """Quick device-resident tiles/s probe for the ViT tile encoder (development aid, not bench.py)."""
 import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
+
 from stamp_b200.vit import TileEncoder, UNI_ARCH, VIRCHOW2_ARCH, random_state_dict
 
 arch = VIRCHOW2_ARCH if "virchow2" in sys.argv else UNI_ARCH

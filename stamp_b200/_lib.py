@@ -22,6 +22,9 @@ SIGNATURES: dict[str, tuple] = {
     "stamp_b200_strerror": (C.c_char_p, [c_int]),
     "stamp_b200_launch_count": (c_ll, []),
     "stamp_b200_reset_launch_count": (None, []),
+    "stamp_b200_profile_enable": (None, [c_int]),
+    "stamp_b200_profile_summary": (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                           C.POINTER(C.c_longlong), c_int]),
     "stamp_gemm_tn": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_int,
                               c_int, c_void_p]),
@@ -77,3 +80,19 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     load().stamp_b200_reset_launch_count()
+
+
+PROFILE_CATEGORIES = ("gemm", "attention", "rowops", "macenko", "pool")
+
+
+def profile_enable(on: bool) -> None:
+    load().stamp_b200_profile_enable(int(on))
+
+
+def profile_summary() -> dict[str, dict[str, float]]:
+    """Per-category {ms, work, count} of the launches recorded since the last summary."""
+    n = len(PROFILE_CATEGORIES)
+    ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_longlong * n)()
+    load().stamp_b200_profile_summary(ms, work, cnt, n)
+    return {name: {"ms": ms[i], "work": work[i], "count": int(cnt[i])}
+            for i, name in enumerate(PROFILE_CATEGORIES)}

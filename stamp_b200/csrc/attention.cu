@@ -72,16 +72,20 @@ flash_attn_kernel(const AttnParams p) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
-    const int b = blockIdx.y / p.H, h = blockIdx.y % p.H;
-    const int q0 = blockIdx.x * BQ;
+    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+    const int q0 = blockIdx.y * BQ;
     const int S = p.S;
 
     const __half* qb = p.q + b * p.batch_stride + h * HD;
     const __half* kb = p.k + b * p.batch_stride + h * HD;
     const __half* vb = p.v + b * p.batch_stride + h * HD;
     const float2* cb = ALIBI ? reinterpret_cast<const float2*>(p.coords) + static_cast<long long>(b) * S : nullptr;
-    const uint8_t* mb = (p.mask != nullptr) ? p.mask + static_cast<long long>(b) * S : nullptr;
-    const int mask_mode = (mb != nullptr) ? p.mask_mode : 0;
+    const int mask_mode = (p.mask != nullptr) ? p.mask_mode : 0;
+    // mask_mode 2 keeps a reference quirk (vision_tranformer.py:222-226): the mask is expanded with
+    // .repeat(H,1,1) (rows ordered head-major) but nn.MultiheadAttention indexes it bag-major, so
+    // (bag b, head h) uses the mask row of bag (b*H + h) % B.
+    const int mrow = (mask_mode == 2) ? (b * p.H + h) % p.B : b;
+    const uint8_t* mb = (p.mask != nullptr) ? p.mask + static_cast<long long>(mrow) * S : nullptr;
 
     const int ntiles = (S + BKV - 1) / BKV;
 
@@ -373,7 +377,9 @@ int launch_attn(const AttnParams& p, cudaStream_t stream) {
             return SB_ERR_CUDA;
         configured = true;
     }
-    dim3 grid((p.S + BQ - 1) / BQ, p.B * p.H);
+    dim3 grid(p.B * p.H, (p.S + BQ - 1) / BQ);  // (bag, head) on x: heatmaps call with B = n_tiles
+    // algorithmic FLOPs of the reference math: QK^T and one [S,S]x[S,hd] product per head
+    ProfScope prof(PROF_ATTN, 4.0 * p.B * p.H * static_cast<double>(p.S) * p.S * HD, stream);
     flash_attn_kernel<HD, ALIBI><<<grid, ATT_THREADS, bytes, stream>>>(p);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
@@ -383,7 +389,7 @@ int launch_attn(const AttnParams& p, cudaStream_t stream) {
 
 int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream) {
     if (p.B <= 0 || p.S <= 0 || p.H <= 0 || p.q == nullptr || p.out == nullptr) return SB_ERR_BAD_ARG;
-    if (static_cast<long long>(p.B) * p.H > 65535) return SB_ERR_UNSUPPORTED;
+    if (static_cast<long long>(p.B) * p.H > 2147483647LL || (p.S + BQ - 1) / BQ > 65535) return SB_ERR_UNSUPPORTED;
     if ((p.row_stride % 8) != 0 || (p.batch_stride % 8) != 0 || (p.out_row_stride % 2) != 0)
         return SB_ERR_BAD_ARG;
     const bool alibi = p.coords != nullptr;

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "profile.cuh"
+
 namespace sb {
 
 // ----------------------------------------------------------------------------

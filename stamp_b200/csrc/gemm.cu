@@ -373,6 +373,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
         configured = true;
     }
     int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    ProfScope prof(PROF_GEMM, 2.0 * p.M * static_cast<double>(p.N) * p.K, stream);
     gemm_tn_kernel<BN, TF32><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, p);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;

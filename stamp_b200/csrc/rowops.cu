@@ -185,6 +185,7 @@ int layernorm(const float* x, long long ldx, const float* w, const float* b, voi
         return SB_ERR_BAD_ARG;
     const int threads = 256;
     const int blocks = (rows * 32 + threads - 1) / threads;
+    ProfScope prof(PROF_ROWOP, static_cast<double>(rows) * cols * (4.0 + (out_kind == 2 ? 4.0 : 2.0)), stream);
     if (cols <= 512)
         layernorm_kernel<4><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, ldo, rows, cols, eps, out_kind);
     else if (cols <= 1024)

@@ -1,0 +1,211 @@
+"""Drop-in MIL backbone: STAMP's ALiBi ``VisionTransformer`` with its forward running in
+``libstamp_b200.so``.
+
+Contract mirrored from the reference (src/stamp/modeling/models/vision_tranformer.py:298-384 and
+SURVEY.md 8b):
+
+* constructor ``VisionTransformer(*, dim_output, dim_input, dim_model, n_layers, n_heads,
+  dim_feedforward, dropout, use_alibi)`` -- ``Base._build_backbone`` filters Lightning kwargs by this
+  signature (src/stamp/modeling/models/__init__.py:112-131);
+* ``forward(bags [B,N,F], *, coords [B,N,2], mask [B,N] | None) -> [B,C]``;
+* identical parameter / buffer names, shapes and initialisation, so ``.ckpt`` files written by the
+  reference load here and vice versa (``LitX.load_from_checkpoint(model_class=VisionTransformer)``,
+  src/stamp/modeling/deploy.py:49-58).
+
+The sub-modules below only hold parameters under the reference's names; the arithmetic is one call
+to ``stamp_mil_forward`` (per-head Q/K/V Linears are packed into one [3d, d] GEMM operand, see
+``_pack``).  Inference only in this round: calling it with autograd enabled on trainable
+parameters raises (the backward kernels are SURVEY.md 8f row N1).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+
+
+class StampMilConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("dim_input", "dim_model", "n_layers", "n_heads", "dim_ff",
+                                       "dim_output", "use_alibi")]
+
+
+class StampMilWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("proj_w", "proj_b", "class_token", "norm_w", "norm_b",
+                                          "head_w", "head_b")]
+
+
+class StampMilLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "slope", "fc_w", "fc_b",
+                                          "ln2_w", "ln2_b", "ff1_w", "ff1_b", "ff2_w", "ff2_b")]
+
+
+def _bind() -> C.CDLL:
+    lib = _lib.load()
+    if not getattr(lib, "_mil_bound", False):
+        lib.stamp_mil_workspace_bytes.restype = C.c_size_t
+        lib.stamp_mil_workspace_bytes.argtypes = [C.POINTER(StampMilConfig), C.c_int, C.c_int]
+        lib.stamp_mil_forward.restype = C.c_int
+        lib.stamp_mil_forward.argtypes = [C.POINTER(StampMilConfig), C.POINTER(StampMilWeights),
+                                          C.POINTER(StampMilLayer), C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib._mil_bound = True
+    return lib
+
+
+def round_to_tf32(t: Tensor) -> Tensor:
+    """Round-to-nearest onto TF32's 10 explicit mantissa bits (the tensor core would truncate)."""
+    i = t.detach().float().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+# ---- parameter containers named exactly like the reference's modules ---------------------------
+class _RunningMeanScaler(nn.Module):
+    def __init__(self) -> None:
+        super().__init__()
+        self.running_mean = nn.Buffer(torch.ones(1))
+        self.items_so_far = nn.Buffer(torch.ones(1))
+
+
+class _ALiBi(nn.Module):
+    def __init__(self) -> None:
+        super().__init__()
+        self.scale_distance = _RunningMeanScaler()
+        self.bias_scale = nn.Parameter(torch.rand(1))
+
+
+class MultiHeadALiBi(nn.Module):
+    def __init__(self, *, embed_dim: int, num_heads: int) -> None:
+        super().__init__()
+        if embed_dim % num_heads != 0:
+            raise ValueError(f"{embed_dim=} has to be divisible by {num_heads=}")
+        hd = embed_dim // num_heads
+        mk = lambda: nn.ModuleList([nn.Linear(embed_dim, hd) for _ in range(num_heads)])
+        self.query_encoders, self.key_encoders, self.value_encoders = mk(), mk(), mk()
+        self.attentions = nn.ModuleList([_ALiBi() for _ in range(num_heads)])
+        self.fc = nn.Linear(embed_dim, embed_dim)
+
+
+class SelfAttention(nn.Module):
+    def __init__(self, *, dim: int, num_heads: int, dropout: float, use_alibi: bool) -> None:
+        super().__init__()
+        self.heads = num_heads
+        self.norm = nn.LayerNorm(dim)
+        self.mhsa = (MultiHeadALiBi(embed_dim=dim, num_heads=num_heads) if use_alibi
+                     else nn.MultiheadAttention(dim, num_heads, dropout, batch_first=True))
+
+
+def feed_forward(dim: int, hidden_dim: int, dropout: float = 0.5) -> nn.Sequential:
+    return nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout),
+                         nn.Linear(hidden_dim, dim), nn.Dropout(dropout))
+
+
+class Transformer(nn.Module):
+    def __init__(self, *, dim: int, depth: int, heads: int, mlp_dim: int, dropout: float,
+                 use_alibi: bool) -> None:
+        super().__init__()
+        self.depth = depth
+        self.layers = nn.ModuleList([
+            nn.ModuleList([SelfAttention(dim=dim, num_heads=heads, dropout=dropout, use_alibi=use_alibi),
+                           feed_forward(dim, mlp_dim)])
+            for _ in range(depth)])
+        self.norm = nn.LayerNorm(dim)
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, *, dim_output: int, dim_input: int, dim_model: int, n_layers: int, n_heads: int,
+                 dim_feedforward: int, dropout: float, use_alibi: bool) -> None:
+        super().__init__()
+        self.class_token = nn.Parameter(torch.randn(dim_model))
+        self.project_features = nn.Sequential(nn.Linear(dim_input, dim_model, bias=True), nn.GELU(),
+                                              nn.Dropout(dropout))
+        self.transformer = Transformer(dim=dim_model, depth=n_layers, heads=n_heads,
+                                       mlp_dim=dim_feedforward, dropout=dropout, use_alibi=use_alibi)
+        self.mlp_head = nn.Sequential(nn.Linear(dim_model, dim_output))
+        self._cfg = dict(dim_input=dim_input, dim_model=dim_model, n_layers=n_layers, n_heads=n_heads,
+                         dim_ff=dim_feedforward, dim_output=dim_output, use_alibi=int(use_alibi))
+        self._packed = None       # (key, tensors kept alive, cfg, weights, layers)
+        self._workspace: Tensor | None = None
+
+    # ---- weight packing: reference layout -> GEMM operands (cached until a parameter changes) ----
+    def _pack_key(self):
+        ps = list(self.parameters()) + list(self.buffers())
+        return (str(ps[0].device), tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
+
+    def _pack(self):
+        key = self._pack_key()
+        if self._packed is not None and self._packed[0] == key:
+            return self._packed
+        keep: list[Tensor] = []
+
+        def f32(t: Tensor) -> int:
+            t = t.detach().float().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def f16(t: Tensor) -> int:
+            t = t.detach().half().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        cfg = StampMilConfig(**self._cfg)
+        use_alibi = bool(self._cfg["use_alibi"])
+        w = StampMilWeights(f16(self.project_features[0].weight), f32(self.project_features[0].bias),
+                            f32(self.class_token), f32(self.transformer.norm.weight),
+                            f32(self.transformer.norm.bias), f32(self.mlp_head[0].weight),
+                            f32(self.mlp_head[0].bias))
+        layers = (StampMilLayer * max(1, self._cfg["n_layers"]))()
+        for i, (att, ff) in enumerate(self.transformer.layers):
+            m = att.mhsa
+            if use_alibi:
+                qkv_w = torch.cat([e.weight for grp in (m.query_encoders, m.key_encoders, m.value_encoders) for e in grp])
+                qkv_b = torch.cat([e.bias for grp in (m.query_encoders, m.key_encoders, m.value_encoders) for e in grp])
+                slope = torch.cat([a.bias_scale / a.scale_distance.running_mean for a in m.attentions])
+                fc_w, fc_b, slope_p = f32(round_to_tf32(m.fc.weight)), f32(m.fc.bias), f32(slope)
+            else:
+                qkv_w, qkv_b = m.in_proj_weight, m.in_proj_bias
+                fc_w, fc_b, slope_p = f16(m.out_proj.weight), f32(m.out_proj.bias), None
+            layers[i] = StampMilLayer(f32(att.norm.weight), f32(att.norm.bias), f16(qkv_w), f32(qkv_b),
+                                      slope_p, fc_w, fc_b, f32(ff[0].weight), f32(ff[0].bias),
+                                      f16(ff[1].weight), f32(ff[1].bias), f16(ff[4].weight), f32(ff[4].bias))
+        self._packed = (key, keep, cfg, w, layers)
+        return self._packed
+
+    def forward(self, bags: Tensor, *, coords: Tensor, mask: Tensor | None) -> Tensor:
+        if bags.dim() != 3 or coords.dim() != 3 or coords.shape[:2] != bags.shape[:2] or coords.shape[2] != 2:
+            raise TypeError(f"expected bags [B,N,F] and coords [B,N,2], got {tuple(bags.shape)} / {tuple(coords.shape)}")
+        if not bags.is_floating_point() or not coords.is_floating_point():
+            raise TypeError("bags and coords must be floating point tensors")
+        if mask is not None and (mask.dtype != torch.bool or mask.shape != bags.shape[:2]):
+            raise TypeError("mask must be a bool tensor [B,N] or None")
+        if bags.shape[2] != self._cfg["dim_input"]:
+            raise ValueError(f"bags have {bags.shape[2]} features, model expects {self._cfg['dim_input']}")
+        if not bags.is_cuda or not self.class_token.is_cuda:
+            raise RuntimeError("stamp_b200 VisionTransformer runs on a CUDA device only (no CPU fallback)")
+        if torch.is_grad_enabled() and (bags.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError(
+                "the B200 MIL path is forward-only in this round: wrap the call in torch.no_grad() / "
+                "inference_mode() (validation, predict, deploy); training needs the backward kernels")
+        lib = _bind()
+        _, _, cfg, w, layers = self._pack()
+        B, N, _ = bags.shape
+        dev = bags.device
+        bags32 = bags.detach().float().contiguous()
+        coords32 = coords.detach().float().contiguous()
+        mask8 = mask.to(torch.uint8).contiguous() if mask is not None else None
+        logits = torch.empty((B, self._cfg["dim_output"]), dtype=torch.float32, device=dev)
+        need = lib.stamp_mil_workspace_bytes(C.byref(cfg), B, N)
+        if need == 0:
+            raise ValueError("unsupported MIL configuration for the sm_100a kernels "
+                             "(dims must be multiples of 8, head dim 32 or 64)")
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        code = lib.stamp_mil_forward(C.byref(cfg), C.byref(w), layers, bags32.data_ptr(), coords32.data_ptr(),
+                                     None if mask8 is None else mask8.data_ptr(), logits.data_ptr(), B, N,
+                                     self._workspace.data_ptr(), self._workspace.numel(),
+                                     torch.cuda.current_stream().cuda_stream)
+        _lib.check(code, "stamp_mil_forward")
+        return logits.to(bags.dtype)

@@ -151,7 +151,9 @@ def _attn_ref(qkv, H, coords=None, slope=None, mask=None, mask_mode=1):
         attn_mask[:, 1:, 0] = True
         attn_mask = attn_mask[:, None]
         if mask_mode == 2:
-            logits = logits.masked_fill(attn_mask, float("-inf"))
+            # reference quirk: (bag b, head h) uses the mask of bag (b*H + h) % B (see attention.cu)
+            idx = (torch.arange(B, device=qkv.device)[:, None] * H + torch.arange(H, device=qkv.device)[None, :]) % B
+            logits = logits.masked_fill(attn_mask[:, 0][idx], float("-inf"))
     w = torch.softmax(logits, -1)
     if coords is not None:
         c = coords.double()
