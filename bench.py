@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- tiles/sec of the UNI ViT-L/16 tile-feature-extraction hot path (BASELINE.json
+configs[1]: 1 x B200, synthetic 10k-tile slide) plus MIL slide predictions/sec, next to the
+reference's CPU path timed on the box's host cores.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # reference CPU path (oracle port)
+
+A "step" is one pass of the hot path over one synthetic 10,000-tile slide per GPU (uint8
+[10000,224,224,3], 1.5 GB: larger than L2, so no explicit flush between steps).
+  value : whole-job tiles/s with the slide resident in HBM (uint8 -> normalise -> ViT-L/16 -> fp16 feats)
+  e2e   : same metric through the public API (Extractor model + extract_slide_features) from
+          pinned HOST uint8 tiles to HOST fp16 features, copies inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "tiles/sec (ViT-L/16 224px) + MIL slides/sec"
+WORKLOAD = "UNI ViT-L/16 tile feature extraction, synthetic 10k-tile slide per GPU (BASELINE configs[1])"
+SLIDE_TILES = 10_000
+FLOPS_PER_TILE = 123.107e9  # SURVEY.md 8a row a4 / VitArch.flops_per_tile()
+MIL_FLOPS_PER_BAG = 98.8e9  # SURVEY.md 8d, 4096 x 1024 bag, reference math
+
+
+def load_peaks() -> tuple[dict, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int) -> None:
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self) -> None:
+        assert self.proc is not None and self.proc.stdout is not None
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference's CPU path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_vit_tiles_per_s(sample_tiles: int, reps: int, warm: int) -> tuple[float, int, float]:
+    import torch
+
+    from oracle import vit_oracle as vo
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    w = vo.make_weights(vo.UNI)
+    tiles = vo.synthetic_tiles(sample_tiles, seed=0)
+    with torch.inference_mode():
+        for _ in range(warm):
+            vo.forward(w, vo.UNI, tiles[: max(1, sample_tiles // 4)])
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            vo.forward(w, vo.UNI, tiles).half()
+        dt = time.perf_counter() - t0
+    return sample_tiles * reps / dt, torch.get_num_threads(), dt
+
+
+def cpu_mil_slides_per_s(n_tiles: int, reps: int) -> float:
+    import torch
+
+    from oracle import mil_oracle
+
+    sd = mil_oracle.init_state_dict(dim_input=1024, dim_output=2, seed=0)
+    bags, coords = mil_oracle.synthetic_bag(n_tiles, 1024, seed=0)
+    with torch.inference_mode():
+        mil_oracle.forward(sd, bags[:, :256], coords[:, :256], None)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            mil_oracle.forward(sd, bags, coords, None)
+        dt = time.perf_counter() - t0
+    return reps / dt
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 16
+    tps, cores, dt = cpu_vit_tiles_per_s(sample, reps=args.steps, warm=min(args.warmup, 2))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": tps, "unit": "tiles/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": f"{sample} tiles per step"},
+        "cpu_baseline": {"value": tps, "unit": "tiles/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} synthetic tiles x {args.steps} steps, ViT-L/16 fp32 oracle "
+                                   "port of the timm path (timm is not installable offline)"},
+        "e2e": {"value": tps, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this framework
+# ------------------------------------------------------------------------------------------------
+def run_b200(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from stamp_b200 import _lib
+    from stamp_b200.extractor import extract_slide_features, uni
+    from stamp_b200.mil import VisionTransformer
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- workload: one synthetic 10k-tile slide per GPU (slides shard one per GPU, no collective)
+    ext = uni(weights="random", max_batch=args.batch)
+    model = ext.model.to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    tiles_dev = torch.randint(0, 256, (args.slide_tiles, 224, 224, 3), dtype=torch.uint8, device=dev, generator=g)
+
+    def step_device():
+        return model(tiles_dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = _lib.launch_count()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    value = world * args.slide_tiles * args.steps / (ms_total * 1e-3)
+
+    # ---- dominant kernel (tcgen05 GEMM): CUDA events around every launch of one extra step
+    _lib.profile_enable(True)
+    step_device()
+    prof = _lib.profile_summary()
+    _lib.profile_enable(False)
+    peaks, peak_src = load_peaks()
+    gemm = prof["gemm"]
+    gemm_tflops = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    roofline = {
+        "bound": "tensor", "kernel": "gemm_tn_kernel (tcgen05, all dense layers)",
+        "achieved": gemm_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tflops / peak_tf,
+        "peak_source": f"bf16_tflops_sustained, {peak_src}",
+        "avg_launch_us": gemm["ms"] * 1e3 / max(1, gemm["count"]), "launches_per_step": gemm["count"],
+        "flops_per_launch": gemm["work"] / max(1, gemm["count"]),
+        "kernel_share_of_step": {k: v["ms"] / tot_ms for k, v in prof.items() if v["count"]},
+        "whole_step_frac": (value / world) * FLOPS_PER_TILE / 1e12 / peak_tf,
+        "traffic": None,
+    }
+    traffic_file = ROOT / "profiles" / "gemm_traffic.json"
+    if traffic_file.exists():
+        roofline["traffic"] = json.loads(traffic_file.read_text())
+
+    # ---- end to end through the public API: pinned host tiles -> host fp16 features
+    tiles_host = tiles_dev.cpu().pin_memory()
+    del tiles_dev
+    torch.cuda.empty_cache()
+    extract_slide_features(ext, tiles_host, dev, batch_size=args.batch)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        feats = extract_slide_features(ext, tiles_host, dev, batch_size=args.batch)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e = {"value": world * args.slide_tiles * args.steps / (e2e_ms * 1e-3), "unit": "tiles/s",
+           "h2d_bytes_per_step": tiles_host.numel(), "d2h_bytes_per_step": feats.numel() * 2}
+    del tiles_host
+
+    # ---- MIL slide predictions / s (deploy path: batch 1, all tiles, ALiBi, 4096 x 1024 bags)
+    mil_out = None
+    if not args.skip_mil:
+        n_bags, n_tiles = 32, 4096
+        mil = VisionTransformer(dim_output=2, dim_input=1024, dim_model=512, n_layers=2, n_heads=8,
+                                dim_feedforward=512, dropout=0.25, use_alibi=True).to(dev).eval()
+        gb = torch.Generator(device=dev).manual_seed(7 + rank)
+        bags = torch.randn(n_bags, n_tiles, 1024, device=dev, generator=gb).half().float()
+        coords = torch.randint(0, 100, (n_bags, n_tiles, 2), device=dev, generator=gb).float() * 256.0
+        bags_host, coords_host = bags.cpu().pin_memory(), coords.cpu().pin_memory()
+
+        def mil_step_device():
+            with torch.inference_mode():
+                for i in range(n_bags):
+                    mil(bags[i:i + 1], coords=coords[i:i + 1], mask=None)
+
+        def mil_step_e2e():
+            out = []
+            with torch.inference_mode():
+                for i in range(n_bags):
+                    b = bags_host[i:i + 1].to(dev, non_blocking=True)
+                    c = coords_host[i:i + 1].to(dev, non_blocking=True)
+                    out.append(torch.softmax(mil(b, coords=c, mask=None), 1).cpu())
+            return out
+
+        res = {}
+        for name, fn in (("value", mil_step_device), ("e2e", mil_step_e2e)):
+            fn()
+            barrier()
+            e0.record()
+            for _ in range(2):
+                fn()
+            e1.record()
+            barrier()
+            res[name] = world * n_bags * 2 / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+        mil_out = {"metric": "MIL slide predictions/sec (ALiBi Transformer-MIL, 4096x1024 bag, batch 1)",
+                   "value": res["value"], "e2e": res["e2e"], "unit": "slides/s",
+                   "roofline_frac": (res["value"] / world) * MIL_FLOPS_PER_BAG / 1e12 / peak_tf,
+                   "h2d_bytes_per_slide": n_tiles * 1026 * 4}
+
+    # ---- CPU baseline (rank 0, single GPU runs only): oracle port on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        tps, cores, dt = cpu_vit_tiles_per_s(16, reps=2, warm=1)
+        cpu = {"value": tps, "unit": "tiles/s", "cores": cores, "kind": "port",
+               "sample": f"2 x 16 synthetic tiles ({dt:.1f} s), ViT-L/16 fp32 oracle port of the timm path"}
+        if mil_out is not None:
+            cpu["mil_slides_per_s"] = cpu_mil_slides_per_s(4096, reps=3)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp16 operands / fp32 accumulate + residual",
+            "data": "synthetic (uniform random uint8 tiles, random-init ViT-L/16 weights)",
+            "config": {"workload": WORKLOAD, "tiles_per_step_per_gpu": args.slide_tiles,
+                       "batch": args.batch, "l2": "inputs (1.5 GB/slide) larger than L2, no flush",
+                       "sharding": f"slides[rank::{world}], no data-path collective"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": cpu, "mil": mil_out,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=192)
+    ap.add_argument("--slide-tiles", type=int, default=SLIDE_TILES)
+    ap.add_argument("--skip-mil", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,11 +69,13 @@ int stamp_gemm_tn(const void* A, long long lda, const void* W, long long ldw, vo
                   int gout, int goff, void* stream);
 
 /* LayerNorm over the last dim of an fp32 matrix; out_kind 0 fp16, 1 bf16, 2 fp32.
+ * out_lo (fp16 output only, may be NULL) receives fp16(y - fp16(y)): the low half of a
+ * split-precision GEMM operand (same leading dimension as out).
  * replaces: timm Block.norm1/norm2/norm (eps 1e-6); nn.LayerNorm in
  *   src/stamp/modeling/models/vision_tranformer.py:161,186,277 (eps 1e-5). */
 int stamp_layernorm(const float* x, long long ldx, const float* weight, const float* bias,
-                    void* out, long long ldo, int rows, int cols, float eps, int out_kind,
-                    void* stream);
+                    void* out, void* out_lo, long long ldo, int rows, int cols, float eps,
+                    int out_kind, void* stream);
 
 /* x[g*rows_per_group + row_off + r, :] = src[r, :] (+ add[r, :]);  class / register token rows.
  * replaces: timm VisionTransformer._pos_embed (cls/reg token concat);
@@ -186,9 +188,12 @@ typedef struct {
 typedef struct {
     const float *ln1_w, *ln1_b;              /* layers.l.0.norm */
     const void* qkv_w; const float* qkv_b;   /* fp16 [3d, d]: rows = q heads | k heads | v heads */
+    const void* v_w_lo;                      /* ALiBi: fp16 [d, d] = fp16(Wv - fp16(Wv)), low half of the
+                                                split-precision V projection; else NULL */
     const float* slope;                      /* [H] bias_scale_h / running_mean_h (ALiBi only) */
     const void* fc_w;  const float* fc_b;    /* ALiBi: fp32 [d,d] rounded to TF32 (mhsa.fc);
                                                 else fp16 [d,d] (mhsa.out_proj) */
+    const void* fc_w_lo;                     /* ALiBi: fp32 [d,d] = tf32(W - tf32(W)); else NULL */
     const float *ln2_w, *ln2_b;              /* layers.l.1.0 */
     const void* ff1_w; const float* ff1_b;   /* fp16 [ff, d]  layers.l.1.1 */
     const void* ff2_w; const float* ff2_b;   /* fp16 [d, ff]  layers.l.1.4 */

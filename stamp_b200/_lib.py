@@ -28,7 +28,7 @@ SIGNATURES: dict[str, tuple] = {
     "stamp_gemm_tn": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_int,
                               c_int, c_void_p]),
-    "stamp_layernorm": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int,
+    "stamp_layernorm": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int,
                                 c_float, c_int, c_void_p]),
     "stamp_fill_rows": (c_int, [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll,
                                 c_int, c_int, c_void_p]),

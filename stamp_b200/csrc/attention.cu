@@ -78,7 +78,8 @@ flash_attn_kernel(const AttnParams p) {
 
     const __half* qb = p.q + b * p.batch_stride + h * HD;
     const __half* kb = p.k + b * p.batch_stride + h * HD;
-    const __half* vb = p.v + b * p.batch_stride + h * HD;
+    const long long v_rs = p.v_row_stride ? p.v_row_stride : p.row_stride;
+    const __half* vb = p.v + b * (p.v_row_stride ? p.v_batch_stride : p.batch_stride) + h * HD;
     const float2* cb = ALIBI ? reinterpret_cast<const float2*>(p.coords) + static_cast<long long>(b) * S : nullptr;
     const int mask_mode = (p.mask != nullptr) ? p.mask_mode : 0;
     // mask_mode 2 keeps a reference quirk (vision_tranformer.py:222-226): the mask is expanded with
@@ -91,7 +92,7 @@ flash_attn_kernel(const AttnParams p) {
 
     auto load_kv = [&](int kt, int buf) {
         load_rows_async<HD>(Ks + buf * SM::KV_HALFS, kb, p.row_stride, kt * BKV, S, tid);
-        load_rows_async<HD>(Vs + buf * SM::KV_HALFS, vb, p.row_stride, kt * BKV, S, tid);
+        load_rows_async<HD>(Vs + buf * SM::KV_HALFS, vb, v_rs, kt * BKV, S, tid);
         if (tid < BKV) {
             const int key = kt * BKV + tid;
             if constexpr (ALIBI) Cs[buf * BKV + tid] = (key < S) ? __ldg(cb + key) : make_float2(0.f, 0.f);
@@ -316,12 +317,20 @@ flash_attn_kernel(const AttnParams p) {
             // fp32 output pre-rounded (round-to-nearest) to TF32: it is the A operand of a
             // kind::tf32 GEMM, whose hardware conversion would otherwise truncate
             float* of = reinterpret_cast<float*>(p.out) + obase;
+            const float ha0 = round_tf32(ya0), ha1 = round_tf32(ya1), hb0 = round_tf32(yb0), hb1 = round_tf32(yb1);
             if (row_a < S)
-                *reinterpret_cast<float2*>(of + static_cast<long long>(row_a) * p.out_row_stride + col) =
-                    make_float2(round_tf32(ya0), round_tf32(ya1));
+                *reinterpret_cast<float2*>(of + static_cast<long long>(row_a) * p.out_row_stride + col) = make_float2(ha0, ha1);
             if (row_b < S)
-                *reinterpret_cast<float2*>(of + static_cast<long long>(row_b) * p.out_row_stride + col) =
-                    make_float2(round_tf32(yb0), round_tf32(yb1));
+                *reinterpret_cast<float2*>(of + static_cast<long long>(row_b) * p.out_row_stride + col) = make_float2(hb0, hb1);
+            if (p.out_lo != nullptr) {
+                float* ol = p.out_lo + obase;
+                if (row_a < S)
+                    *reinterpret_cast<float2*>(ol + static_cast<long long>(row_a) * p.out_row_stride + col) =
+                        make_float2(round_tf32(ya0 - ha0), round_tf32(ya1 - ha1));
+                if (row_b < S)
+                    *reinterpret_cast<float2*>(ol + static_cast<long long>(row_b) * p.out_row_stride + col) =
+                        make_float2(round_tf32(yb0 - hb0), round_tf32(yb1 - hb1));
+            }
         } else {
             __half* oh = reinterpret_cast<__half*>(p.out) + obase;
             if (row_a < S)
@@ -390,7 +399,7 @@ int launch_attn(const AttnParams& p, cudaStream_t stream) {
 int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream) {
     if (p.B <= 0 || p.S <= 0 || p.H <= 0 || p.q == nullptr || p.out == nullptr) return SB_ERR_BAD_ARG;
     if (static_cast<long long>(p.B) * p.H > 2147483647LL || (p.S + BQ - 1) / BQ > 65535) return SB_ERR_UNSUPPORTED;
-    if ((p.row_stride % 8) != 0 || (p.batch_stride % 8) != 0 || (p.out_row_stride % 2) != 0)
+    if ((p.row_stride % 8) != 0 || (p.batch_stride % 8) != 0 || (p.v_row_stride % 8) != 0 || (p.v_batch_stride % 8) != 0 || (p.out_row_stride % 2) != 0)
         return SB_ERR_BAD_ARG;
     const bool alibi = p.coords != nullptr;
     if (alibi && (p.slope == nullptr || p.dscale == nullptr)) return SB_ERR_BAD_ARG;

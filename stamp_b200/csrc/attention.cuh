@@ -12,8 +12,11 @@ struct AttnParams {
     const __half* v;
     long long row_stride;    // elements between consecutive tokens
     long long batch_stride;  // elements between consecutive bags / tiles
+    long long v_row_stride;  // same for v (0 -> use row_stride / batch_stride)
+    long long v_batch_stride;
     void* out;               // [B, S, H*head_dim], head-major concat; fp16, or fp32 (TF32-rounded) if out_f32
     int out_f32;
+    float* out_lo;           // out_f32 only, may be null: tf32(o - tf32(o)), the low half of a split-precision operand
     long long out_row_stride;
     long long out_batch_stride;
     int B, S, H;

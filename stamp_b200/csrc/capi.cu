@@ -49,10 +49,10 @@ int stamp_gemm_tn(const void* A, long long lda, const void* W, long long ldw, vo
 }
 
 int stamp_layernorm(const float* x, long long ldx, const float* weight, const float* bias,
-                    void* out, long long ldo, int rows, int cols, float eps, int out_kind,
-                    void* stream) {
+                    void* out, void* out_lo, long long ldo, int rows, int cols, float eps,
+                    int out_kind, void* stream) {
     if (x == nullptr || weight == nullptr || bias == nullptr || out == nullptr) return STAMP_ERR_BAD_ARG;
-    return sb::layernorm(x, ldx, weight, bias, out, ldo, rows, cols, eps, out_kind,
+    return sb::layernorm(x, ldx, weight, bias, out, out_lo, ldo, rows, cols, eps, out_kind,
                          static_cast<cudaStream_t>(stream));
 }
 
@@ -86,6 +86,8 @@ int stamp_attention_fwd(const void* q, const void* k, const void* v, long long r
     p.row_stride = row_stride; p.batch_stride = batch_stride;
     p.out = out;
     p.out_f32 = out_f32;
+    p.out_lo = nullptr;       // split-precision low half: only the MIL composite uses it
+    p.v_row_stride = 0; p.v_batch_stride = 0;
     p.out_row_stride = out_row_stride; p.out_batch_stride = out_batch_stride;
     p.B = B; p.S = S; p.H = H;
     p.scale_log2 = scale * 1.4426950408889634f;

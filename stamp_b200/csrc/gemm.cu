@@ -75,6 +75,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     switch (p.store) {
     case ST_16: {
         uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + n0;
+        if (p.table != nullptr) {  // fp32 addend (split-precision accumulation): v += table[m, n]
+            const float* t = p.table + static_cast<long long>(p.gin > 0 ? (m % p.gin) : m) * p.ldt + n0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) v[j] += __ldg(t + j);
+        }
         if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {

@@ -11,7 +11,7 @@ enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 
 // store stage
 enum GemmStore : int {
-    ST_16 = 0,       // out16[row, n] = v
+    ST_16 = 0,       // out16[row, n] = v (+ table[m % gin, n])
     ST_32 = 1,       // out32[row, n] = v (+ table[m % gin, n])
     ST_RESID32 = 2,  // out32[row, n] += gamma[n] * v           (gamma == null -> 1)
     ST_SWIGLU16 = 3, // out16[row, n/2] = silu(v[n]) * v[n+1]   (n even; weights row-interleaved)
@@ -28,7 +28,7 @@ struct GemmParams {
     long long ldo;       // leading dimension of out, elements
     const float* bias;   // [N] or null
     const float* gamma;  // [N] or null
-    const float* table;  // [gin, ldt] or null (ST_32 only)
+    const float* table;  // [gin, ldt] fp32 addend or null (ST_16 / ST_32)
     long long ldt;
     // optional row remap (token layouts with prefix rows):
     //   row = (m / gin) * gout + goff + (m % gin);   gin == 0 -> row = m

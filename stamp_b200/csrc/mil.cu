@@ -112,7 +112,8 @@ inline int grid_for(long long total, int block) {
 
 struct Layout {
     long long M, S;
-    size_t off_x, off_xn, off_qkv, off_att, off_h, off_bags, off_coords, off_mask, off_dscale, total;
+    size_t off_x, off_xn, off_xn_lo, off_qkv, off_att, off_att_lo, off_h, off_bags, off_coords, off_mask,
+        off_dscale, total;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -130,8 +131,10 @@ bool make_layout(const StampMilConfig* c, int B, int N, Layout* L) {
     size_t o = 0;
     L->off_x = o;      o = align_up(o + M * d * 4, 256);
     L->off_xn = o;     o = align_up(o + M * d * 2, 256);
+    L->off_xn_lo = o;  o = align_up(o + M * d * 2, 256);
     L->off_qkv = o;    o = align_up(o + M * 3 * d * 2, 256);
     L->off_att = o;    o = align_up(o + M * d * 4, 256);
+    L->off_att_lo = o; o = align_up(o + M * d * 4, 256);
     L->off_h = o;      o = align_up(o + M * c->dim_ff * 2, 256);
     L->off_bags = o;   o = align_up(o + static_cast<size_t>(B) * N * c->dim_input * 2 + 16, 256);
     L->off_coords = o; o = align_up(o + M * 8, 256);
@@ -202,44 +205,82 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w, const
         count_launch();
     }
 
+    __half* xn_lo = reinterpret_cast<__half*>(ws + L.off_xn_lo);
+    float* att_lo = reinterpret_cast<float*>(ws + L.off_att_lo);
+    const float scale_log2 = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
+
     for (int l = 0; l < cfg->n_layers; ++l) {
         const StampMilLayer& y = layers[l];
-        rc = layernorm(x, d, y.ln1_w, y.ln1_b, xn, d, M, d, 1e-5f, 0, stream);
-        if (rc != SB_OK) return rc;
-        {
+        AttnParams a{};
+        a.out = att; a.out_row_stride = d; a.out_batch_stride = static_cast<long long>(d) * S;
+        a.B = B; a.S = S; a.H = H; a.scale_log2 = scale_log2;
+        if (alibi) {
+            // The reference's ALiBi term (unscaled distances times V) dominates the layer output by
+            // orders of magnitude, so the two contractions it flows through -- the V projection and
+            // fc -- run in split precision (operand = hi + lo, three tensor-core passes, fp32
+            // accumulate); q/k and the softmax side are plain fp16.  Error budget: DESIGN.md.
+            rc = layernorm(x, d, y.ln1_w, y.ln1_b, xn, xn_lo, d, M, d, 1e-5f, 0, stream);
+            if (rc != SB_OK) return rc;
+            __half* qk = qkv;                                   // [M, 2d]
+            __half* v16 = qkv + static_cast<size_t>(M) * 2 * d;  // [M, d]
+            float* vacc = reinterpret_cast<float*>(att);        // fp32 scratch, dead before attention writes att
+            const __half* wv_hi = static_cast<const __half*>(y.qkv_w) + static_cast<size_t>(2) * d * d;
+            GemmParams p{};
+            p.M = M; p.K = d;
+            p.N = 2 * d; p.store = ST_16; p.out = qk; p.ldo = 2 * d; p.bias = y.qkv_b;
+            rc = gemm_tn(xn, d, y.qkv_w, d, p, stream);
+            if (rc != SB_OK) return rc;
+            p.N = d; p.store = ST_32; p.out = vacc; p.ldo = d; p.bias = y.qkv_b + 2 * d;
+            rc = gemm_tn(xn, d, wv_hi, d, p, stream);            // hi . hi (+ bias)
+            if (rc != SB_OK) return rc;
+            p.store = ST_RESID32; p.bias = nullptr;
+            rc = gemm_tn(xn_lo, d, wv_hi, d, p, stream);         // lo . hi
+            if (rc != SB_OK) return rc;
+            p.store = ST_16; p.out = v16; p.table = vacc; p.ldt = d;
+            rc = gemm_tn(xn, d, y.v_w_lo, d, p, stream);         // hi . lo, + fp32 partial -> fp16 V
+            if (rc != SB_OK) return rc;
+
+            rc = alibi_dist_scale(reinterpret_cast<const float*>(coords_s), y.slope, B, S, H, dscale, stream);
+            if (rc != SB_OK) return rc;
+            a.q = qk; a.k = qk + d; a.row_stride = 2LL * d; a.batch_stride = 2LL * d * S;
+            a.v = v16; a.v_row_stride = d; a.v_batch_stride = static_cast<long long>(d) * S;
+            a.out_f32 = 1; a.out_lo = att_lo;
+            a.coords = reinterpret_cast<const float*>(coords_s); a.slope = y.slope; a.dscale = dscale;
+            if (mask != nullptr) { a.mask = mask_s; a.mask_mode = 1; }
+            rc = attention_fwd(a, hd, stream);
+            if (rc != SB_OK) return rc;
+
+            // x += fc(att): 3 x TF32 (att = hi + lo from the attention epilogue, W = hi + lo packed on the host)
+            GemmParams f{};
+            f.M = M; f.N = d; f.K = d; f.tf32 = 1; f.store = ST_RESID32; f.out = x; f.ldo = d;
+            f.bias = y.fc_b;
+            rc = gemm_tn(att, d, y.fc_w, d, f, stream);
+            if (rc != SB_OK) return rc;
+            f.bias = nullptr;
+            rc = gemm_tn(att_lo, d, y.fc_w, d, f, stream);
+            if (rc != SB_OK) return rc;
+            rc = gemm_tn(att, d, y.fc_w_lo, d, f, stream);
+            if (rc != SB_OK) return rc;
+        } else {
+            rc = layernorm(x, d, y.ln1_w, y.ln1_b, xn, nullptr, d, M, d, 1e-5f, 0, stream);
+            if (rc != SB_OK) return rc;
             GemmParams p{};
             p.M = M; p.N = 3 * d; p.K = d;
             p.store = ST_16; p.out = qkv; p.ldo = 3 * d; p.bias = y.qkv_b;
             rc = gemm_tn(xn, d, y.qkv_w, d, p, stream);
             if (rc != SB_OK) return rc;
-        }
-        if (alibi) {
-            rc = alibi_dist_scale(reinterpret_cast<const float*>(coords_s), y.slope, B, S, H, dscale, stream);
-            if (rc != SB_OK) return rc;
-        }
-        {
-            AttnParams a{};
             a.q = qkv; a.k = qkv + d; a.v = qkv + 2 * d;
             a.row_stride = 3LL * d; a.batch_stride = 3LL * d * S;
-            a.out = att; a.out_f32 = alibi ? 1 : 0;
-            a.out_row_stride = d; a.out_batch_stride = static_cast<long long>(d) * S;
-            a.B = B; a.S = S; a.H = H;
-            a.scale_log2 = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
-            if (alibi) { a.coords = reinterpret_cast<const float*>(coords_s); a.slope = y.slope; a.dscale = dscale; }
-            if (mask != nullptr) { a.mask = mask_s; a.mask_mode = alibi ? 1 : 2; }
+            a.out_f32 = 0;
+            if (mask != nullptr) { a.mask = mask_s; a.mask_mode = 2; }
             rc = attention_fwd(a, hd, stream);
             if (rc != SB_OK) return rc;
-        }
-        {
-            // x = fc(att) + x : TF32 operands for the ALiBi variant (fp32 att, huge dynamic range)
-            GemmParams p{};
-            p.M = M; p.N = d; p.K = d;
-            p.store = ST_RESID32; p.out = x; p.ldo = d; p.bias = y.fc_b;
-            p.tf32 = alibi ? 1 : 0;
-            rc = gemm_tn(att, d, y.fc_w, d, p, stream);
+            GemmParams f{};
+            f.M = M; f.N = d; f.K = d; f.store = ST_RESID32; f.out = x; f.ldo = d; f.bias = y.fc_b;
+            rc = gemm_tn(att, d, y.fc_w, d, f, stream);
             if (rc != SB_OK) return rc;
         }
-        rc = layernorm(x, d, y.ln2_w, y.ln2_b, xn, d, M, d, 1e-5f, 0, stream);
+        rc = layernorm(x, d, y.ln2_w, y.ln2_b, xn, nullptr, d, M, d, 1e-5f, 0, stream);
         if (rc != SB_OK) return rc;
         {
             GemmParams p{};

@@ -18,8 +18,8 @@ namespace {
 template <int MAXV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w,
-                 const float* __restrict__ b, void* __restrict__ out, long long ldo, int rows,
-                 int cols, float eps, int out_kind /*0 fp16, 1 bf16, 2 fp32*/) {
+                 const float* __restrict__ b, void* __restrict__ out, uint16_t* __restrict__ out_lo,
+                 long long ldo, int rows, int cols, float eps, int out_kind /*0 fp16, 1 bf16, 2 fp32*/) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -67,6 +67,14 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __rest
                 pk.x = pack_16(y0, y1, out_kind == 1);
                 pk.y = pack_16(y2, y3, out_kind == 1);
                 *reinterpret_cast<uint2*>(o + idx * 4) = pk;
+                if (out_lo != nullptr) {
+                    // split precision: y = hi + lo with hi = fp16(y), lo = fp16(y - hi)
+                    const __half2 h01 = *reinterpret_cast<__half2*>(&pk.x), h23 = *reinterpret_cast<__half2*>(&pk.y);
+                    uint2 lo;
+                    lo.x = pack_f16(y0 - __low2float(h01), y1 - __high2float(h01));
+                    lo.y = pack_f16(y2 - __low2float(h23), y3 - __high2float(h23));
+                    *reinterpret_cast<uint2*>(out_lo + static_cast<long long>(warp) * ldo + idx * 4) = lo;
+                }
             }
         }
     }
@@ -178,20 +186,21 @@ inline int grid_for(long long total, int block) {
 
 }  // namespace
 
-int layernorm(const float* x, long long ldx, const float* w, const float* b, void* out,
+int layernorm(const float* x, long long ldx, const float* w, const float* b, void* out, void* out_lo,
               long long ldo, int rows, int cols, float eps, int out_kind, cudaStream_t stream) {
     if (rows <= 0 || cols <= 0 || (cols % 4) != 0 || (ldx % 4) != 0 || (ldo % 4) != 0 ||
-        out_kind < 0 || out_kind > 2)
+        out_kind < 0 || out_kind > 2 || (out_lo != nullptr && out_kind != 0))
         return SB_ERR_BAD_ARG;
+    uint16_t* lo = static_cast<uint16_t*>(out_lo);
     const int threads = 256;
     const int blocks = (rows * 32 + threads - 1) / threads;
     ProfScope prof(PROF_ROWOP, static_cast<double>(rows) * cols * (4.0 + (out_kind == 2 ? 4.0 : 2.0)), stream);
     if (cols <= 512)
-        layernorm_kernel<4><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, ldo, rows, cols, eps, out_kind);
+        layernorm_kernel<4><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, lo, ldo, rows, cols, eps, out_kind);
     else if (cols <= 1024)
-        layernorm_kernel<8><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, ldo, rows, cols, eps, out_kind);
+        layernorm_kernel<8><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, lo, ldo, rows, cols, eps, out_kind);
     else if (cols <= 2048)
-        layernorm_kernel<16><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, ldo, rows, cols, eps, out_kind);
+        layernorm_kernel<16><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, lo, ldo, rows, cols, eps, out_kind);
     else
         return SB_ERR_UNSUPPORTED;
     count_launch();

@@ -5,8 +5,8 @@
 
 namespace sb {
 
-// out_kind: 0 fp16, 1 bf16, 2 fp32
-int layernorm(const float* x, long long ldx, const float* w, const float* b, void* out,
+// out_kind: 0 fp16, 1 bf16, 2 fp32; out_lo (fp16 only, may be null) receives fp16(y - fp16(y))
+int layernorm(const float* x, long long ldx, const float* w, const float* b, void* out, void* out_lo,
               long long ldo, int rows, int cols, float eps, int out_kind, cudaStream_t stream);
 
 // x[g * rows_per_group + row_off + r, :] = src[r, :] (+ add[r, :]) for g < groups, r < nrows

@@ -99,7 +99,7 @@ int stamp_vit_forward(const StampVitConfig* cfg, const StampVitWeights* w,
 
     for (int l = 0; l < cfg->depth; ++l) {
         const StampVitBlock& b = blocks[l];
-        rc = layernorm(x, D, b.ln1_w, b.ln1_b, xn, D, M, D, cfg->ln_eps, 0, stream);
+        rc = layernorm(x, D, b.ln1_w, b.ln1_b, xn, nullptr, D, M, D, cfg->ln_eps, 0, stream);
         if (rc != SB_OK) return rc;
         {
             GemmParams p{};
@@ -125,7 +125,7 @@ int stamp_vit_forward(const StampVitConfig* cfg, const StampVitWeights* w,
             rc = gemm_tn(xn, D, b.proj_w, D, p, stream);
             if (rc != SB_OK) return rc;
         }
-        rc = layernorm(x, D, b.ln2_w, b.ln2_b, xn, D, M, D, cfg->ln_eps, 0, stream);
+        rc = layernorm(x, D, b.ln2_w, b.ln2_b, xn, nullptr, D, M, D, cfg->ln_eps, 0, stream);
         if (rc != SB_OK) return rc;
         {
             GemmParams p{};
@@ -145,7 +145,7 @@ int stamp_vit_forward(const StampVitConfig* cfg, const StampVitWeights* w,
         }
     }
     // final norm on the class-token rows only (global_pool='token'): row b*T of x
-    return layernorm(x, static_cast<long long>(D) * T, w->norm_w, w->norm_b, feats16, D, B, D,
+    return layernorm(x, static_cast<long long>(D) * T, w->norm_w, w->norm_b, feats16, nullptr, D, B, D,
                      cfg->ln_eps, 0, stream);
 }
 

@@ -91,7 +91,7 @@ def layernorm(x: Tensor, weight: Tensor, bias: Tensor, eps: float, out_dtype: to
     if out is None:
         out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
     code = _lib.load().stamp_layernorm(x.data_ptr(), x.stride(0), weight.data_ptr(), bias.data_ptr(),
-                                       out.data_ptr(), out.stride(0), x.shape[0], x.shape[1],
+                                       out.data_ptr(), None, out.stride(0), x.shape[0], x.shape[1],
                                        float(eps), kind, _stream())
     _lib.check(code, "stamp_layernorm")
     return out
