@@ -49,11 +49,11 @@ def pil_to_u8_hwc(img) -> Tensor:
 def _resolve_weights(arch: VitArch, weights, hub_id: str | None, hub_kwargs: dict) -> Mapping[str, Tensor]:
     if isinstance(weights, Mapping):
         return weights
+    if isinstance(weights, str) and weights == "random":
+        return random_state_dict(arch)
     if isinstance(weights, (str, Path)):
         sd = torch.load(str(weights), map_location="cpu", weights_only=True)
         return sd.get("state_dict", sd)
-    if weights == "random":
-        return random_state_dict(arch)
     if weights is None and hub_id is not None:
         try:  # the reference's own source of weights (needs timm + network / HF cache)
             import timm
