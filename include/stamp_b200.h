@@ -206,6 +206,49 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w,
                       const float* coords, const uint8_t* mask, float* logits, int B, int N,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Macenko stain normalisation over a batch of uint8 RGB tiles (in/out [n_tiles,H,W,3]).
+ * The reference snapshot has no Macenko code (README.md:35 only): the stage is named by
+ * BASELINE.json's north_star; algorithm as specified in SURVEY.md 8c (oracle/macenko_oracle.py).
+ * One stain matrix is fitted per group of `tiles_per_fit` consecutive tiles (<= 0: one fit over the
+ * whole batch) and applied per pixel.  Optional outputs: he_out [G,3,2] (columns H, E),
+ * maxc_out [G,2], valid_out [G] (0 = fewer than 16 tissue pixels: tiles passed through).
+ * H*W*3 must be a multiple of 48; in/out 16-byte aligned; workspace 256-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+size_t stamp_macenko_workspace_bytes(int n_tiles, int tiles_per_fit);
+int stamp_macenko_u8(const uint8_t* in, uint8_t* out, int n_tiles, int H, int W, int tiles_per_fit,
+                     float Io, float alpha, float beta, float* he_out, float* maxc_out,
+                     int* valid_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Slide-level pooling.
+ * stamp_gated_attn_pool -- CHIEF's gated-attention MIL pooling:
+ *   h = ReLU(W1 x + b1); A_raw = Wc (tanh(Wa h + ba) * sigmoid(Wb h + bb)) + bc;
+ *   pooled = softmax_over_tiles(A_raw) @ x           (x: the ORIGINAL fp32 features [N, D])
+ *   replaces CHIEFModel.forward / Attn_Net_Gated.forward, src/stamp/encoding/encoder/chief.py:74-89,
+ *   :255-275 (size 'small': D 768, L 512, Dh 256).  The score chain runs in split precision
+ *   (hi/lo fp16 operand pairs, fp32 accumulate) so that top-k over attn_raw matches fp32.
+ * stamp_topk_f32 -- exact top-k (k <= 1024) of fp32 scores, largest (or smallest) first, ties by
+ *   lower index; replaces torch.topk at src/stamp/encoding/encoder/eagle.py:108-109 and
+ *   src/stamp/heatmaps/__init__.py:216-229.
+ * stamp_gather_mean_f32 -- mean of k gathered rows (EAGLE embedding, eagle.py:112-118).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* fc_w_hi; const void* fc_w_lo; const float* fc_b;   /* fp16 [L, D] hi / lo; [L] */
+    const void* ab_w_hi; const void* ab_w_lo; const float* ab_b;   /* fp16 [2*Dh, L], rows a_0,b_0,a_1,b_1,..; [2*Dh] */
+    const float* c_w;                                              /* [Dh] attention_c.weight */
+    float c_b;
+} StampGatedAttnWeights;
+
+size_t stamp_gated_attn_pool_workspace_bytes(int N, int D, int L, int Dh);
+int stamp_gated_attn_pool(const StampGatedAttnWeights* w, const float* x, int N, int D, int L, int Dh,
+                          float* attn_raw /* [N] */, float* pooled /* [D] */, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int stamp_topk_f32(const float* scores, int N, int k, int largest, long long* idx_out,
+                   float* val_out /* may be NULL */, void* stream);
+int stamp_gather_mean_f32(const float* feats, const long long* idx, int k, int D, float* out,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,7 +38,7 @@ int stamp_gemm_tn(const void* A, long long lda, const void* W, long long ldw, vo
                   int act, int store, int dtype, const float* table, long long ldt, int gin,
                   int gout, int goff, void* stream) {
     if (act < 0 || act > 2 || store < 0 || store > 4 || dtype < 0 || dtype > 2) return STAMP_ERR_BAD_ARG;
-    sb::GemmParams p;
+    sb::GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.act = act; p.store = store; p.bf16 = (dtype == 1); p.tf32 = (dtype == 2);
     p.out = out; p.ldo = ldo;

@@ -63,6 +63,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
                 if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
         }
     }
+    if (p.table != nullptr) {
+        // fp32 addend applied BEFORE the activation: position table of the patch embedding, or the
+        // running fp32 partial of a split-precision (hi + lo) product
+        const float* t = p.table + static_cast<long long>(p.gin > 0 ? (m % p.gin) : m) * p.ldt + n0;
+        if (full && ((reinterpret_cast<uintptr_t>(t) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 tt = ldg4(t + j);
+                v[j] += tt.x; v[j + 1] += tt.y; v[j + 2] += tt.z; v[j + 3] += tt.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) v[j] += __ldg(t + j);
+        }
+    }
     if (p.act == ACT_GELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
@@ -75,12 +91,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     switch (p.store) {
     case ST_16: {
         uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + n0;
-        if (p.table != nullptr) {  // fp32 addend (split-precision accumulation): v += table[m, n]
-            const float* t = p.table + static_cast<long long>(p.gin > 0 ? (m % p.gin) : m) * p.ldt + n0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) v[j] += __ldg(t + j);
-        }
         if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
@@ -90,6 +100,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
                 w.z = pack_16(v[j + 4], v[j + 5], bf);
                 w.w = pack_16(v[j + 6], v[j + 7], bf);
                 *reinterpret_cast<uint4*>(o + j) = w;
+                if (p.out_lo != nullptr) {  // low half of a split-precision operand (fp16 only)
+                    const __half2* h = reinterpret_cast<const __half2*>(&w);
+                    uint4 lo;
+                    lo.x = pack_f16(v[j] - __low2float(h[0]), v[j + 1] - __high2float(h[0]));
+                    lo.y = pack_f16(v[j + 2] - __low2float(h[1]), v[j + 3] - __high2float(h[1]));
+                    lo.z = pack_f16(v[j + 4] - __low2float(h[2]), v[j + 5] - __high2float(h[2]));
+                    lo.w = pack_f16(v[j + 6] - __low2float(h[3]), v[j + 7] - __high2float(h[3]));
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_lo) + row * p.ldo + n0 + j) = lo;
+                }
             }
         } else {
 #pragma unroll
@@ -103,24 +122,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     }
     case ST_32: {
         float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + n0;
-        const float* t = (p.table != nullptr)
-                             ? p.table + static_cast<long long>(p.gin > 0 ? (m % p.gin) : m) * p.ldt + n0
-                             : nullptr;
-        if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) &&
-            (t == nullptr || (reinterpret_cast<uintptr_t>(t) & 15) == 0)) {
+        if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 w = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (t != nullptr) {
-                    float4 tt = ldg4(t + j);
-                    w.x += tt.x; w.y += tt.y; w.z += tt.z; w.w += tt.w;
-                }
-                *reinterpret_cast<float4*>(o + j) = w;
-            }
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) o[j] = v[j] + (t != nullptr ? __ldg(t + j) : 0.0f);
+                if (n0 + j < p.N) o[j] = v[j];
         }
         break;
     }
@@ -168,6 +177,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
                 w.z = pack_16(g[j + 4], g[j + 5], bf);
                 w.w = pack_16(g[j + 6], g[j + 7], bf);
                 *reinterpret_cast<uint4*>(o + j) = w;
+                if (p.out_lo != nullptr) {
+                    const __half2* h = reinterpret_cast<const __half2*>(&w);
+                    uint4 lo;
+                    lo.x = pack_f16(g[j] - __low2float(h[0]), g[j + 1] - __high2float(h[0]));
+                    lo.y = pack_f16(g[j + 2] - __low2float(h[1]), g[j + 3] - __high2float(h[1]));
+                    lo.z = pack_f16(g[j + 4] - __low2float(h[2]), g[j + 5] - __high2float(h[2]));
+                    lo.w = pack_f16(g[j + 6] - __low2float(h[3]), g[j + 7] - __high2float(h[3]));
+                    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_lo) + row * p.ldo + (n0 >> 1) + j) = lo;
+                }
             }
         } else {
 #pragma unroll

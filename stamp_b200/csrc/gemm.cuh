@@ -11,8 +11,8 @@ enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 
 // store stage
 enum GemmStore : int {
-    ST_16 = 0,       // out16[row, n] = v (+ table[m % gin, n])
-    ST_32 = 1,       // out32[row, n] = v (+ table[m % gin, n])
+    ST_16 = 0,       // out16[row, n] = v
+    ST_32 = 1,       // out32[row, n] = v
     ST_RESID32 = 2,  // out32[row, n] += gamma[n] * v           (gamma == null -> 1)
     ST_SWIGLU16 = 3, // out16[row, n/2] = silu(v[n]) * v[n+1]   (n even; weights row-interleaved)
     ST_GATED16 = 4,  // out16[row, n/2] = tanh(v[n]) * sigmoid(v[n+1])
@@ -25,10 +25,11 @@ struct GemmParams {
     int bf16;            // 16-bit operands and 16-bit outputs are bf16 instead of fp16
     int tf32;            // operands are fp32 read as TF32 (kind::tf32); 16-bit outputs follow bf16
     void* out;           // fp16/bf16 or fp32 matrix
+    void* out_lo;        // fp16 16-bit stores only, may be null: fp16(v - fp16(v)), same ldo (full tiles)
     long long ldo;       // leading dimension of out, elements
     const float* bias;   // [N] or null
     const float* gamma;  // [N] or null
-    const float* table;  // [gin, ldt] fp32 addend or null (ST_16 / ST_32)
+    const float* table;  // [gin, ldt] fp32 addend applied before the activation, or null
     long long ldt;
     // optional row remap (token layouts with prefix rows):
     //   row = (m / gin) * gout + goff + (m % gin);   gin == 0 -> row = m

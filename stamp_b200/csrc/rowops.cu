@@ -178,6 +178,36 @@ tiles_to_patches_generic_kernel(const uint8_t* __restrict__ tiles, uint16_t* __r
     }
 }
 
+// fp32 -> fp16 hi (+ optional lo = fp16(v - hi)), 8 elements per thread, 128-bit loads/stores
+__global__ void __launch_bounds__(256)
+cast_split_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo,
+                  long long n8, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const uint4 a = ld_nc_v4(in + i * 8), b = ld_nc_v4(in + i * 8 + 4);
+        const float v[8] = {__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w),
+                            __uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w)};
+        uint4 w;
+        w.x = pack_f16(v[0], v[1]); w.y = pack_f16(v[2], v[3]); w.z = pack_f16(v[4], v[5]); w.w = pack_f16(v[6], v[7]);
+        *reinterpret_cast<uint4*>(hi + i * 8) = w;
+        if (lo != nullptr) {
+            const __half2* h = reinterpret_cast<const __half2*>(&w);
+            uint4 l;
+            l.x = pack_f16(v[0] - __low2float(h[0]), v[1] - __high2float(h[0]));
+            l.y = pack_f16(v[2] - __low2float(h[1]), v[3] - __high2float(h[1]));
+            l.z = pack_f16(v[4] - __low2float(h[2]), v[5] - __high2float(h[2]));
+            l.w = pack_f16(v[6] - __low2float(h[3]), v[7] - __high2float(h[3]));
+            *reinterpret_cast<uint4*>(lo + i * 8) = l;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n - n8 * 8)) {
+        const long long j = n8 * 8 + threadIdx.x;
+        const __half h = __float2half_rn(in[j]);
+        hi[j] = h;
+        if (lo != nullptr) lo[j] = __float2half_rn(in[j] - __half2float(h));
+    }
+}
+
 inline int grid_for(long long total, int block) {
     long long g = (total + block - 1) / block;
     const long long cap = 148LL * 16;
@@ -236,6 +266,16 @@ int tiles_to_patches(const uint8_t* tiles, void* patches, int B, int img, int P,
             tiles, reinterpret_cast<uint16_t*>(patches), B, img, P, Kpad, scale, shift, bf16);
     count_launch();
     }
+    return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+int cast_f32_f16(const float* in, __half* hi, __half* lo, long long n, cudaStream_t stream) {
+    if (in == nullptr || hi == nullptr || n <= 0 || (reinterpret_cast<uintptr_t>(in) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(hi) & 15) != 0)
+        return SB_ERR_BAD_ARG;
+    ProfScope prof(PROF_ROWOP, n * (lo != nullptr ? 8.0 : 6.0), stream);
+    cast_split_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(in, hi, lo, n / 8, n);
+    count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 

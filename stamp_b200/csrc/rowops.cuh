@@ -1,5 +1,6 @@
 // Row-wise HBM-bound kernels (rowops.cu).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -17,5 +18,8 @@ int fill_rows(float* x, long long ldx, int groups, int rows_per_group, int row_o
 // uint8 HWC tiles -> normalised 16-bit patch matrix [B * (img/P)^2, Kpad], columns (c, ky, kx)
 int tiles_to_patches(const uint8_t* tiles, void* patches, int B, int img, int P, int Kpad,
                      const float mean[3], const float stdv[3], int bf16, cudaStream_t stream);
+
+// fp32 -> fp16 (round to nearest); lo (may be null) receives fp16(v - fp16(v))
+int cast_f32_f16(const float* in, __half* hi, __half* lo, long long n, cudaStream_t stream);
 
 }  // namespace sb

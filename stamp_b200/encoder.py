@@ -1,0 +1,147 @@
+"""Slide-level encoders backed by the B200 pooling kernels: CHIEF (gated-attention pooling) and
+EAGLE (CHIEF attention -> top-25 tiles -> mean of the aggregation features).
+
+Mirrors the reference's ``Encoder`` contract (src/stamp/encoding/encoder/__init__.py:29-171):
+``_generate_slide_embedding(feats [N, D], device, **kw) -> np.ndarray [D']``.  Model arithmetic:
+src/stamp/encoding/encoder/chief.py:27-89,255-275 and eagle.py:92-120.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from collections.abc import Mapping
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib
+
+
+class StampGatedAttnWeights(C.Structure):
+    _fields_ = [("fc_w_hi", C.c_void_p), ("fc_w_lo", C.c_void_p), ("fc_b", C.c_void_p),
+                ("ab_w_hi", C.c_void_p), ("ab_w_lo", C.c_void_p), ("ab_b", C.c_void_p),
+                ("c_w", C.c_void_p), ("c_b", C.c_float)]
+
+
+def _bind() -> C.CDLL:
+    lib = _lib.load()
+    if not getattr(lib, "_pool_bound", False):
+        lib.stamp_gated_attn_pool_workspace_bytes.restype = C.c_size_t
+        lib.stamp_gated_attn_pool_workspace_bytes.argtypes = [C.c_int] * 4
+        lib.stamp_gated_attn_pool.restype = C.c_int
+        lib.stamp_gated_attn_pool.argtypes = [C.POINTER(StampGatedAttnWeights), C.c_void_p, C.c_int, C.c_int,
+                                              C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_size_t, C.c_void_p]
+        lib.stamp_topk_f32.restype = C.c_int
+        lib.stamp_topk_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.stamp_gather_mean_f32.restype = C.c_int
+        lib.stamp_gather_mean_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        lib._pool_bound = True
+    return lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def topk(scores: Tensor, k: int, largest: bool = True) -> tuple[Tensor, Tensor]:
+    """Exact top-k of a 1-D fp32 CUDA tensor -> (values, int64 indices); ties by lower index."""
+    if not scores.is_cuda or scores.dtype != torch.float32 or scores.dim() != 1 or not scores.is_contiguous():
+        raise TypeError("scores must be a contiguous 1-D float32 CUDA tensor")
+    idx = torch.empty(k, dtype=torch.int64, device=scores.device)
+    val = torch.empty(k, dtype=torch.float32, device=scores.device)
+    code = _bind().stamp_topk_f32(scores.data_ptr(), scores.numel(), k, int(largest), idx.data_ptr(),
+                                  val.data_ptr(), _stream())
+    _lib.check(code, "stamp_topk_f32")
+    return val, idx
+
+
+class GatedAttentionPool(torch.nn.Module):
+    """CHIEF's ``attention_net`` (fc + Attn_Net_Gated) + softmax pooling, weights from a CHIEF
+    state dict (keys ``attention_net.0.*``, ``attention_net.3.attention_{a,b}.0.*``,
+    ``attention_net.3.attention_c.*`` -- chief.py:45-58,255-268)."""
+
+    def __init__(self, state_dict: Mapping[str, Tensor]) -> None:
+        super().__init__()
+        sd = {k: v.detach().float() for k, v in state_dict.items()}
+        fc_w, fc_b = sd["attention_net.0.weight"], sd["attention_net.0.bias"]
+        gate = next(k for k in sd if k.endswith("attention_a.0.weight")).rsplit("attention_a", 1)[0]
+        a_w, a_b = sd[gate + "attention_a.0.weight"], sd[gate + "attention_a.0.bias"]
+        b_w, b_b = sd[gate + "attention_b.0.weight"], sd[gate + "attention_b.0.bias"]
+        c_w, c_b = sd[gate + "attention_c.weight"], sd[gate + "attention_c.bias"]
+        self.D, self.L, self.Dh = fc_w.shape[1], fc_w.shape[0], a_w.shape[0]
+        ab_w = torch.stack([a_w, b_w], 1).reshape(2 * self.Dh, self.L)   # rows a_0, b_0, a_1, b_1, ...
+        ab_b = torch.stack([a_b, b_b], 1).reshape(2 * self.Dh)
+
+        def split(name: str, w: Tensor) -> None:
+            hi = w.half()
+            self.register_buffer(name + "_hi", hi.contiguous(), persistent=False)
+            self.register_buffer(name + "_lo", (w - hi.float()).half().contiguous(), persistent=False)
+
+        split("fc_w", fc_w)
+        split("ab_w", ab_w)
+        self.register_buffer("fc_b", fc_b.contiguous(), persistent=False)
+        self.register_buffer("ab_b", ab_b.contiguous(), persistent=False)
+        self.register_buffer("c_w", c_w.reshape(-1).contiguous(), persistent=False)
+        self.c_b = float(c_b.reshape(-1)[0])
+
+    @torch.no_grad()
+    def forward(self, feats: Tensor) -> dict[str, Tensor]:
+        """feats fp32 [N, D] (CUDA) -> {"attention_raw": [1, N], "WSI_feature": [1, D]}."""
+        if not feats.is_cuda or not self.c_w.is_cuda:
+            raise RuntimeError("GatedAttentionPool runs on a CUDA device only (no CPU fallback)")
+        x = feats.detach().float().contiguous()
+        N, D = x.shape
+        if D != self.D:
+            raise ValueError(f"expected {self.D}-dim features, got {D}")
+        lib = _bind()
+        w = StampGatedAttnWeights(self.fc_w_hi.data_ptr(), self.fc_w_lo.data_ptr(), self.fc_b.data_ptr(),
+                                  self.ab_w_hi.data_ptr(), self.ab_w_lo.data_ptr(), self.ab_b.data_ptr(),
+                                  self.c_w.data_ptr(), self.c_b)
+        attn = torch.empty(N, dtype=torch.float32, device=x.device)
+        pooled = torch.empty(D, dtype=torch.float32, device=x.device)
+        ws = torch.empty(lib.stamp_gated_attn_pool_workspace_bytes(N, D, self.L, self.Dh), dtype=torch.uint8,
+                         device=x.device)
+        code = lib.stamp_gated_attn_pool(C.byref(w), x.data_ptr(), N, D, self.L, self.Dh, attn.data_ptr(),
+                                         pooled.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        _lib.check(code, "stamp_gated_attn_pool")
+        return {"attention_raw": attn[None], "WSI_feature": pooled[None]}
+
+
+class ChiefB200:
+    """``Encoder``-shaped CHIEF slide encoder (identifier "chief", needs ctranspath features)."""
+
+    identifier = "chief"
+    precision = torch.float32
+
+    def __init__(self, state_dict: Mapping[str, Tensor]) -> None:
+        self.model = GatedAttentionPool(state_dict)
+
+    def _generate_slide_embedding(self, feats: Tensor, device, **kwargs) -> np.ndarray:
+        self.model.to(device)
+        out = self.model(feats.to(device))
+        return out["WSI_feature"].float().squeeze().cpu().numpy()
+
+    def _generate_patient_embedding(self, feats_list: list[Tensor], device, **kwargs) -> np.ndarray:
+        return self._generate_slide_embedding(torch.cat(feats_list, 0), device)
+
+
+class EagleB200(ChiefB200):
+    """EAGLE: CHIEF attention over ctranspath features -> top-25 tiles -> mean of the matching
+    Virchow2 features (eagle.py:92-120)."""
+
+    identifier = "eagle"
+
+    def _generate_slide_embedding(self, feats: Tensor, device, agg_feats: Tensor | None = None, **kwargs) -> np.ndarray:
+        if agg_feats is None:
+            raise ValueError("agg_feats is required for slide embedding")
+        self.model.to(device)
+        attn = self.model(feats.to(device))["attention_raw"].squeeze(0).contiguous()
+        k = min(25, attn.shape[0])
+        _, idx = topk(attn, k)
+        agg = agg_feats.to(device).float().contiguous()
+        out = torch.empty(agg.shape[1], dtype=torch.float32, device=agg.device)
+        code = _bind().stamp_gather_mean_f32(agg.data_ptr(), idx.data_ptr(), k, agg.shape[1], out.data_ptr(), _stream())
+        _lib.check(code, "stamp_gather_mean_f32")
+        return out.cpu().numpy()

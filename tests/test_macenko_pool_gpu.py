@@ -1,0 +1,136 @@
+"""Macenko stain normalisation and slide-level pooling parity on the GPU (through the C ABI).
+
+Macenko: uint8 images within 1 LSB of the fp64 NumPy oracle, stain vectors within 1e-4
+(SURVEY.md 8c); properties at full size: idempotence of the pass-through, determinism.
+CHIEF / EAGLE: attention scores and pooled embedding vs the fp32/fp64 oracle, top-k indices
+bit-exact (north_star)."""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _tiles(n, seed, img=224):
+    from oracle import vit_oracle as vo
+
+    return vo.synthetic_tiles(n, seed=seed, img=img)
+
+
+@pytest.mark.parametrize("n_tiles,tpf", [(8, None), (12, 4), (5, 2), (3, 1)])
+def test_macenko_matches_oracle(cuda_device, n_tiles, tpf):
+    from oracle import macenko_oracle as mo
+    from stamp_b200.macenko import macenko_normalize
+
+    tiles = _tiles(n_tiles, seed=20 + n_tiles)
+    ref, he_ref, maxc_ref, valid_ref = mo.normalize(tiles.numpy(), tiles_per_fit=tpf)
+    out, fit = macenko_normalize(tiles.to(cuda_device), tiles_per_fit=tpf, return_fit=True)
+    assert out.dtype == torch.uint8 and out.shape == tiles.shape
+    assert np.array_equal(fit.valid.cpu().numpy(), valid_ref)
+    he = fit.stain_matrix.cpu().numpy()
+    assert np.abs(he - he_ref).max() < 1e-4, np.abs(he - he_ref).max()
+    assert np.abs(fit.max_conc.cpu().numpy() - maxc_ref).max() / np.abs(maxc_ref).max() < 1e-4
+    diff = np.abs(out.cpu().numpy().astype(np.int16) - ref.astype(np.int16))
+    assert diff.max() <= 1, diff.max()
+    assert (diff > 0).mean() < 0.02  # only truncation-boundary pixels may differ
+
+
+def test_macenko_no_tissue_passthrough_and_mixed_groups(cuda_device):
+    from oracle import macenko_oracle as mo
+    from stamp_b200.macenko import macenko_normalize
+
+    tiles = _tiles(4, seed=31)
+    tiles[2:] = 250  # background: every OD < beta -> no tissue pixels in groups 2, 3
+    ref, _, _, valid_ref = mo.normalize(tiles.numpy(), tiles_per_fit=1)
+    out, fit = macenko_normalize(tiles.to(cuda_device), tiles_per_fit=1, return_fit=True)
+    assert fit.valid.cpu().tolist() == valid_ref.tolist() == [True, True, False, False]
+    assert torch.equal(out[2:].cpu(), tiles[2:])
+    assert np.abs(out.cpu().numpy().astype(np.int16) - ref.astype(np.int16)).max() <= 1
+
+
+def test_macenko_deterministic_and_non_224(cuda_device):
+    from oracle import macenko_oracle as mo
+    from stamp_b200.macenko import macenko_normalize
+
+    tiles = _tiles(6, seed=33, img=96).to(cuda_device)
+    a, b = macenko_normalize(tiles), macenko_normalize(tiles)
+    assert torch.equal(a, b)
+    ref, *_ = mo.normalize(tiles.cpu().numpy())
+    assert np.abs(a.cpu().numpy().astype(np.int16) - ref.astype(np.int16)).max() <= 1
+
+
+def test_macenko_batch_scale_property(cuda_device):
+    """Full extraction batch (192 tiles, 29 MB): fit is pooled, so normalising a batch made of the
+    same tile set twice gives the same stain matrix as the set itself (percentiles are replication
+    invariant up to interpolation)."""
+    from stamp_b200.macenko import macenko_normalize
+
+    base = _tiles(16, seed=35).to(cuda_device)
+    tiles = base.repeat(12, 1, 1, 1)
+    _, fit_big = macenko_normalize(tiles, return_fit=True)
+    _, fit_small = macenko_normalize(base, return_fit=True)
+    assert (fit_big.stain_matrix - fit_small.stain_matrix).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("n", [1, 5, 300, 5000])
+def test_gated_attention_pool_matches_oracle(cuda_device, n):
+    from oracle import chief_oracle as co
+    from stamp_b200.encoder import GatedAttentionPool
+
+    sd = co.init_state_dict(seed=1)
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, 768, generator=g)
+    ref = co.forward(sd, x.double())
+    out = GatedAttentionPool(sd).to(cuda_device)(x.to(cuda_device))
+    a, a_ref = out["attention_raw"].cpu().double(), ref["attention_raw"]
+    assert a.shape == a_ref.shape
+    assert (a - a_ref).abs().max().item() < 2e-5 * max(1.0, a_ref.abs().max().item())  # fp32-grade scores
+    p, p_ref = out["WSI_feature"].cpu().double(), ref["WSI_feature"]
+    assert ((p - p_ref).norm() / p_ref.norm()).item() < 1e-4
+
+
+def test_eagle_topk_indices_bit_exact(cuda_device):
+    from oracle import chief_oracle as co
+    from stamp_b200.encoder import EagleB200
+
+    sd = co.init_state_dict(seed=2)
+    g = torch.Generator().manual_seed(7)
+    feats, agg = torch.randn(4000, 768, generator=g), torch.randn(4000, 1280, generator=g)
+    emb_ref, idx_ref = co.eagle_embedding(sd, feats, agg)
+    enc = EagleB200(sd)
+    emb = enc._generate_slide_embedding(feats, cuda_device, agg_feats=agg)
+    attn = enc.model(feats.to(cuda_device))["attention_raw"].squeeze(0)
+    from stamp_b200.encoder import topk
+
+    _, idx = topk(attn.contiguous(), 25)
+    assert torch.equal(idx.cpu(), idx_ref)            # same tiles, same order
+    assert np.allclose(emb, emb_ref.numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,k,largest", [(3, 2, True), (3, 2, False), (1000, 25, True), (50000, 100, True), (70, 64, False), (1024, 1024, True)])
+def test_topk_matches_torch(cuda_device, n, k, largest):
+    from stamp_b200.encoder import topk
+
+    g = torch.Generator().manual_seed(n + k)
+    s = torch.randn(n, generator=g).to(cuda_device)
+    val, idx = topk(s, k, largest)
+    rv, ri = torch.topk(s, k, largest=largest)
+    assert torch.equal(val, rv)
+    assert torch.equal(s[idx], rv)
+    assert idx.unique().numel() == k
+
+
+def test_topk_heatmap_fixture_and_ties(cuda_device):
+    """tests/test_heatmaps.py:15-59 of the reference: scores [0.1, 0.9, 0.3] -> top (0.9, 0.3),
+    bottom (0.1, 0.3); ties resolve to the lower index."""
+    from stamp_b200.encoder import topk
+
+    s = torch.tensor([0.1, 0.9, 0.3], device=cuda_device)
+    v, i = topk(s, 2, True)
+    assert i.tolist() == [1, 2] and v.tolist() == pytest.approx([0.9, 0.3])
+    v, i = topk(s, 2, False)
+    assert i.tolist() == [0, 2]
+    t = torch.tensor([1.0, 2.0, 2.0, 2.0, 0.5], device=cuda_device)
+    assert topk(t, 3, True)[1].tolist() == [1, 2, 3]
+    assert topk(torch.zeros(40, device=cuda_device), 5, True)[1].tolist() == [0, 1, 2, 3, 4]
