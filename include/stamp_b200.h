@@ -63,6 +63,10 @@ int stamp_b200_profile_summary(double* host_ms, double* host_work, long long* ho
  *        to TF32 to avoid the hardware's truncation); 16-bit outputs are fp16 (bf16 if dtype 1).
  * lda/ldw/ldo/ldt in elements; A, W 16-byte aligned with 16-byte row pitch.
  * ------------------------------------------------------------------------------------------- */
+/* tile-shape override for tests / tuning: 0 auto, 1 single-CTA tiles only, 2 CTA-pair
+ * (tcgen05 cta_group::2, 256x256) tiles whenever legal */
+void stamp_b200_gemm_force_mode(int mode);
+
 int stamp_gemm_tn(const void* A, long long lda, const void* W, long long ldw, void* out,
                   long long ldo, int M, int N, int K, const float* bias, const float* gamma,
                   int act, int store, int dtype, const float* table, long long ldt, int gin,

@@ -33,6 +33,8 @@ const char* stamp_b200_strerror(int code) {
 long long stamp_b200_launch_count(void) { return sb::g_launches.load(std::memory_order_relaxed); }
 void stamp_b200_reset_launch_count(void) { sb::g_launches.store(0, std::memory_order_relaxed); }
 
+void stamp_b200_gemm_force_mode(int mode) { sb::gemm_force_mode(mode); }
+
 int stamp_gemm_tn(const void* A, long long lda, const void* W, long long ldw, void* out,
                   long long ldo, int M, int N, int K, const float* bias, const float* gamma,
                   int act, int store, int dtype, const float* table, long long ldt, int gin,

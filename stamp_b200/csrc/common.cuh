@@ -289,23 +289,39 @@ __device__ __forceinline__ float round_tf32(float x) {
 
 // erf with |abs err| < 1.5e-7 (Abramowitz-Stegun 7.1.26): cheap enough to sit in a
 // GEMM epilogue, far below the fp16 rounding of the value it feeds.
-__device__ __forceinline__ float erf_as(float x) {
-    float ax = fabsf(x);
-    float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(r) : "f"(x));
+    return r;
+}
+// q(z) = 1 - erf(z) for z >= 0: branch-free, two MUFU ops (an IEEE reciprocal would expand into a
+// slow path with divergent branches inside the GEMM epilogue)
+__device__ __forceinline__ float erfc_as_pos(float z) {
+    const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
     float p = fmaf(t, 1.061405429f, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
     p *= t;
-    float e = __expf(-ax * ax);
-    float r = fmaf(-p, e, 1.0f);
-    return copysignf(r, x);
+    return p * ex2_approx(z * z * -1.4426950408889634f);
 }
+__device__ __forceinline__ float erf_as(float x) {
+    return copysignf(1.0f - erfc_as_pos(fabsf(x)), x);
+}
+// exact-erf GELU: 0.5 x (1 + erf(x / sqrt 2)) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2)
 __device__ __forceinline__ float gelu_erf(float x) {
-    return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f));
+    const float ax = fabsf(x);
+    return fmaxf(x, 0.0f) - 0.5f * ax * erfc_as_pos(ax * 0.70710678118654752f);
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) {
+    return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f));
+}
+__device__ __forceinline__ float silu(float x) { return x * sigmoidf_(x); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -1,19 +1,27 @@
 // Persistent, warp-specialised tcgen05 GEMM for sm_100a.
 //
-//   C[M,N] = epilogue( A[M,K] . B[N,K]^T )        A, B: K-major fp16/bf16, fp32 accumulate
+//   C[M,N] = epilogue( A[M,K] . B[N,K]^T )     A, B: K-major fp16 / bf16 / tf32, fp32 accumulate
 //
-// One CTA per SM loops over 128 x BN output tiles.
-//   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B swizzle, STAGES-deep mbarrier ring)
-//   warp 1      : MMA issuer    (one lane issues tcgen05.mma kind::f16, accumulators in TMEM,
-//                                two accumulator stages so the epilogue overlaps the next tile)
-//   warps 2..9  : epilogue      (tcgen05.ld -> registers -> bias / activation / residual -> HBM)
+// Two tile shapes share one kernel template:
+//   CTAS = 1 : one CTA per SM, 128 x BN tile (BN = 128 | 256), tcgen05.mma.cta_group::1
+//   CTAS = 2 : a CTA pair (cluster of 2, one TPC) owns a 256 x 256 tile: each CTA loads its own 128
+//              rows of A and HALF of the B tile, the leader issues tcgen05.mma.cta_group::2
+//              (M = 256) which reads both halves -- per-SM operand traffic from L2 drops by a third.
+// Roles per CTA:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B swizzle, mbarrier ring)
+//   warp 1      : MMA issuer    (one lane; accumulators in TMEM, two accumulator stages so the
+//                                epilogue of tile i overlaps the mainloop of tile i+1)
+//   warps 2..9  : epilogue      (tcgen05.ld -> per-warp swizzled smem transpose -> every global
+//                                access is a full 128-byte line: bias / GELU / ReLU / SwiGLU /
+//                                gate / LayerScale + residual RMW / fp32 addend / hi-lo split)
 //
-// This is the contraction engine behind every dense layer of the hot path:
-// the reference issues them as cuBLAS/ATen addmm calls from timm's ViT blocks
-// (reference: src/stamp/preprocessing/__init__.py:325) and from the MIL aggregator
-// (reference: src/stamp/modeling/models/vision_tranformer.py:137-139,153,163-167,314-318).
+// This is the contraction engine behind every dense layer of the hot path: the reference issues
+// them as cuBLAS/ATen addmm calls from timm's ViT blocks (src/stamp/preprocessing/__init__.py:325)
+// and from the MIL aggregator (src/stamp/modeling/models/vision_tranformer.py:137-139,153,163-167,
+// 314-318).
 #include "gemm.cuh"
 
+#include <cstdio>
 #include <mutex>
 
 #include "common.cuh"
@@ -22,177 +30,205 @@ namespace sb {
 
 namespace {
 
-constexpr int BM = 128;
-constexpr int BK_BYTES = 128;  // one 128-byte swizzle row of K per tile row: 64 x 16-bit or 32 x tf32
-constexpr int UMMA_K_BYTES = 32;  // K extent of one tcgen05.mma: 16 x 16-bit or 8 x tf32
+constexpr int BM = 128;            // rows of A per CTA
+constexpr int BK_BYTES = 128;      // one 128-byte swizzle row of K per tile row: 64 x 16-bit or 32 x tf32
+constexpr int UMMA_K_BYTES = 32;   // K extent of one tcgen05.mma: 16 x 16-bit or 8 x tf32
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per epilogue warp: one 32 x 32 fp32 block
 
-template <int BN>
+template <int BN, int CTAS>
 struct Cfg {
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int B_ROWS = BN / CTAS;  // rows of the B tile this CTA loads
     static constexpr int A_BYTES = BM * BK_BYTES;
-    static constexpr int B_BYTES = BN * BK_BYTES;
+    static constexpr int B_BYTES = B_ROWS * BK_BYTES;
+    static constexpr int STAGES = (A_BYTES + B_BYTES == 48 * 1024) ? 4 : 6;
     static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES;
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;
+    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + EPI_BYTES + BAR_BYTES + 1024;
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) {
     return __ldg(reinterpret_cast<const float4*>(p));
 }
 
-// Epilogue for 32 consecutive columns [n0, n0+32) of one output row.
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32],
-                                               int m, long long row, int n0) {
-    float v[32];
-    const bool full = (n0 + 32 <= p.N);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+// ---- cluster helpers (2-CTA mode) ------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cta2(uint32_t smem_dst, const CUtensorMap* tm,
+                                                 uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(smem_dst),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     smem_u32(smem_result)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_cta2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once) on the barrier at the same smem offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_cta2(uint64_t* bar) {
+    const uint16_t mask = 0x3;
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+        "[%0], %1;\n" ::"r"(smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+}
 
-    if (p.bias != nullptr) {
-        if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 b = ldg4(p.bias + n0 + j);
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
-        }
-    }
+// ---- epilogue for 4 consecutive columns [n, n+4) of output row `orow` (input row m) ------------
+// (slow path: only the ragged right edge of a matrix with N % 4 != 0 comes through here)
+// (inlined exactly once, in a non-unrolled loop: a real call would force the kernel parameter
+//  struct into local memory and turn every p.field read of the hot path into an LDL)
+__device__ __forceinline__ void epilogue4(const GemmParams& p, float4 acc, int m, long long orow, int n,
+                                          float4 bias4, float4 gamma4) {
+    float v[4] = {acc.x + bias4.x, acc.y + bias4.y, acc.z + bias4.z, acc.w + bias4.w};
+    const bool full = (n + 4 <= p.N);
     if (p.table != nullptr) {
         // fp32 addend applied BEFORE the activation: position table of the patch embedding, or the
         // running fp32 partial of a split-precision (hi + lo) product
-        const float* t = p.table + static_cast<long long>(p.gin > 0 ? (m % p.gin) : m) * p.ldt + n0;
+        const float* t = p.table + static_cast<long long>(p.gin > 0 ? (m % p.gin) : m) * p.ldt + n;
         if (full && ((reinterpret_cast<uintptr_t>(t) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 tt = ldg4(t + j);
-                v[j] += tt.x; v[j + 1] += tt.y; v[j + 2] += tt.z; v[j + 3] += tt.w;
-            }
+            const float4 tt = ldg4(t);
+            v[0] += tt.x; v[1] += tt.y; v[2] += tt.z; v[3] += tt.w;
         } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) v[j] += __ldg(t + j);
+            for (int j = 0; j < 4; ++j)
+                if (n + j < p.N) v[j] += __ldg(t + j);
         }
     }
     if (p.act == ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
     } else if (p.act == ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.0f);
     }
-
     const bool bf = p.bf16 != 0;
     switch (p.store) {
     case ST_16: {
-        uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + n0;
-        if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                uint4 w;
-                w.x = pack_16(v[j], v[j + 1], bf);
-                w.y = pack_16(v[j + 2], v[j + 3], bf);
-                w.z = pack_16(v[j + 4], v[j + 5], bf);
-                w.w = pack_16(v[j + 6], v[j + 7], bf);
-                *reinterpret_cast<uint4*>(o + j) = w;
-                if (p.out_lo != nullptr) {  // low half of a split-precision operand (fp16 only)
-                    const __half2* h = reinterpret_cast<const __half2*>(&w);
-                    uint4 lo;
-                    lo.x = pack_f16(v[j] - __low2float(h[0]), v[j + 1] - __high2float(h[0]));
-                    lo.y = pack_f16(v[j + 2] - __low2float(h[1]), v[j + 3] - __high2float(h[1]));
-                    lo.z = pack_f16(v[j + 4] - __low2float(h[2]), v[j + 5] - __high2float(h[2]));
-                    lo.w = pack_f16(v[j + 6] - __low2float(h[3]), v[j + 7] - __high2float(h[3]));
-                    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_lo) + row * p.ldo + n0 + j) = lo;
-                }
+        uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + orow * p.ldo + n;
+        if (full && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
+            uint2 w;
+            w.x = pack_16(v[0], v[1], bf);
+            w.y = pack_16(v[2], v[3], bf);
+            *reinterpret_cast<uint2*>(o) = w;
+            if (p.out_lo != nullptr) {  // low half of a split-precision operand (fp16 only)
+                const __half2* h = reinterpret_cast<const __half2*>(&w);
+                uint2 lo;
+                lo.x = pack_f16(v[0] - __low2float(h[0]), v[1] - __high2float(h[0]));
+                lo.y = pack_f16(v[2] - __low2float(h[1]), v[3] - __high2float(h[1]));
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_lo) + orow * p.ldo + n) = lo;
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) {
-                    uint32_t w = pack_16(v[j], 0.f, bf);
+            for (int j = 0; j < 4; ++j)
+                if (n + j < p.N) {
+                    const uint32_t w = pack_16(v[j], 0.f, bf);
                     o[j] = static_cast<uint16_t>(w & 0xFFFF);
+                    if (p.out_lo != nullptr) {
+                        const float hi = __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xFFFF)));
+                        reinterpret_cast<__half*>(p.out_lo)[orow * p.ldo + n + j] = __float2half_rn(v[j] - hi);
+                    }
                 }
         }
         break;
     }
     case ST_32: {
-        float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + n0;
+        float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + n;
         if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
         } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) o[j] = v[j];
+            for (int j = 0; j < 4; ++j)
+                if (n + j < p.N) o[j] = v[j];
         }
         break;
     }
     case ST_RESID32: {
-        float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + n0;
+        float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + n;
         if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 x = *reinterpret_cast<const float4*>(o + j);
-                float4 g = (p.gamma != nullptr) ? ldg4(p.gamma + n0 + j)
-                                                : make_float4(1.f, 1.f, 1.f, 1.f);
-                x.x = fmaf(g.x, v[j], x.x);
-                x.y = fmaf(g.y, v[j + 1], x.y);
-                x.z = fmaf(g.z, v[j + 2], x.z);
-                x.w = fmaf(g.w, v[j + 3], x.w);
-                *reinterpret_cast<float4*>(o + j) = x;
-            }
+            float4 x = *reinterpret_cast<const float4*>(o);
+            x.x = fmaf(gamma4.x, v[0], x.x);
+            x.y = fmaf(gamma4.y, v[1], x.y);
+            x.z = fmaf(gamma4.z, v[2], x.z);
+            x.w = fmaf(gamma4.w, v[3], x.w);
+            *reinterpret_cast<float4*>(o) = x;
         } else {
+            const float g[4] = {gamma4.x, gamma4.y, gamma4.z, gamma4.w};
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) {
-                    float g = (p.gamma != nullptr) ? __ldg(p.gamma + n0 + j) : 1.0f;
-                    o[j] = fmaf(g, v[j], o[j]);
-                }
+            for (int j = 0; j < 4; ++j)
+                if (n + j < p.N) o[j] = fmaf(g[j], v[j], o[j]);
         }
         break;
     }
     case ST_SWIGLU16:
     case ST_GATED16: {
-        float g[16];
+        float g0, g1;
         if (p.store == ST_SWIGLU16) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = silu(v[2 * j]) * v[2 * j + 1];
+            g0 = silu(v[0]) * v[1];
+            g1 = silu(v[2]) * v[3];
         } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = tanhf(v[2 * j]) * sigmoidf_(v[2 * j + 1]);
+            g0 = tanhf(v[0]) * sigmoidf_(v[1]);
+            g1 = tanhf(v[2]) * sigmoidf_(v[3]);
         }
-        uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + row * p.ldo + (n0 >> 1);
-        if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 8) {
-                uint4 w;
-                w.x = pack_16(g[j], g[j + 1], bf);
-                w.y = pack_16(g[j + 2], g[j + 3], bf);
-                w.z = pack_16(g[j + 4], g[j + 5], bf);
-                w.w = pack_16(g[j + 6], g[j + 7], bf);
-                *reinterpret_cast<uint4*>(o + j) = w;
-                if (p.out_lo != nullptr) {
-                    const __half2* h = reinterpret_cast<const __half2*>(&w);
-                    uint4 lo;
-                    lo.x = pack_f16(g[j] - __low2float(h[0]), g[j + 1] - __high2float(h[0]));
-                    lo.y = pack_f16(g[j + 2] - __low2float(h[1]), g[j + 3] - __high2float(h[1]));
-                    lo.z = pack_f16(g[j + 4] - __low2float(h[2]), g[j + 5] - __high2float(h[2]));
-                    lo.w = pack_f16(g[j + 6] - __low2float(h[3]), g[j + 7] - __high2float(h[3]));
-                    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out_lo) + row * p.ldo + (n0 >> 1) + j) = lo;
-                }
+        uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + orow * p.ldo + (n >> 1);
+        if (full) {
+            const uint32_t w = pack_16(g0, g1, bf);
+            *reinterpret_cast<uint32_t*>(o) = w;
+            if (p.out_lo != nullptr) {
+                const __half2 h = *reinterpret_cast<const __half2*>(&w);
+                *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.out_lo) + orow * p.ldo + (n >> 1)) =
+                    pack_f16(g0 - __low2float(h), g1 - __high2float(h));
             }
         } else {
+            const float g[2] = {g0, g1};
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (n0 + 2 * j + 1 < p.N) {
-                    uint32_t w = pack_16(g[j], 0.f, bf);
+            for (int j = 0; j < 2; ++j)
+                if (n + 2 * j + 1 < p.N) {
+                    const uint32_t w = pack_16(g[j], 0.f, bf);
                     o[j] = static_cast<uint16_t>(w & 0xFFFF);
+                    if (p.out_lo != nullptr) {
+                        const float hi = __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xFFFF)));
+                        reinterpret_cast<__half*>(p.out_lo)[orow * p.ldo + (n >> 1) + j] = __float2half_rn(g[j] - hi);
+                    }
                 }
         }
         break;
@@ -202,18 +238,20 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     }
 }
 
-template <int BN, bool TF32>
+template <int BN, bool TF32, int CTAS>
+// 10 warps: one SM sub-partition (16K registers) hosts 3 of them -> at most 168 registers per thread
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, CTAS>;
     extern __shared__ uint8_t smem_raw[];
-    // 128B swizzle needs 1024-byte aligned tiles
+    // 128B swizzle needs 1024-byte aligned tiles (identical offset in both CTAs of a pair)
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + C::STAGES * C::A_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * (C::A_BYTES + C::B_BYTES));
+    float* sEpi = reinterpret_cast<float*>(smem + C::STAGES * (C::A_BYTES + C::B_BYTES));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * (C::A_BYTES + C::B_BYTES) + C::EPI_BYTES);
     uint64_t* empty_bar = full_bar + C::STAGES;
     uint64_t* tfull_bar = empty_bar + C::STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -221,6 +259,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -233,51 +273,65 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], NUM_EPI_WARPS);
+            mbar_init(&tempty_bar[i], NUM_EPI_WARPS * CTAS);  // the leader hears both CTAs' epilogues
         }
         fence_barrier_init();
     }
     if (warp == 1) {
         __syncwarp();
-        tmem_alloc(tmem_slot, C::TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (CTAS == 2) { tmem_alloc2(tmem_slot, C::TMEM_COLS); tmem_relinquish2(); }
+        else { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_m = (p.M + BM - 1) / BM;
+    constexpr int BK = TF32 ? 32 : 64;  // elements of K per pipeline stage
+    constexpr int TILE_M = BM * CTAS;
+    const int num_m = (p.M + TILE_M - 1) / TILE_M;
     const int num_n = (p.N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
-    constexpr int BK = TF32 ? 32 : 64;  // elements of K per pipeline stage
     const int num_kb = (p.K + BK - 1) / BK;
+    const int first_tile = blockIdx.x / CTAS;
+    const int tile_step = gridDim.x / CTAS;
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = first_tile; t < num_tiles; t += tile_step) {
                 const int m_blk = t / num_n, n_blk = t % num_n;
+                const int row_a = m_blk * TILE_M + static_cast<int>(cta_rank) * BM;
+                const int row_b = n_blk * BN + static_cast<int>(cta_rank) * C::B_ROWS;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_expect_tx(&full_bar[stage], C::A_BYTES + C::B_BYTES);
-                    tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
-                    tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+                    if constexpr (CTAS == 2) {
+                        // both CTAs' bytes complete on the LEADER's barrier, which expects all of them
+                        const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+                        if (leader) mbar_expect_tx(&full_bar[stage], 2 * (C::A_BYTES + C::B_BYTES));
+                        tma_load_2d_cta2(smem_u32(sA + stage * C::A_BYTES), &tmA, lbar, kb * BK, row_a);
+                        tma_load_2d_cta2(smem_u32(sB + stage * C::B_BYTES), &tmB, lbar, kb * BK, row_b);
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], C::A_BYTES + C::B_BYTES);
+                        tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], kb * BK, row_a);
+                        tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], kb * BK, row_b);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------ MMA issuer --------------------------------
-        if (lane == 0) {
-            const uint32_t idesc = TF32 ? umma_idesc_tf32(BM, BN) : umma_idesc_f16(BM, BN, p.bf16 != 0, false, false);
+        // ------------------------------ MMA issuer (leader CTA) --------------------
+        if (lane == 0 && leader) {
+            const uint32_t idesc = TF32 ? umma_idesc_tf32(TILE_M, BN)
+                                        : umma_idesc_f16(TILE_M, BN, p.bf16 != 0, false, false);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = first_tile; t < num_tiles; t += tile_step) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -290,13 +344,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int k = 0; k < BK_BYTES / UMMA_K_BYTES; ++k) {
                         // advancing 32 B along K inside the swizzle row: +2 in the
                         // 16-byte-granular start-address field
-                        if constexpr (TF32)
-                            umma_tf32_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                        else
-                            umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                        if constexpr (CTAS == 2) umma_f16_ss_cta2(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accum);
+                        else if constexpr (TF32) umma_tf32_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accum);
+                        else umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accum);
                     }
-                    umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-                    if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+                    // smem slot reusable (in both CTAs) once these MMAs retire
+                    if constexpr (CTAS == 2) umma_commit_cta2(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+                    if (kb == num_kb - 1) {
+                        if constexpr (CTAS == 2) umma_commit_cta2(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -308,15 +365,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int quarter = warp & 3;      // TMEM lane quarter this warp may access
         const int chalf = ew >> 2;         // which half of the BN columns
         constexpr int COLS_PER_WARP = BN / 2;
+        float* stg = sEpi + ew * (EPI_STAGE_BYTES / 4);
+        const int seg = lane & 7;          // 16-byte column segment this lane owns when reading back
+        const int rsub = lane >> 3;        // row (mod 4) this lane owns when reading back
+        const uint32_t tempty_leader = (CTAS == 2) ? map_to_cta(smem_u32(&tempty_bar[0]), 0) : 0u;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int t = first_tile; t < num_tiles; t += tile_step) {
             const int m_blk = t / num_n, n_blk = t % num_n;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const int m = m_blk * BM + quarter * 32 + lane;
-            long long row = m;
-            if (p.gin > 0) row = static_cast<long long>(m / p.gin) * p.gout + p.goff + (m % p.gin);
+            const int m_base = m_blk * TILE_M + static_cast<int>(cta_rank) * BM + quarter * 32;
+            // output row offsets in elements (32-bit row index x ldo fits 63 bits; kept as
+            // row indices to save registers: the epilogue is right at the 168-register cap)
+            int orow[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int m = m_base + rsub + 4 * k;
+                orow[k] = (p.gin > 0) ? (m / p.gin) * p.gout + p.goff + (m % p.gin) : m;
+            }
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
             for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
@@ -326,20 +393,148 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(t_row + col, r);
                 tmem_ld_wait();
-                if (m < p.M) epilogue_chunk(p, r, m, row, n0);
+                // transpose through smem: lane = row writes 8 x 16 B, segment index XOR-swizzled by row
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int pj = j ^ (lane & 7);
+                    *reinterpret_cast<uint4*>(stg + lane * 32 + pj * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                }
+                __syncwarp();
+                const int n = n0 + seg * 4;
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), gamma4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (n + 4 <= p.N) {
+                    if (p.bias != nullptr) bias4 = ldg4(p.bias + n);
+                    if (p.gamma != nullptr) gamma4 = ldg4(p.gamma + n);
+                } else if (n < p.N) {
+                    float b[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {1.f, 1.f, 1.f, 1.f};
+                    for (int j = 0; j < 4; ++j)
+                        if (n + j < p.N) {
+                            if (p.bias != nullptr) b[j] = __ldg(p.bias + n + j);
+                            if (p.gamma != nullptr) g[j] = __ldg(p.gamma + n + j);
+                        }
+                    bias4 = make_float4(b[0], b[1], b[2], b[3]);
+                    gamma4 = make_float4(g[0], g[1], g[2], g[3]);
+                }
+                if (n + 4 <= p.N) {
+                    // fast path: this lane owns 4 full columns of 8 rows.  All loads of a phase are
+                    // issued before the first dependent use, mode dispatch happens once per chunk.
+                    float v[32];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int rl = rsub + 4 * k;  // row inside the 32 x 32 block
+                        const float4 t4 = *reinterpret_cast<const float4*>(stg + rl * 32 + ((seg ^ (rl & 7)) * 4));
+                        v[4 * k] = t4.x + bias4.x; v[4 * k + 1] = t4.y + bias4.y;
+                        v[4 * k + 2] = t4.z + bias4.z; v[4 * k + 3] = t4.w + bias4.w;
+                    }
+                    const int rows_valid = p.M - (m_base + rsub);   // row k valid iff 4k < rows_valid
+                    if (p.table != nullptr) {
+                        float4 tt[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int m = m_base + rsub + 4 * k;
+                            tt[k] = (4 * k < rows_valid)
+                                        ? ldg4(p.table + static_cast<long long>(p.gin > 0 ? (m % p.gin) : m) * p.ldt + n)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            v[4 * k] += tt[k].x; v[4 * k + 1] += tt[k].y; v[4 * k + 2] += tt[k].z; v[4 * k + 3] += tt[k].w;
+                        }
+                    }
+                    if (p.act == ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    } else if (p.act == ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                    }
+                    const bool bf = p.bf16 != 0;
+                    if (p.store == ST_RESID32) {
+                        float* o = reinterpret_cast<float*>(p.out) + n;
+                        float4 x[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (4 * k < rows_valid) x[k] = *reinterpret_cast<const float4*>(o + orow[k] * p.ldo);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (4 * k < rows_valid) {
+                                x[k].x = fmaf(gamma4.x, v[4 * k], x[k].x);
+                                x[k].y = fmaf(gamma4.y, v[4 * k + 1], x[k].y);
+                                x[k].z = fmaf(gamma4.z, v[4 * k + 2], x[k].z);
+                                x[k].w = fmaf(gamma4.w, v[4 * k + 3], x[k].w);
+                                *reinterpret_cast<float4*>(o + orow[k] * p.ldo) = x[k];
+                            }
+                    } else if (p.store == ST_16) {
+                        uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + n;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (4 * k < rows_valid) {
+                                uint2 w;
+                                w.x = pack_16(v[4 * k], v[4 * k + 1], bf);
+                                w.y = pack_16(v[4 * k + 2], v[4 * k + 3], bf);
+                                *reinterpret_cast<uint2*>(o + orow[k] * p.ldo) = w;
+                                if (p.out_lo != nullptr) {  // low half of a split-precision operand (fp16)
+                                    const __half2* h = reinterpret_cast<const __half2*>(&w);
+                                    uint2 lo;
+                                    lo.x = pack_f16(v[4 * k] - __low2float(h[0]), v[4 * k + 1] - __high2float(h[0]));
+                                    lo.y = pack_f16(v[4 * k + 2] - __low2float(h[1]), v[4 * k + 3] - __high2float(h[1]));
+                                    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.out_lo) + n + orow[k] * p.ldo) = lo;
+                                }
+                            }
+                    } else if (p.store == ST_32) {
+                        float* o = reinterpret_cast<float*>(p.out) + n;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (4 * k < rows_valid)
+                                *reinterpret_cast<float4*>(o + orow[k] * p.ldo) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                    } else {  // ST_SWIGLU16 / ST_GATED16: column pairs (x1, x2) -> one output
+                        uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + (n >> 1);
+                        const bool swiglu = p.store == ST_SWIGLU16;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (4 * k < rows_valid) {
+                                const float g0 = swiglu ? silu(v[4 * k]) * v[4 * k + 1] : tanhf(v[4 * k]) * sigmoidf_(v[4 * k + 1]);
+                                const float g1 = swiglu ? silu(v[4 * k + 2]) * v[4 * k + 3] : tanhf(v[4 * k + 2]) * sigmoidf_(v[4 * k + 3]);
+                                const uint32_t w = pack_16(g0, g1, bf);
+                                *reinterpret_cast<uint32_t*>(o + orow[k] * p.ldo) = w;
+                                if (p.out_lo != nullptr) {
+                                    const __half2 h = *reinterpret_cast<const __half2*>(&w);
+                                    *reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(p.out_lo) + (n >> 1) + orow[k] * p.ldo) =
+                                        pack_f16(g0 - __low2float(h), g1 - __high2float(h));
+                                }
+                            }
+                    }
+                } else if (n < p.N) {
+                    // ragged right edge (N % 4 != 0): generic scalar path, one row at a time
+                    // (not unrolled, and the row remap is recomputed: a dynamic index into orow[]
+                    //  would push that array into local memory for every path)
+#pragma unroll 1
+                    for (int k = 0; k < 8; ++k) {
+                        const int rl = rsub + 4 * k;
+                        const float4 t4 = *reinterpret_cast<const float4*>(stg + rl * 32 + ((seg ^ (rl & 7)) * 4));
+                        const int m = m_base + rl;
+                        const long long orow_k =
+                            (p.gin > 0) ? static_cast<long long>(m / p.gin) * p.gout + p.goff + (m % p.gin) : m;
+                        if (m < p.M) epilogue4(p, t4, m, orow_k, n, bias4, gamma4);
+                    }
+                }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if constexpr (CTAS == 2) mbar_arrive_cluster(tempty_leader + acc * 8);
+                else mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, C::TMEM_COLS);
+        if constexpr (CTAS == 2) tmem_dealloc2(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
     }
 }
 
@@ -369,38 +564,57 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, long long ld
               int kind /*0 fp16, 1 bf16, 2 fp32(tf32)*/) {
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) return SB_ERR_DRIVER;
-    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
     const int esz = (kind == 2) ? 4 : 2;
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
     cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * esz};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(BK_BYTES / esz), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     const CUtensorMapDataType dt = (kind == 2)   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                    : (kind == 1) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                                  : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    CUresult r = fn(tm, dt, 2,
-                    const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = fn(tm, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? SB_OK : SB_ERR_DRIVER;
 }
 
 int g_num_sms = 0;
+int g_force_mode = 0;  // 0 auto, 1 never use the 2-CTA kernel, 2 always (when legal): tests / tuning
 
-template <int BN, bool TF32>
+template <int BN, bool TF32, int CTAS>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int tiles,
            cudaStream_t stream) {
+    using C = Cfg<BN, CTAS>;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tn_kernel<BN, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg<BN>::SMEM_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute(gemm_tn_kernel<BN, TF32, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 C::SMEM_BYTES) != cudaSuccess)
             return SB_ERR_CUDA;
         configured = true;
     }
-    int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    const int units = g_num_sms / CTAS;  // CTAs (or CTA pairs) that fit the chip
+    const int grid = (tiles < units ? tiles : units) * CTAS;
     ProfScope prof(PROF_GEMM, 2.0 * p.M * static_cast<double>(p.N) * p.K, stream);
-    gemm_tn_kernel<BN, TF32><<<grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, TF32, CTAS>, tmA, tmB, p);
     count_launch();
-    return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+    if (e != cudaSuccess) {
+        fprintf(stderr, "stamp_b200: gemm_tn_kernel<%d,%d,%d> launch failed: %s (grid %d, smem %d)\n", BN,
+                static_cast<int>(TF32), CTAS, cudaGetErrorString(e), grid, C::SMEM_BYTES);
+        cudaGetLastError();
+    }
+    return e == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 
 }  // namespace
@@ -415,6 +629,8 @@ int gemm_num_sms() {
     return g_num_sms;
 }
 
+void gemm_force_mode(int mode) { g_force_mode = mode; }
+
 int gemm_tn(const void* A, long long lda, const void* B, long long ldb, const GemmParams& p,
             cudaStream_t stream) {
     if (p.M <= 0 || p.N <= 0 || p.K <= 0 || A == nullptr || B == nullptr || p.out == nullptr)
@@ -424,24 +640,35 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, const Ge
         (reinterpret_cast<uintptr_t>(B) & 15) != 0)
         return SB_ERR_BAD_ARG;
     if ((p.store == ST_SWIGLU16 || p.store == ST_GATED16) && (p.N % 2) != 0) return SB_ERR_BAD_ARG;
+    // the epilogue moves 4 columns per lane with vector accesses: 16-byte aligned bases, pitches % 4
+    auto misaligned = [](const void* q) { return q != nullptr && (reinterpret_cast<uintptr_t>(q) & 15) != 0; };
+    if ((p.ldo % 4) != 0 || misaligned(p.out) || misaligned(p.out_lo) || misaligned(p.bias) ||
+        misaligned(p.gamma) || misaligned(p.table) || (p.table != nullptr && (p.ldt % 4) != 0))
+        return SB_ERR_BAD_ARG;
     gemm_num_sms();
 
     const int num_m = (p.M + BM - 1) / BM;
-    // 128 x 256 tiles unless that leaves most SMs without a tile
     const int tiles256 = num_m * ((p.N + 255) / 256);
+    const int tiles128 = num_m * ((p.N + 127) / 128);
+    // CTA-pair tiles (256 x 256) once there are at least two waves of them; else single-CTA tiles,
+    // 128 x 256 unless that leaves most SMs without a tile
+    const int tiles_pair = ((p.M + 255) / 256) * ((p.N + 255) / 256);
+    bool use_pair = !p.tf32 && p.N >= 256 && tiles_pair >= 2 * (g_num_sms / 2);
+    if (g_force_mode == 1) use_pair = false;
+    if (g_force_mode == 2 && !p.tf32) use_pair = true;
     const bool use256 = (p.N >= 256) && (tiles256 >= g_num_sms);
-    const int bn = use256 ? 256 : 128;
+    const int bn = (use_pair || use256) ? 256 : 128;
 
-    CUtensorMap tmA, tmB;
     const int kind = p.tf32 ? 2 : (p.bf16 ? 1 : 0);
+    CUtensorMap tmA, tmB;
     int rc = make_tmap(&tmA, A, p.M, p.K, lda, BM, kind);
     if (rc != SB_OK) return rc;
-    rc = make_tmap(&tmB, B, p.N, p.K, ldb, bn, kind);
+    rc = make_tmap(&tmB, B, p.N, p.K, ldb, use_pair ? 128 : bn, kind);
     if (rc != SB_OK) return rc;
 
-    const int tiles128 = num_m * ((p.N + 127) / 128);
-    if (p.tf32) return use256 ? launch<256, true>(tmA, tmB, p, tiles256, stream) : launch<128, true>(tmA, tmB, p, tiles128, stream);
-    return use256 ? launch<256, false>(tmA, tmB, p, tiles256, stream) : launch<128, false>(tmA, tmB, p, tiles128, stream);
+    if (use_pair) return launch<256, false, 2>(tmA, tmB, p, tiles_pair, stream);
+    if (p.tf32) return use256 ? launch<256, true, 1>(tmA, tmB, p, tiles256, stream) : launch<128, true, 1>(tmA, tmB, p, tiles128, stream);
+    return use256 ? launch<256, false, 1>(tmA, tmB, p, tiles256, stream) : launch<128, false, 1>(tmA, tmB, p, tiles128, stream);
 }
 
 }  // namespace sb

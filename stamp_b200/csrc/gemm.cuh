@@ -45,3 +45,8 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, const Ge
 int gemm_num_sms();
 
 }  // namespace sb
+
+namespace sb {
+// 0 auto, 1 single-CTA tiles only, 2 CTA-pair (cta_group::2) tiles whenever legal
+void gemm_force_mode(int mode);
+}  // namespace sb

@@ -53,6 +53,32 @@ def test_gemm_tf32(cuda_device, M, N, K):
     assert _rel(x, ref) < 1e-5
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(300, 1024, 768), (257, 72 * 4, 200), (12608, 3072, 1024), (5000, 1024, 4096), (130, 256, 64)])
+def test_gemm_tile_shapes(cuda_device, M, N, K, mode):
+    """Same products through single-CTA tiles (mode 1) and CTA-pair cta_group::2 tiles (mode 2),
+    with the fp32 residual epilogue (LayerScale gamma) and the fp16 store."""
+    from stamp_b200 import _lib, ops
+
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(cuda_device, torch.float16)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(cuda_device, torch.float16)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    gamma = torch.rand(N, generator=g).to(cuda_device) + 0.5
+    ref = a.float() @ w.float().T + bias
+    _lib.load().stamp_b200_gemm_force_mode(mode)
+    try:
+        out = torch.full((M, N), float("nan"), device=cuda_device, dtype=torch.float16)
+        ops.gemm_tn(a, w, out=out, bias=bias)
+        x = torch.ones(M, N, device=cuda_device)
+        ops.gemm_tn(a, w, out=x, bias=bias, gamma=gamma, store=ops.ST_RESID32)
+    finally:
+        _lib.load().stamp_b200_gemm_force_mode(0)
+    assert torch.isfinite(out).all()
+    assert _rel(out.float(), ref) < 2e-3
+    assert _rel(x, 1.0 + gamma * ref) < 1e-5
+
+
 def test_gemm_epilogues(cuda_device):
     from stamp_b200 import ops
 
