@@ -26,6 +26,7 @@ SIGNATURES: dict[str, tuple] = {
     "stamp_b200_profile_summary": (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double),
                                            C.POINTER(C.c_longlong), c_int]),
     "stamp_b200_gemm_force_mode": (None, [c_int]),
+    "stamp_b200_attention_tc_enable": (None, [c_int]),
     "stamp_gemm_tn": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_int,
                               c_int, c_void_p]),

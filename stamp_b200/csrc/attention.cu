@@ -401,6 +401,11 @@ int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream) {
     if (static_cast<long long>(p.B) * p.H > 2147483647LL || (p.S + BQ - 1) / BQ > 65535) return SB_ERR_UNSUPPORTED;
     if ((p.row_stride % 8) != 0 || (p.batch_stride % 8) != 0 || (p.v_row_stride % 8) != 0 || (p.v_batch_stride % 8) != 0 || (p.out_row_stride % 2) != 0)
         return SB_ERR_BAD_ARG;
+    // short unmasked sequences (ViT tiles): tcgen05 kernel; anything else: the general kernel below
+    {
+        const int rc = attention_tc_fwd(p, head_dim, stream);
+        if (rc != SB_ERR_UNSUPPORTED) return rc;
+    }
     const bool alibi = p.coords != nullptr;
     if (alibi && (p.slope == nullptr || p.dscale == nullptr)) return SB_ERR_BAD_ARG;
     if (head_dim == 64) return alibi ? launch_attn<64, true>(p, stream) : launch_attn<64, false>(p, stream);

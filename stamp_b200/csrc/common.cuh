@@ -179,6 +179,17 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "r"(taddr)
         : "memory");
 }
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
@@ -314,9 +325,17 @@ __device__ __forceinline__ float erf_as(float x) {
     return copysignf(1.0f - erfc_as_pos(fabsf(x)), x);
 }
 // exact-erf GELU: 0.5 x (1 + erf(x / sqrt 2)) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2)
+// (constants of erfc_as_pos folded: z = |x|/sqrt2, the 0.5 factor inside the polynomial)
 __device__ __forceinline__ float gelu_erf(float x) {
     const float ax = fabsf(x);
-    return fmaxf(x, 0.0f) - 0.5f * ax * erfc_as_pos(ax * 0.70710678118654752f);
+    const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
+    float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+    p = fmaf(p, t, 0.5f * 1.421413741f);
+    p = fmaf(p, t, 0.5f * -0.284496736f);
+    p = fmaf(p, t, 0.5f * 0.254829592f);
+    p *= t;
+    const float e = ex2_approx(ax * ax * (-0.5f * 1.4426950408889634f));
+    return fmaxf(x, 0.0f) - ax * p * e;
 }
 __device__ __forceinline__ float sigmoidf_(float x) {
     return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f));

@@ -69,8 +69,11 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local), "r"(rank));
     return r;
 }
+// relaxed: the only thing the leader's MMA thread must observe is that this warp's tcgen05.ld of
+// the accumulator stage completed (tcgen05.wait::ld + tcgen05.fence before this arrive); a
+// cluster-scope release would additionally wait for all of the warp's outstanding global stores
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr)
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr)
                  : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_cta2(uint32_t smem_dst, const CUtensorMap* tm,
@@ -577,6 +580,26 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int rows, int cols, long long ld
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? SB_OK : SB_ERR_DRIVER;
 }
+
+}  // namespace
+
+// fp16 [batches][rows][inner] view with zero fill outside `rows`: per-(bag, head) Q/K/V tiles of the
+// tcgen05 attention (attention_tc.cu); 128-byte swizzle, box = {box_inner, box_rows, 1}
+int make_tmap_3d_f16(CUtensorMap* tm, const void* ptr, int inner, int rows, int batches,
+                     long long row_stride, long long batch_stride, int box_inner, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return SB_ERR_DRIVER;
+    cuuint64_t gdim[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batches)};
+    cuuint64_t gstr[2] = {static_cast<cuuint64_t>(row_stride) * 2, static_cast<cuuint64_t>(batch_stride) * 2};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SB_OK : SB_ERR_DRIVER;
+}
+
+namespace {
 
 int g_num_sms = 0;
 int g_force_mode = 0;  // 0 auto, 1 never use the 2-CTA kernel, 2 always (when legal): tests / tuning

@@ -50,3 +50,9 @@ namespace sb {
 // 0 auto, 1 single-CTA tiles only, 2 CTA-pair (cta_group::2) tiles whenever legal
 void gemm_force_mode(int mode);
 }  // namespace sb
+
+namespace sb {
+// fp16 [batches][rows][inner] tensor map, 128B swizzle, zero fill outside `rows` (gemm.cu)
+int make_tmap_3d_f16(CUtensorMap* tm, const void* ptr, int inner, int rows, int batches,
+                     long long row_stride, long long batch_stride, int box_inner, int box_rows);
+}  // namespace sb

@@ -244,6 +244,25 @@ def test_attention_mask_mode2(cuda_device):
     assert _rel(out.float(), ref) < 2e-3
 
 
+@pytest.mark.parametrize("B,S,H", [(2, 16, 2), (3, 100, 3), (2, 128, 2), (2, 129, 2), (5, 197, 16), (2, 256, 4), (1, 7, 1)])
+def test_attention_tcgen05_vs_general(cuda_device, B, S, H):
+    """Short unmasked head_dim-64 sequences take the tcgen05 kernel; same result as the general one."""
+    from stamp_b200 import _lib, ops
+
+    g = torch.Generator(device="cpu").manual_seed(S * 3 + H)
+    qkv = torch.randn(B, S, 3 * H * 64, generator=g).to(cuda_device, torch.float16)
+    ref = _attn_ref(qkv, H)
+    out_tc = ops.attention(qkv, H)
+    _lib.load().stamp_b200_attention_tc_enable(0)
+    try:
+        out_gen = ops.attention(qkv, H)
+    finally:
+        _lib.load().stamp_b200_attention_tc_enable(1)
+    assert torch.isfinite(out_tc).all()
+    assert _rel(out_tc.float(), ref) < 2e-3
+    assert _rel(out_gen.float(), ref) < 2e-3
+
+
 def test_launch_counter(cuda_device):
     from stamp_b200 import _lib, ops
 
