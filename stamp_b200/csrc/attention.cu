@@ -406,6 +406,11 @@ int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream) {
         const int rc = attention_tc_fwd(p, head_dim, stream);
         if (rc != SB_ERR_UNSUPPORTED) return rc;
     }
+    // long unmasked bags (MIL aggregator, plain or ALiBi): tcgen05 two-pass kernel
+    {
+        const int rc = attention_mil_tc_fwd(p, head_dim, stream);
+        if (rc != SB_ERR_UNSUPPORTED) return rc;
+    }
     const bool alibi = p.coords != nullptr;
     if (alibi && (p.slope == nullptr || p.dscale == nullptr)) return SB_ERR_BAD_ARG;
     if (head_dim == 64) return alibi ? launch_attn<64, true>(p, stream) : launch_attn<64, false>(p, stream);

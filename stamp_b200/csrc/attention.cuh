@@ -33,6 +33,9 @@ int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 // tcgen05 path for short unmasked sequences (attention_tc.cu); SB_ERR_UNSUPPORTED = not applicable
 int attention_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 void attention_tc_enable(int on);
+// tcgen05 two-pass kernel for long unmasked bags, plain or ALiBi (attention_mil_tc.cu)
+int attention_mil_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
+void attention_mil_tc_enable(int on);
 
 int alibi_dist_scale(const float* coords, const float* slope, int B, int S, int H, float* dscale,
                      cudaStream_t stream);

@@ -1,0 +1,370 @@
+// tcgen05 attention for long feature bags (the MIL aggregator: S = 4097 ... 50001 tokens, head_dim 64).
+//
+//   plain : O = softmax(Q K^T * scale) V
+//   ALiBi : O = softmax(Q K^T * scale) V  -  c_h * Dist V          (bias subtracted AFTER the softmax,
+//           src/stamp/modeling/models/vision_tranformer.py:58-72; Dist recomputed from the [S,2] coordinates)
+//
+// One CTA = 128 query rows of one (bag, head); key/value tiles of 128 rows stream through a 2-stage
+// TMA ring.  Two passes over the keys instead of an online softmax:
+//   pass 1 : S = Q K^T on tcgen05 (double-buffered in TMEM), each softmax thread (= query row = TMEM
+//            lane) takes the running max of its row straight from TMEM -- no exp, no shuffles;
+//   pass 2 : S again; P = exp2(s*scale - m) and D = c_h*|x_q - x_k| are written as fp16 in the
+//            K-major 128B-swizzled UMMA layout; O1 += P V and O2 += D V accumulate in TMEM for the
+//            whole pass (the max is final, so the accumulators never need rescaling); the row sum l
+//            accumulates in a register.  O = O1 / l - O2.
+//   warp 0 TMA, warp 1 MMA issue, warps 2-5 softmax.  TMEM: S0 | S1 | O1 | O2 = 384 of 512 columns.
+// Costs 4 tensor-core units (2 x QK^T, PV, DV) against the reference's 2, but only one exp and one
+// sqrt per (query, key) pair -- the MUFU pipe, not the tensor core, bounds this kernel.
+#include <math.h>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace sb {
+namespace {
+
+constexpr int MT_THREADS = 192;
+constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 halfs
+
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t addr, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};\n" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;\n" : "=f"(r) : "f"(x));
+    return r;
+}
+
+struct MtSmem {
+    static constexpr int off_q = 0;
+    static constexpr int off_k = TILE_BYTES;                 // 2 stages
+    static constexpr int off_v = off_k + 2 * TILE_BYTES;     // 2 stages
+    static constexpr int off_p = off_v + 2 * TILE_BYTES;     // 2 x 64-key blocks
+    static constexpr int off_d = off_p + 2 * TILE_BYTES;     // 2 x 64-key blocks
+    static constexpr int off_c = off_d + 2 * TILE_BYTES;     // key coordinates, 2 x 128 float2
+    static constexpr int off_bar = off_c + 2 * 128 * 8;
+    static constexpr int total = off_bar + 128 + 1024;
+};
+
+template <bool ALIBI>
+__global__ void __launch_bounds__(MT_THREADS, 1)
+mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_v,
+                   const AttnParams p, int k_col0) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* sQ = smem + MtSmem::off_q;
+    uint8_t* sK = smem + MtSmem::off_k;
+    uint8_t* sV = smem + MtSmem::off_v;
+    uint8_t* sP = smem + MtSmem::off_p;
+    uint8_t* sD = smem + MtSmem::off_d;
+    float2* sC = reinterpret_cast<float2*>(smem + MtSmem::off_c);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MtSmem::off_bar);
+    uint64_t* kfull = bars;        // [2] TMA -> MMA
+    uint64_t* kempty = bars + 2;   // [2] MMA -> TMA
+    uint64_t* sfull = bars + 4;    // [2] MMA -> softmax   (S tile in TMEM)
+    uint64_t* sempty = bars + 6;   // [2] softmax -> MMA
+    uint64_t* pfull = bars + 8;    // softmax -> MMA       (P/D tiles in smem)
+    uint64_t* pempty = bars + 9;   // MMA -> softmax
+    uint64_t* ofull = bars + 10;
+    uint64_t* qfull = bars + 11;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+    const int q0 = blockIdx.y * 128;
+    const int S = p.S;
+    const int nkt = (S + 127) / 128;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_qk);
+        tma_prefetch_desc(&tm_v);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kfull[i], 1);
+            mbar_init(&kempty[i], 1);
+            mbar_init(&sfull[i], 1);
+            mbar_init(&sempty[i], 4);
+        }
+        mbar_init(pfull, 4);
+        mbar_init(pempty, 1);
+        mbar_init(ofull, 1);
+        mbar_init(qfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    constexpr uint32_t COL_O1 = 256, COL_O2 = 320;
+
+    if (warp == 0) {
+        // ------------------------------------ TMA producer ------------------------------------
+        if (lane == 0) {
+            mbar_expect_tx(qfull, TILE_BYTES);
+            tma_load_3d(sQ, &tm_qk, qfull, h * 64, q0, b);
+            int it = 0;
+            for (int pass = 0; pass < 2; ++pass)
+                for (int kt = 0; kt < nkt; ++kt, ++it) {
+                    const int s = it & 1;
+                    mbar_wait(&kempty[s], ((it >> 1) & 1) ^ 1);
+                    mbar_expect_tx(&kfull[s], pass == 0 ? TILE_BYTES : 2 * TILE_BYTES);
+                    tma_load_3d(sK + s * TILE_BYTES, &tm_qk, &kfull[s], k_col0 + h * 64, kt * 128, b);
+                    if (pass == 1) tma_load_3d(sV + s * TILE_BYTES, &tm_v, &kfull[s], h * 64, kt * 128, b);
+                }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------ MMA issuer --------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc_s = umma_idesc_f16(128, 128, false, false, false);
+            const uint32_t idesc_o = umma_idesc_f16(128, 64, false, false, true);  // V: MN-major B
+            const uint64_t q_desc = umma_desc_k128(smem_u32(sQ));
+            mbar_wait(qfull, 0);
+            int is = 0;  // S tiles issued so far (both passes)
+            auto issue_s = [&]() {
+                const int s = is & 1;
+                const uint32_t ph = (is >> 1) & 1;
+                mbar_wait(&kfull[s], ph);
+                mbar_wait(&sempty[s], ph ^ 1);
+                tc_fence_after();
+                const uint64_t k_desc = umma_desc_k128(smem_u32(sK + s * TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16_ss(tmem + s * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+                umma_commit(&sfull[s]);
+                ++is;
+            };
+            // pass 1: row maxima only -- the K stage is free as soon as S is computed
+            for (int kt = 0; kt < nkt; ++kt) {
+                const int s = is & 1;
+                issue_s();
+                umma_commit(&kempty[s]);
+            }
+            // pass 2: S(kt+1) is issued before waiting for the P/D tiles of kt
+            issue_s();
+            for (int kt = 0; kt < nkt; ++kt) {
+                if (kt + 1 < nkt) issue_s();
+                const int s = (nkt + kt) & 1;  // K/V stage of tile kt in pass 2
+                mbar_wait(pfull, kt & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t v_desc = umma_desc_mn128(smem_u32(sV + s * TILE_BYTES + k * 2048), 0);
+                    const uint64_t p_desc = umma_desc_k128(smem_u32(sP + (k >> 2) * TILE_BYTES)) + 2 * (k & 3);
+                    umma_f16_ss(tmem + COL_O1, p_desc, v_desc, idesc_o, (kt | k) != 0);
+                    if constexpr (ALIBI) {
+                        const uint64_t d_desc = umma_desc_k128(smem_u32(sD + (k >> 2) * TILE_BYTES)) + 2 * (k & 3);
+                        umma_f16_ss(tmem + COL_O2, d_desc, v_desc, idesc_o, (kt | k) != 0);
+                    }
+                }
+                umma_commit(pempty);
+                umma_commit(&kempty[s]);
+            }
+            umma_commit(ofull);
+        }
+    } else {
+        // ------------------------ softmax: thread <-> query row <-> TMEM lane ------------------
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const int st = threadIdx.x - 64;   // 0..127 among the softmax threads
+        const int row = q0 + r;
+        const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
+        const float sl2 = p.scale_log2;
+        const uint32_t sC_addr = smem_u32(sC), sP_addr = smem_u32(sP), sD_addr = smem_u32(sD);
+        int ic = 0;  // S tiles consumed so far (both passes)
+
+        // ---- pass 1: exact row max ----
+        float mx = -INFINITY;
+        for (int kt = 0; kt < nkt; ++kt, ++ic) {
+            const int s = ic & 1;
+            mbar_wait(&sfull[s], (ic >> 1) & 1);
+            tc_fence_after();
+            const int kv_valid = min(128, S - kt * 128);
+#pragma unroll
+            for (int c = 0; c < 4; c += 2) {
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32b_x32(t_lane + s * 128 + c * 32, v0);
+                tmem_ld_32x32b_x32(t_lane + s * 128 + (c + 1) * 32, v1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (c * 32 + j < kv_valid) mx = fmaxf(mx, __uint_as_float(v0[j]));
+                    if ((c + 1) * 32 + j < kv_valid) mx = fmaxf(mx, __uint_as_float(v1[j]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sempty[s]);
+        }
+        const float ms = mx * sl2;
+
+        // ---- pass 2: P, D tiles -> smem, l in a register ----
+        float2 cq = make_float2(0.f, 0.f);
+        float slope = 0.f, descale = 1.f;
+        const float2* cb = nullptr;
+        if constexpr (ALIBI) {
+            cb = reinterpret_cast<const float2*>(p.coords) + static_cast<long long>(b) * S;
+            if (row < S) cq = __ldg(cb + row);
+            slope = __ldg(p.slope + h) * __ldg(p.dscale + 2 * b);
+            descale = __ldg(p.dscale + 2 * b + 1);
+        }
+        float l = 0.f;
+        for (int kt = 0; kt < nkt; ++kt, ++ic) {
+            const int s = ic & 1;
+            const int kv_valid = min(128, S - kt * 128);
+            if constexpr (ALIBI) {
+                const int key = kt * 128 + st;
+                sts_f2(sC_addr + ((kt & 1) * 128 + st) * 8, (key < S) ? __ldg(cb + key) : make_float2(0.f, 0.f));
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            }
+            mbar_wait(&sfull[s], (ic >> 1) & 1);
+            mbar_wait(pempty, (kt & 1) ^ 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(t_lane + s * 128 + c * 32, v);
+                tmem_ld_wait();
+                uint32_t pw[16], dw[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float pv[2], dv[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int kl = c * 32 + j + e;
+                        const bool valid = kl < kv_valid;
+                        pv[e] = valid ? ex2_approx(fmaf(__uint_as_float(v[j + e]), sl2, -ms)) : 0.f;
+                        l += pv[e];
+                        if constexpr (ALIBI) {
+                            const float2 ck = lds_f2(sC_addr + ((kt & 1) * 128 + kl) * 8);
+                            const float dx = cq.x - ck.x, dy = cq.y - ck.y;
+                            dv[e] = valid ? sqrt_approx(fmaf(dx, dx, dy * dy)) * slope : 0.f;
+                        }
+                    }
+                    pw[j >> 1] = pack_f16(pv[0], pv[1]);
+                    if constexpr (ALIBI) dw[j >> 1] = pack_f16(dv[0], dv[1]);
+                }
+                // 32 keys = four 16-byte chunks of row r inside 64-key block c / 2
+                const uint32_t pb = sP_addr + (c >> 1) * TILE_BYTES + r * 128;
+                const uint32_t db = sD_addr + (c >> 1) * TILE_BYTES + r * 128;
+                const int ch0 = (c & 1) * 4;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int off = ((ch0 + q) ^ (r & 7)) * 16;
+                    sts_u4(pb + off, make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]));
+                    if constexpr (ALIBI)
+                        sts_u4(db + off, make_uint4(dw[4 * q], dw[4 * q + 1], dw[4 * q + 2], dw[4 * q + 3]));
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(pfull);
+                mbar_arrive(&sempty[s]);
+            }
+        }
+
+        // ---- epilogue: O = O1 / l - descale * O2 ----
+        mbar_wait(ofull, 0);
+        tc_fence_after();
+        const float inv = 1.0f / l;
+        const long long obase = b * p.out_batch_stride + static_cast<long long>(row) * p.out_row_stride + h * 64;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            uint32_t o1[32], o2[32];
+            tmem_ld_32x32b_x32(t_lane + COL_O1 + c * 32, o1);
+            if constexpr (ALIBI) tmem_ld_32x32b_x32(t_lane + COL_O2 + c * 32, o2);
+            tmem_ld_wait();
+            if (row < S) {
+                float y[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    y[j] = __uint_as_float(o1[j]) * inv;
+                    if constexpr (ALIBI) y[j] = fmaf(-descale, __uint_as_float(o2[j]), y[j]);
+                }
+                if (p.out_f32) {
+                    float* of = reinterpret_cast<float*>(p.out) + obase + c * 32;
+                    float* ol = (p.out_lo != nullptr) ? p.out_lo + obase + c * 32 : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 hi = make_float4(round_tf32(y[j]), round_tf32(y[j + 1]), round_tf32(y[j + 2]), round_tf32(y[j + 3]));
+                        *reinterpret_cast<float4*>(of + j) = hi;
+                        if (ol != nullptr)
+                            *reinterpret_cast<float4*>(ol + j) = make_float4(round_tf32(y[j] - hi.x), round_tf32(y[j + 1] - hi.y),
+                                                                             round_tf32(y[j + 2] - hi.z), round_tf32(y[j + 3] - hi.w));
+                    }
+                } else {
+                    __half* oh = reinterpret_cast<__half*>(p.out) + obase + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8)
+                        *reinterpret_cast<uint4*>(oh + j) = make_uint4(pack_f16(y[j], y[j + 1]), pack_f16(y[j + 2], y[j + 3]),
+                                                                       pack_f16(y[j + 4], y[j + 5]), pack_f16(y[j + 6], y[j + 7]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+template <bool ALIBI>
+int launch_mil(const CUtensorMap& tm_qk, const CUtensorMap& tm_v, const AttnParams& p, int k_col0, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(mil_attn_tc_kernel<ALIBI>, cudaFuncAttributeMaxDynamicSharedMemorySize, MtSmem::total) != cudaSuccess)
+            return SB_ERR_CUDA;
+        configured = true;
+    }
+    dim3 grid(p.B * p.H, (p.S + 127) / 128);
+    ProfScope prof(PROF_ATTN, 4.0 * p.B * p.H * static_cast<double>(p.S) * p.S * 64, stream);
+    mil_attn_tc_kernel<ALIBI><<<grid, MT_THREADS, MtSmem::total, stream>>>(tm_qk, tm_v, p, k_col0);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+int g_mil_tc_enabled = 1;
+
+}  // namespace
+
+void attention_mil_tc_enable(int on) { g_mil_tc_enabled = on; }
+
+// SB_ERR_UNSUPPORTED: outside this kernel's envelope (masked calls, head_dim != 64, short
+// sequences that the single-pass kernel covers) -> the caller uses the general kernel
+int attention_mil_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream) {
+    if (!g_mil_tc_enabled || head_dim != 64 || p.mask != nullptr || p.S <= 256) return SB_ERR_UNSUPPORTED;
+    const long long koff = p.k - p.q;
+    const long long v_rs = p.v_row_stride ? p.v_row_stride : p.row_stride;
+    const long long v_bs = p.v_row_stride ? p.v_batch_stride : p.batch_stride;
+    if (koff < 0 || koff + static_cast<long long>(p.H) * 64 > p.row_stride || (koff % 8) != 0 ||
+        (reinterpret_cast<uintptr_t>(p.q) & 15) != 0 || (reinterpret_cast<uintptr_t>(p.v) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(p.out) & 15) != 0 || (p.out_row_stride % 8) != 0 ||
+        static_cast<long long>(p.H) * 64 > v_rs || (p.S + 127) / 128 > 65535)
+        return SB_ERR_UNSUPPORTED;
+    const bool alibi = p.coords != nullptr;
+    if (alibi != (p.out_f32 != 0)) return SB_ERR_UNSUPPORTED;
+    CUtensorMap tm_qk, tm_v;
+    int rc = make_tmap_3d_f16(&tm_qk, p.q, static_cast<int>(p.row_stride), p.S, p.B, p.row_stride, p.batch_stride, 64, 128);
+    if (rc != SB_OK) return rc;
+    rc = make_tmap_3d_f16(&tm_v, p.v, static_cast<int>(v_rs), p.S, p.B, v_rs, v_bs, 64, 128);
+    if (rc != SB_OK) return rc;
+    return alibi ? launch_mil<true>(tm_qk, tm_v, p, static_cast<int>(koff), stream)
+                 : launch_mil<false>(tm_qk, tm_v, p, static_cast<int>(koff), stream);
+}
+
+}  // namespace sb

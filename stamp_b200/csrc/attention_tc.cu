@@ -166,13 +166,13 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 l += p[j];
             }
             const int blk = key0 >> 6;
-            uint8_t* pb = (blk == 0) ? sK : (blk == 3 ? sQ : sP12 + (blk - 1) * P_BLOCK_BYTES);
+            const uint32_t pb = smem_u32((blk == 0) ? sK : (blk == 3 ? sQ : sP12 + (blk - 1) * P_BLOCK_BYTES));
             const int ch0 = (key0 & 63) >> 3;
             uint4 w0, w1;
             w0.x = pack_f16(p[0], p[1]);  w0.y = pack_f16(p[2], p[3]);  w0.z = pack_f16(p[4], p[5]);  w0.w = pack_f16(p[6], p[7]);
             w1.x = pack_f16(p[8], p[9]);  w1.y = pack_f16(p[10], p[11]); w1.z = pack_f16(p[12], p[13]); w1.w = pack_f16(p[14], p[15]);
-            *reinterpret_cast<uint4*>(pb + r * 128 + ((ch0 ^ (r & 7)) * 16)) = w0;
-            *reinterpret_cast<uint4*>(pb + r * 128 + (((ch0 + 1) ^ (r & 7)) * 16)) = w1;
+            sts_v4(pb + r * 128 + ((ch0 ^ (r & 7)) * 16), w0);
+            sts_v4(pb + r * 128 + (((ch0 + 1) ^ (r & 7)) * 16), w1);
         };
         for (int c = 0; c < n32; c += 2) {
             uint32_t v0[32], v1[32];

@@ -34,7 +34,10 @@ long long stamp_b200_launch_count(void) { return sb::g_launches.load(std::memory
 void stamp_b200_reset_launch_count(void) { sb::g_launches.store(0, std::memory_order_relaxed); }
 
 void stamp_b200_gemm_force_mode(int mode) { sb::gemm_force_mode(mode); }
-void stamp_b200_attention_tc_enable(int on) { sb::attention_tc_enable(on); }
+void stamp_b200_attention_tc_enable(int on) {
+    sb::attention_tc_enable(on);
+    sb::attention_mil_tc_enable(on);
+}
 
 int stamp_gemm_tn(const void* A, long long lda, const void* W, long long ldw, void* out,
                   long long ldo, int M, int N, int K, const float* bias, const float* gamma,

@@ -45,6 +45,18 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// explicit shared-space accesses (32-bit shared addresses): dynamic smem carved from an integer-
+// aligned base pointer otherwise compiles to generic LD.E / ST.E
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ float4 lds_v4f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 // ----------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------
@@ -72,12 +84,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+    // with a suspend-time hint the hardware parks the waiting thread instead of letting it spin:
+    // the single-thread TMA / MMA roles otherwise burn the issue slots of their SM sub-partition
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }

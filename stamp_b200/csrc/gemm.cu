@@ -368,7 +368,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int quarter = warp & 3;      // TMEM lane quarter this warp may access
         const int chalf = ew >> 2;         // which half of the BN columns
         constexpr int COLS_PER_WARP = BN / 2;
-        float* stg = sEpi + ew * (EPI_STAGE_BYTES / 4);
+        const uint32_t stg = smem_u32(sEpi) + ew * EPI_STAGE_BYTES;  // shared-space byte address
         const int seg = lane & 7;          // 16-byte column segment this lane owns when reading back
         const int rsub = lane >> 3;        // row (mod 4) this lane owns when reading back
         const uint32_t tempty_leader = (CTAS == 2) ? map_to_cta(smem_u32(&tempty_bar[0]), 0) : 0u;
@@ -400,7 +400,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int pj = j ^ (lane & 7);
-                    *reinterpret_cast<uint4*>(stg + lane * 32 + pj * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    sts_v4(stg + lane * 128 + pj * 16, make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
                 }
                 __syncwarp();
                 const int n = n0 + seg * 4;
@@ -425,7 +425,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int rl = rsub + 4 * k;  // row inside the 32 x 32 block
-                        const float4 t4 = *reinterpret_cast<const float4*>(stg + rl * 32 + ((seg ^ (rl & 7)) * 4));
+                        const float4 t4 = lds_v4f(stg + rl * 128 + ((seg ^ (rl & 7)) * 16));
                         v[4 * k] = t4.x + bias4.x; v[4 * k + 1] = t4.y + bias4.y;
                         v[4 * k + 2] = t4.z + bias4.z; v[4 * k + 3] = t4.w + bias4.w;
                     }
@@ -514,7 +514,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
                     for (int k = 0; k < 8; ++k) {
                         const int rl = rsub + 4 * k;
-                        const float4 t4 = *reinterpret_cast<const float4*>(stg + rl * 32 + ((seg ^ (rl & 7)) * 4));
+                        const float4 t4 = lds_v4f(stg + rl * 128 + ((seg ^ (rl & 7)) * 16));
                         const int m = m_base + rl;
                         const long long orow_k =
                             (p.gin > 0) ? static_cast<long long>(m / p.gin) * p.gout + p.goff + (m % p.gin) : m;

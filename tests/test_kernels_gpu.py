@@ -263,6 +263,33 @@ def test_attention_tcgen05_vs_general(cuda_device, B, S, H):
     assert _rel(out_gen.float(), ref) < 2e-3
 
 
+@pytest.mark.parametrize("S", [257, 1000, 4097])
+@pytest.mark.parametrize("alibi", [False, True])
+def test_attention_long_bag_tcgen05_vs_general(cuda_device, S, alibi):
+    """Unmasked long bags take the two-pass tcgen05 kernel (plain and ALiBi); both kernels vs fp64."""
+    from stamp_b200 import _lib, ops
+
+    B, H = 2, 8
+    g = torch.Generator(device="cpu").manual_seed(S + alibi)
+    qkv = torch.randn(B, S, 3 * H * 64, generator=g).to(cuda_device, torch.float16)
+    coords = slope = None
+    if alibi:
+        coords = (torch.randint(0, 100, (B, S, 2), generator=g).float() * 256.0).to(cuda_device)
+        coords[:, 0] = 0
+        slope = torch.rand(H, generator=g).to(cuda_device)
+    ref = _attn_ref(qkv, H, coords, slope)
+    out_tc = ops.attention(qkv, H, coords=coords, slope=slope)
+    _lib.load().stamp_b200_attention_tc_enable(0)
+    try:
+        out_gen = ops.attention(qkv, H, coords=coords, slope=slope)
+    finally:
+        _lib.load().stamp_b200_attention_tc_enable(1)
+    assert torch.isfinite(out_tc).all()
+    tol = 1e-3 if alibi else 2e-3
+    assert _rel(out_tc.float(), ref) < tol, _rel(out_tc.float(), ref)
+    assert _rel(out_gen.float(), ref) < tol
+
+
 def test_launch_counter(cuda_device):
     from stamp_b200 import _lib, ops
 
