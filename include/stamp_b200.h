@@ -195,12 +195,13 @@ typedef struct {
 typedef struct {
     const float *ln1_w, *ln1_b;              /* layers.l.0.norm */
     const void* qkv_w; const float* qkv_b;   /* fp16 [3d, d]: rows = q heads | k heads | v heads */
-    const void* v_w_lo;                      /* ALiBi: fp16 [d, d] = fp16(Wv - fp16(Wv)), low half of the
-                                                split-precision V projection; else NULL */
+    const void* v_w3;                        /* ALiBi: fp16 [d, 3d] = [Wv_hi | Wv_hi | Wv_lo], Wv_lo =
+                                                fp16(Wv - fp16(Wv)): K-concatenated split-precision V
+                                                projection against LayerNorm output [hi | lo]; else NULL */
     const float* slope;                      /* [H] bias_scale_h / running_mean_h (ALiBi only) */
-    const void* fc_w;  const float* fc_b;    /* ALiBi: fp32 [d,d] rounded to TF32 (mhsa.fc);
-                                                else fp16 [d,d] (mhsa.out_proj) */
-    const void* fc_w_lo;                     /* ALiBi: fp32 [d,d] = tf32(W - tf32(W)); else NULL */
+    const void* fc_w;  const float* fc_b;    /* ALiBi: fp32 [d, 3d] = [W_hi | W_hi | W_lo] rounded to TF32
+                                                (mhsa.fc, 3 x TF32 against the attention output [hi | lo]);
+                                                else fp16 [d, d] (mhsa.out_proj) */
     const float *ln2_w, *ln2_b;              /* layers.l.1.0 */
     const void* ff1_w; const float* ff1_b;   /* fp16 [ff, d]  layers.l.1.1 */
     const void* ff2_w; const float* ff2_b;   /* fp16 [d, ff]  layers.l.1.4 */

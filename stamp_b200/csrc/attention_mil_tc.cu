@@ -24,7 +24,7 @@
 namespace sb {
 namespace {
 
-constexpr int MT_THREADS = 192;
+constexpr int MT_THREADS = 320;  // TMA warp, MMA warp, 8 softmax warps (2 threads per query row)
 constexpr int TILE_BYTES = 128 * 128;  // 128 rows x 64 halfs
 
 __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
@@ -51,7 +51,8 @@ struct MtSmem {
     static constexpr int off_p = off_v + 2 * TILE_BYTES;     // 2 x 64-key blocks
     static constexpr int off_d = off_p + 2 * TILE_BYTES;     // 2 x 64-key blocks
     static constexpr int off_c = off_d + 2 * TILE_BYTES;     // key coordinates, 2 x 128 float2
-    static constexpr int off_bar = off_c + 2 * 128 * 8;
+    static constexpr int off_x = off_c + 2 * 128 * 8;        // row-statistics exchange, 2 x 128 floats
+    static constexpr int off_bar = off_x + 2 * 128 * 4;
     static constexpr int total = off_bar + 128 + 1024;
 };
 
@@ -68,6 +69,7 @@ mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_const
     uint8_t* sP = smem + MtSmem::off_p;
     uint8_t* sD = smem + MtSmem::off_d;
     float2* sC = reinterpret_cast<float2*>(smem + MtSmem::off_c);
+    float* sX = reinterpret_cast<float*>(smem + MtSmem::off_x);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MtSmem::off_bar);
     uint64_t* kfull = bars;        // [2] TMA -> MMA
     uint64_t* kempty = bars + 2;   // [2] MMA -> TMA
@@ -92,9 +94,9 @@ mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_const
             mbar_init(&kfull[i], 1);
             mbar_init(&kempty[i], 1);
             mbar_init(&sfull[i], 1);
-            mbar_init(&sempty[i], 4);
+            mbar_init(&sempty[i], 8);
         }
-        mbar_init(pfull, 4);
+        mbar_init(pfull, 8);
         mbar_init(pempty, 1);
         mbar_init(ofull, 1);
         mbar_init(qfull, 1);
@@ -174,39 +176,40 @@ mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_const
             umma_commit(ofull);
         }
     } else {
-        // ------------------------ softmax: thread <-> query row <-> TMEM lane ------------------
+        // ---------- softmax: two threads per query row (= TMEM lane), one 64-key half each ----------
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;          // keys [64*half, 64*half + 64) of every tile
         const int r = quarter * 32 + lane;
-        const int st = threadIdx.x - 64;   // 0..127 among the softmax threads
+        const int st = threadIdx.x - 64;           // 0..255 among the softmax threads
         const int row = q0 + r;
         const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
         const float sl2 = p.scale_log2;
         const uint32_t sC_addr = smem_u32(sC), sP_addr = smem_u32(sP), sD_addr = smem_u32(sD);
         int ic = 0;  // S tiles consumed so far (both passes)
 
-        // ---- pass 1: exact row max ----
+        // ---- pass 1: exact row max (each thread over its half of the columns) ----
         float mx = -INFINITY;
         for (int kt = 0; kt < nkt; ++kt, ++ic) {
             const int s = ic & 1;
             mbar_wait(&sfull[s], (ic >> 1) & 1);
             tc_fence_after();
-            const int kv_valid = min(128, S - kt * 128);
+            const int kv_valid = min(128, S - kt * 128) - half * 64;   // valid keys in this thread's half
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32b_x32(t_lane + s * 128 + half * 64, v0);
+            tmem_ld_32x32b_x32(t_lane + s * 128 + half * 64 + 32, v1);
+            tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 4; c += 2) {
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32b_x32(t_lane + s * 128 + c * 32, v0);
-                tmem_ld_32x32b_x32(t_lane + s * 128 + (c + 1) * 32, v1);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (c * 32 + j < kv_valid) mx = fmaxf(mx, __uint_as_float(v0[j]));
-                    if ((c + 1) * 32 + j < kv_valid) mx = fmaxf(mx, __uint_as_float(v1[j]));
-                }
+            for (int j = 0; j < 32; ++j) {
+                if (j < kv_valid) mx = fmaxf(mx, __uint_as_float(v0[j]));
+                if (32 + j < kv_valid) mx = fmaxf(mx, __uint_as_float(v1[j]));
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sempty[s]);
         }
+        sX[half * 128 + r] = mx;
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        mx = fmaxf(mx, sX[(half ^ 1) * 128 + r]);
         const float ms = mx * sl2;
 
         // ---- pass 2: P, D tiles -> smem, l in a register ----
@@ -220,21 +223,25 @@ mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_const
             descale = __ldg(p.dscale + 2 * b + 1);
         }
         float l = 0.f;
+        const uint32_t pb = sP_addr + half * TILE_BYTES + r * 128;
+        const uint32_t db = sD_addr + half * TILE_BYTES + r * 128;
         for (int kt = 0; kt < nkt; ++kt, ++ic) {
             const int s = ic & 1;
-            const int kv_valid = min(128, S - kt * 128);
+            const int kv_valid = min(128, S - kt * 128) - half * 64;
             if constexpr (ALIBI) {
-                const int key = kt * 128 + st;
-                sts_f2(sC_addr + ((kt & 1) * 128 + st) * 8, (key < S) ? __ldg(cb + key) : make_float2(0.f, 0.f));
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                if (st < 128) {
+                    const int key = kt * 128 + st;
+                    sts_f2(sC_addr + ((kt & 1) * 128 + st) * 8, (key < S) ? __ldg(cb + key) : make_float2(0.f, 0.f));
+                }
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
             }
             mbar_wait(&sfull[s], (ic >> 1) & 1);
             mbar_wait(pempty, (kt & 1) ^ 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t v[32];
-                tmem_ld_32x32b_x32(t_lane + s * 128 + c * 32, v);
+                tmem_ld_32x32b_x32(t_lane + s * 128 + half * 64 + c * 32, v);
                 tmem_ld_wait();
                 uint32_t pw[16], dw[16];
 #pragma unroll
@@ -242,12 +249,12 @@ mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_const
                     float pv[2], dv[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const int kl = c * 32 + j + e;
+                        const int kl = c * 32 + j + e;              // key inside this thread's 64-key half
                         const bool valid = kl < kv_valid;
                         pv[e] = valid ? ex2_approx(fmaf(__uint_as_float(v[j + e]), sl2, -ms)) : 0.f;
                         l += pv[e];
                         if constexpr (ALIBI) {
-                            const float2 ck = lds_f2(sC_addr + ((kt & 1) * 128 + kl) * 8);
+                            const float2 ck = lds_f2(sC_addr + ((kt & 1) * 128 + half * 64 + kl) * 8);
                             const float dx = cq.x - ck.x, dy = cq.y - ck.y;
                             dv[e] = valid ? sqrt_approx(fmaf(dx, dx, dy * dy)) * slope : 0.f;
                         }
@@ -255,13 +262,10 @@ mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_const
                     pw[j >> 1] = pack_f16(pv[0], pv[1]);
                     if constexpr (ALIBI) dw[j >> 1] = pack_f16(dv[0], dv[1]);
                 }
-                // 32 keys = four 16-byte chunks of row r inside 64-key block c / 2
-                const uint32_t pb = sP_addr + (c >> 1) * TILE_BYTES + r * 128;
-                const uint32_t db = sD_addr + (c >> 1) * TILE_BYTES + r * 128;
-                const int ch0 = (c & 1) * 4;
+                // 32 keys = four 16-byte chunks of row r inside this thread's 64-key block
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int off = ((ch0 + q) ^ (r & 7)) * 16;
+                    const int off = ((c * 4 + q) ^ (r & 7)) * 16;
                     sts_u4(pb + off, make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]));
                     if constexpr (ALIBI)
                         sts_u4(db + off, make_uint4(dw[4 * q], dw[4 * q + 1], dw[4 * q + 2], dw[4 * q + 3]));
@@ -275,17 +279,19 @@ mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_const
                 mbar_arrive(&sempty[s]);
             }
         }
+        sX[half * 128 + r] = l;
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        l += sX[(half ^ 1) * 128 + r];
 
-        // ---- epilogue: O = O1 / l - descale * O2 ----
+        // ---- epilogue: O = O1 / l - descale * O2 ; this thread stores 32 of the row's 64 columns ----
         mbar_wait(ofull, 0);
         tc_fence_after();
         const float inv = 1.0f / l;
-        const long long obase = b * p.out_batch_stride + static_cast<long long>(row) * p.out_row_stride + h * 64;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        const long long obase = b * p.out_batch_stride + static_cast<long long>(row) * p.out_row_stride + h * 64 + half * 32;
+        {
             uint32_t o1[32], o2[32];
-            tmem_ld_32x32b_x32(t_lane + COL_O1 + c * 32, o1);
-            if constexpr (ALIBI) tmem_ld_32x32b_x32(t_lane + COL_O2 + c * 32, o2);
+            tmem_ld_32x32b_x32(t_lane + COL_O1 + half * 32, o1);
+            if constexpr (ALIBI) tmem_ld_32x32b_x32(t_lane + COL_O2 + half * 32, o2);
             tmem_ld_wait();
             if (row < S) {
                 float y[32];
@@ -295,8 +301,8 @@ mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_const
                     if constexpr (ALIBI) y[j] = fmaf(-descale, __uint_as_float(o2[j]), y[j]);
                 }
                 if (p.out_f32) {
-                    float* of = reinterpret_cast<float*>(p.out) + obase + c * 32;
-                    float* ol = (p.out_lo != nullptr) ? p.out_lo + obase + c * 32 : nullptr;
+                    float* of = reinterpret_cast<float*>(p.out) + obase;
+                    float* ol = (p.out_lo != nullptr) ? p.out_lo + obase : nullptr;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 hi = make_float4(round_tf32(y[j]), round_tf32(y[j + 1]), round_tf32(y[j + 2]), round_tf32(y[j + 3]));
@@ -306,7 +312,7 @@ mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_const
                                                                              round_tf32(y[j + 2] - hi.z), round_tf32(y[j + 3] - hi.w));
                     }
                 } else {
-                    __half* oh = reinterpret_cast<__half*>(p.out) + obase + c * 32;
+                    __half* oh = reinterpret_cast<__half*>(p.out) + obase;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8)
                         *reinterpret_cast<uint4*>(oh + j) = make_uint4(pack_f16(y[j], y[j + 1]), pack_f16(y[j + 2], y[j + 3]),

@@ -310,15 +310,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int row_b = n_blk * BN + static_cast<int>(cta_rank) * C::B_ROWS;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    // K-concatenated split-precision products read A = [hi | lo] as hi, lo, hi
+                    const int ka = (p.a_kwrap > 0) ? (kb * BK) % p.a_kwrap : kb * BK;
                     if constexpr (CTAS == 2) {
                         // both CTAs' bytes complete on the LEADER's barrier, which expects all of them
                         const uint32_t lbar = map_to_cta(smem_u32(&full_bar[stage]), 0);
                         if (leader) mbar_expect_tx(&full_bar[stage], 2 * (C::A_BYTES + C::B_BYTES));
-                        tma_load_2d_cta2(smem_u32(sA + stage * C::A_BYTES), &tmA, lbar, kb * BK, row_a);
+                        tma_load_2d_cta2(smem_u32(sA + stage * C::A_BYTES), &tmA, lbar, ka, row_a);
                         tma_load_2d_cta2(smem_u32(sB + stage * C::B_BYTES), &tmB, lbar, kb * BK, row_b);
                     } else {
                         mbar_expect_tx(&full_bar[stage], C::A_BYTES + C::B_BYTES);
-                        tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], kb * BK, row_a);
+                        tma_load_2d(sA + stage * C::A_BYTES, &tmA, &full_bar[stage], ka, row_a);
                         tma_load_2d(sB + stage * C::B_BYTES, &tmB, &full_bar[stage], kb * BK, row_b);
                     }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -684,7 +686,8 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, const Ge
 
     const int kind = p.tf32 ? 2 : (p.bf16 ? 1 : 0);
     CUtensorMap tmA, tmB;
-    int rc = make_tmap(&tmA, A, p.M, p.K, lda, BM, kind);
+    if (p.a_kwrap < 0 || (p.a_kwrap % 64) != 0) return SB_ERR_BAD_ARG;
+    int rc = make_tmap(&tmA, A, p.M, p.a_kwrap > 0 ? p.a_kwrap : p.K, lda, BM, kind);
     if (rc != SB_OK) return rc;
     rc = make_tmap(&tmB, B, p.N, p.K, ldb, use_pair ? 128 : bn, kind);
     if (rc != SB_OK) return rc;

@@ -34,6 +34,9 @@ struct GemmParams {
     // optional row remap (token layouts with prefix rows):
     //   row = (m / gin) * gout + goff + (m % gin);   gin == 0 -> row = m
     int gin, gout, goff;
+    // K-concatenated split-precision product: the A operand physically holds a_kwrap columns
+    // ([hi | lo]) and is read at k % a_kwrap, i.e. hi, lo, hi against W' = [W_hi | W_hi | W_lo]; 0 = off
+    int a_kwrap;
 };
 
 // C[M,N] = A[M,K] . B[N,K]^T, A and B K-major 16-bit, fp32 accumulate in TMEM.

@@ -112,8 +112,7 @@ inline int grid_for(long long total, int block) {
 
 struct Layout {
     long long M, S;
-    size_t off_x, off_xn, off_xn_lo, off_qkv, off_att, off_att_lo, off_h, off_bags, off_coords, off_mask,
-        off_dscale, total;
+    size_t off_x, off_xn, off_qkv, off_att, off_h, off_bags, off_coords, off_mask, off_dscale, total;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -125,21 +124,20 @@ bool make_layout(const StampMilConfig* c, int B, int N, Layout* L) {
         return false;
     const int hd = c->dim_model / c->n_heads;
     if (hd != 64 && hd != 32 && !(hd == 80 && !c->use_alibi)) return false;
+    if (c->use_alibi && (c->dim_model % 32) != 0) return false;  // K-wrap of the split-precision GEMMs
     L->S = N + 1LL;
     L->M = L->S * B;
     const size_t d = c->dim_model, M = L->M;
     size_t o = 0;
     L->off_x = o;      o = align_up(o + M * d * 4, 256);
-    L->off_xn = o;     o = align_up(o + M * d * 2, 256);
-    L->off_xn_lo = o;  o = align_up(o + M * d * 2, 256);
+    L->off_xn = o;     o = align_up(o + M * 2 * d * 2, 256);   // [M, 2d] fp16: LayerNorm output hi | lo
     L->off_qkv = o;    o = align_up(o + M * 3 * d * 2, 256);
-    L->off_att = o;    o = align_up(o + M * d * 4, 256);
-    L->off_att_lo = o; o = align_up(o + M * d * 4, 256);
+    L->off_att = o;    o = align_up(o + M * 2 * d * 4, 256);   // [M, 2d] fp32: attention output hi | lo
     L->off_h = o;      o = align_up(o + M * c->dim_ff * 2, 256);
     L->off_bags = o;   o = align_up(o + static_cast<size_t>(B) * N * c->dim_input * 2 + 16, 256);
     L->off_coords = o; o = align_up(o + M * 8, 256);
     L->off_mask = o;   o = align_up(o + M, 256);
-    L->off_dscale = o; o = align_up(o + static_cast<size_t>(B) * 8, 256);
+    L->off_dscale = o; o = align_up(o + static_cast<size_t>(B) * 8 * (c->n_layers > 0 ? c->n_layers : 1), 256);
     L->total = o;
     return true;
 }
@@ -205,10 +203,14 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w, const
         count_launch();
     }
 
-    __half* xn_lo = reinterpret_cast<__half*>(ws + L.off_xn_lo);
-    float* att_lo = reinterpret_cast<float*>(ws + L.off_att_lo);
     const float scale_log2 = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
 
+    if (alibi)  // power-of-two range scale of the distance operand, per layer (slopes differ) and bag
+        for (int l = 0; l < cfg->n_layers; ++l) {
+            rc = alibi_dist_scale(reinterpret_cast<const float*>(coords_s), layers[l].slope, B, S, H,
+                                  dscale + static_cast<size_t>(l) * B * 2, stream);
+            if (rc != SB_OK) return rc;
+        }
     for (int l = 0; l < cfg->n_layers; ++l) {
         const StampMilLayer& y = layers[l];
         AttnParams a{};
@@ -219,47 +221,37 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w, const
             // orders of magnitude, so the two contractions it flows through -- the V projection and
             // fc -- run in split precision (operand = hi + lo, three tensor-core passes, fp32
             // accumulate); q/k and the softmax side are plain fp16.  Error budget: DESIGN.md.
-            rc = layernorm(x, d, y.ln1_w, y.ln1_b, xn, xn_lo, d, M, d, 1e-5f, 0, stream);
+            // LayerNorm -> xn = [hi | lo] (fp16, row pitch 2d)
+            rc = layernorm(x, d, y.ln1_w, y.ln1_b, xn, xn + d, 2LL * d, M, d, 1e-5f, 0, stream);
             if (rc != SB_OK) return rc;
             __half* qk = qkv;                                   // [M, 2d]
             __half* v16 = qkv + static_cast<size_t>(M) * 2 * d;  // [M, d]
-            float* vacc = reinterpret_cast<float*>(att);        // fp32 scratch, dead before attention writes att
-            const __half* wv_hi = static_cast<const __half*>(y.qkv_w) + static_cast<size_t>(2) * d * d;
             GemmParams p{};
             p.M = M; p.K = d;
             p.N = 2 * d; p.store = ST_16; p.out = qk; p.ldo = 2 * d; p.bias = y.qkv_b;
-            rc = gemm_tn(xn, d, y.qkv_w, d, p, stream);
+            rc = gemm_tn(xn, 2LL * d, y.qkv_w, d, p, stream);     // q | k heads from the hi half
             if (rc != SB_OK) return rc;
-            p.N = d; p.store = ST_32; p.out = vacc; p.ldo = d; p.bias = y.qkv_b + 2 * d;
-            rc = gemm_tn(xn, d, wv_hi, d, p, stream);            // hi . hi (+ bias)
-            if (rc != SB_OK) return rc;
-            p.store = ST_RESID32; p.bias = nullptr;
-            rc = gemm_tn(xn_lo, d, wv_hi, d, p, stream);         // lo . hi
-            if (rc != SB_OK) return rc;
-            p.store = ST_16; p.out = v16; p.table = vacc; p.ldt = d;
-            rc = gemm_tn(xn, d, y.v_w_lo, d, p, stream);         // hi . lo, + fp32 partial -> fp16 V
+            // v heads, split precision in ONE launch: K-concatenated hi.Whi + lo.Whi + hi.Wlo
+            p.N = d; p.K = 3 * d; p.a_kwrap = 2 * d; p.out = v16; p.ldo = d; p.bias = y.qkv_b + 2 * d;
+            rc = gemm_tn(xn, 2LL * d, y.v_w3, 3LL * d, p, stream);
             if (rc != SB_OK) return rc;
 
-            rc = alibi_dist_scale(reinterpret_cast<const float*>(coords_s), y.slope, B, S, H, dscale, stream);
-            if (rc != SB_OK) return rc;
             a.q = qk; a.k = qk + d; a.row_stride = 2LL * d; a.batch_stride = 2LL * d * S;
             a.v = v16; a.v_row_stride = d; a.v_batch_stride = static_cast<long long>(d) * S;
-            a.out_f32 = 1; a.out_lo = att_lo;
-            a.coords = reinterpret_cast<const float*>(coords_s); a.slope = y.slope; a.dscale = dscale;
+            // attention output [hi | lo] (TF32-rounded fp32, row pitch 2d)
+            a.out_f32 = 1; a.out_lo = reinterpret_cast<float*>(att) + d;
+            a.out_row_stride = 2LL * d; a.out_batch_stride = 2LL * d * S;
+            a.coords = reinterpret_cast<const float*>(coords_s); a.slope = y.slope;
+            a.dscale = dscale + static_cast<size_t>(l) * B * 2;
             if (mask != nullptr) { a.mask = mask_s; a.mask_mode = 1; }
             rc = attention_fwd(a, hd, stream);
             if (rc != SB_OK) return rc;
 
-            // x += fc(att): 3 x TF32 (att = hi + lo from the attention epilogue, W = hi + lo packed on the host)
+            // x += fc(att): 3 x TF32 in one launch, att = [hi | lo] read as hi, lo, hi
             GemmParams f{};
-            f.M = M; f.N = d; f.K = d; f.tf32 = 1; f.store = ST_RESID32; f.out = x; f.ldo = d;
+            f.M = M; f.N = d; f.K = 3 * d; f.a_kwrap = 2 * d; f.tf32 = 1; f.store = ST_RESID32; f.out = x; f.ldo = d;
             f.bias = y.fc_b;
-            rc = gemm_tn(att, d, y.fc_w, d, f, stream);
-            if (rc != SB_OK) return rc;
-            f.bias = nullptr;
-            rc = gemm_tn(att_lo, d, y.fc_w, d, f, stream);
-            if (rc != SB_OK) return rc;
-            rc = gemm_tn(att, d, y.fc_w_lo, d, f, stream);
+            rc = gemm_tn(att, 2LL * d, y.fc_w, 3LL * d, f, stream);
             if (rc != SB_OK) return rc;
         } else {
             rc = layernorm(x, d, y.ln1_w, y.ln1_b, xn, nullptr, d, M, d, 1e-5f, 0, stream);

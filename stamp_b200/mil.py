@@ -39,9 +39,8 @@ class StampMilWeights(C.Structure):
 
 
 class StampMilLayer(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "v_w_lo", "slope", "fc_w",
-                                          "fc_b", "fc_w_lo", "ln2_w", "ln2_b", "ff1_w", "ff1_b",
-                                          "ff2_w", "ff2_b")]
+    _fields_ = [(n, C.c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "v_w3", "slope", "fc_w",
+                                          "fc_b", "ln2_w", "ln2_b", "ff1_w", "ff1_b", "ff2_w", "ff2_b")]
 
 
 def _bind() -> C.CDLL:
@@ -165,18 +164,21 @@ class VisionTransformer(nn.Module):
                 qkv_w = torch.cat([e.weight for grp in (m.query_encoders, m.key_encoders, m.value_encoders) for e in grp])
                 qkv_b = torch.cat([e.bias for grp in (m.query_encoders, m.key_encoders, m.value_encoders) for e in grp])
                 slope = torch.cat([a.bias_scale / a.scale_distance.running_mean for a in m.attentions])
-                # split precision (hi + lo) for the two contractions the ALiBi term flows through
-                fc_hi = round_to_tf32(m.fc.weight)
-                fc_w, fc_b, slope_p = f32(fc_hi), f32(m.fc.bias), f32(slope)
-                fc_w_lo = f32(round_to_tf32(m.fc.weight.detach().float() - fc_hi))
+                # split precision (hi + lo) for the two contractions the ALiBi term flows through,
+                # K-concatenated so each is ONE GEMM: [hi | lo] read as hi, lo, hi against [W_hi | W_hi | W_lo]
+                fc_full = m.fc.weight.detach().float()
+                fc_hi = round_to_tf32(fc_full)
+                fc_lo = round_to_tf32(fc_full - fc_hi)
+                fc_w, fc_b, slope_p = f32(torch.cat([fc_hi, fc_hi, fc_lo], dim=1)), f32(m.fc.bias), f32(slope)
                 wv = qkv_w[2 * self._cfg["dim_model"]:].detach().float()
-                v_w_lo = f16(wv - wv.half().float())
+                wv_hi = wv.half()
+                v_w3 = f16(torch.cat([wv_hi, wv_hi, (wv - wv_hi.float()).half()], dim=1))
             else:
                 qkv_w, qkv_b = m.in_proj_weight, m.in_proj_bias
                 fc_w, fc_b, slope_p = f16(m.out_proj.weight), f32(m.out_proj.bias), None
-                fc_w_lo = v_w_lo = None
+                v_w3 = None
             layers[i] = StampMilLayer(f32(att.norm.weight), f32(att.norm.bias), f16(qkv_w), f32(qkv_b),
-                                      v_w_lo, slope_p, fc_w, fc_b, fc_w_lo, f32(ff[0].weight), f32(ff[0].bias),
+                                      v_w3, slope_p, fc_w, fc_b, f32(ff[0].weight), f32(ff[0].bias),
                                       f16(ff[1].weight), f32(ff[1].bias), f16(ff[4].weight), f32(ff[4].bias))
         self._packed = (key, keep, cfg, w, layers)
         return self._packed
