@@ -325,7 +325,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=192)
+    ap.add_argument("--batch", type=int, default=192)  # 192 x 197 tokens = 148 row tiles of 256: whole waves on 74 SM pairs
     ap.add_argument("--slide-tiles", type=int, default=SLIDE_TILES)
     ap.add_argument("--skip-mil", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
