@@ -33,6 +33,7 @@ int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 // tcgen05 path for short unmasked sequences (attention_tc.cu); SB_ERR_UNSUPPORTED = not applicable
 int attention_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 void attention_tc_enable(int on);
+void attention_tc_set_trace(long long* device_buf);  // debug: 5 x int64 per CTA (phase cycle counts)
 // tcgen05 two-pass kernel for long unmasked bags, plain or ALiBi (attention_mil_tc.cu)
 int attention_mil_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 void attention_mil_tc_enable(int on);

@@ -49,7 +49,8 @@ inline TcSmem tc_layout(int nk) {
 __global__ void __launch_bounds__(TC_THREADS)
 vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                    __half* __restrict__ out, long long out_row_stride, long long out_batch_stride,
-                   int S, int H, int D, int nk, float scale_log2, TcSmem L) {
+                   int S, int H, int D, int nk, float scale_log2, TcSmem L, long long* trace) {
+    const long long t_start = clock64();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -131,8 +132,12 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         const bool tail16 = (nk & 16) != 0;
         mbar_wait(bar_s, 0);
         tc_fence_after();
-        float mx = -INFINITY;
-        for (int c = 0; c < n32; c += 2) {
+        const long long t_s = clock64();
+        // four independent max / sum accumulators: a single 208-long dependent chain costs ~4 cycles a link
+        // warps whose 32 rows all lie past the last token only keep the barrier protocol alive
+        const bool warp_rows_valid = (q0 + quarter * 32) < S;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int c = 0; warp_rows_valid && c < n32; c += 2) {
             uint32_t v0[32], v1[32];
             const bool two = c + 1 < n32;
             tmem_ld_32x32b_x32(t_row + c * 32, v0);
@@ -140,30 +145,40 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                if (c * 32 + j < S) mx = fmaxf(mx, __uint_as_float(v0[j]));
+                if (c * 32 + j < S) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v0[j]));
             if (two) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if ((c + 1) * 32 + j < S) mx = fmaxf(mx, __uint_as_float(v1[j]));
+                    if ((c + 1) * 32 + j < S) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v1[j]));
             }
         }
-        if (tail16) {
+        if (warp_rows_valid && tail16) {
             uint32_t v[16];
             tmem_ld_32x32b_x16(t_row + n32 * 32, v);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                if (n32 * 32 + j < S) mx = fmaxf(mx, __uint_as_float(v[j]));
+                if (n32 * 32 + j < S) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v[j]));
         }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         const float ms = mx * scale_log2;
-        float l = 0.f;
+        const long long t_m = clock64();
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
         // exp2 + fp16 pack + swizzled store of 16 keys (= two 16-byte chunks of row r in 64-key block)
         auto emit16 = [&](const uint32_t* v, int key0) {
             float p[16];
+            if (key0 + 16 <= S) {  // (uniform) every key of the group is a real token
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                p[j] = (key0 + j < S) ? ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2, -ms)) : 0.f;
-                l += p[j];
+                for (int j = 0; j < 16; ++j) {
+                    p[j] = ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2, -ms));
+                    l4[j & 3] += p[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    p[j] = (key0 + j < S) ? ex2_approx(fmaf(__uint_as_float(v[j]), scale_log2, -ms)) : 0.f;
+                    l4[j & 3] += p[j];
+                }
             }
             const int blk = key0 >> 6;
             const uint32_t pb = smem_u32((blk == 0) ? sK : (blk == 3 ? sQ : sP12 + (blk - 1) * P_BLOCK_BYTES));
@@ -174,7 +189,7 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             sts_v4(pb + r * 128 + ((ch0 ^ (r & 7)) * 16), w0);
             sts_v4(pb + r * 128 + (((ch0 + 1) ^ (r & 7)) * 16), w1);
         };
-        for (int c = 0; c < n32; c += 2) {
+        for (int c = 0; warp_rows_valid && c < n32; c += 2) {
             uint32_t v0[32], v1[32];
             const bool two = c + 1 < n32;
             tmem_ld_32x32b_x32(t_row + c * 32, v0);
@@ -187,7 +202,7 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 emit16(v1 + 16, (c + 1) * 32 + 16);
             }
         }
-        if (tail16) {
+        if (warp_rows_valid && tail16) {
             uint32_t v[16];
             tmem_ld_32x32b_x16(t_row + n32 * 32, v);
             tmem_ld_wait();
@@ -198,9 +213,12 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p);
+        const long long t_p = clock64();
 
         mbar_wait(bar_o, 0);
         tc_fence_after();
+        const long long t_o = clock64();
+        const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         const float inv = 1.0f / l;
         const int row = q0 + r;
         __half* o = out + b * out_batch_stride + static_cast<long long>(row) * out_row_stride + h * 64;
@@ -221,6 +239,10 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
                 }
             }
         }
+        if (trace != nullptr && warp == 2 && lane == 0) {  // debug: cycles per phase of this CTA
+            long long* tr = trace + (static_cast<long long>(blockIdx.y) * gridDim.x + blockIdx.x) * 6;
+            tr[0] = t_s - t_start; tr[1] = t_p - t_s; tr[5] = t_m - t_s; tr[2] = t_o - t_p; tr[3] = clock64() - t_o; tr[4] = t_start;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -233,6 +255,8 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 }  // namespace
 
 static int g_tc_enabled = 1;
+static long long* g_trace = nullptr;
+void attention_tc_set_trace(long long* buf) { g_trace = buf; }
 void attention_tc_enable(int on) { g_tc_enabled = on; }
 
 // returns SB_ERR_UNSUPPORTED when the shape is outside this kernel's envelope (caller falls back
@@ -263,7 +287,7 @@ int attention_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream) {
     ProfScope prof(PROF_ATTN, 4.0 * p.B * p.H * static_cast<double>(p.S) * p.S * 64, stream);
     vit_attn_tc_kernel<<<grid, TC_THREADS, L.total, stream>>>(
         tm_q, tm_kv, static_cast<__half*>(p.out), p.out_row_stride, p.out_batch_stride, p.S, p.H, D, nk,
-        p.scale_log2, L);
+        p.scale_log2, L, g_trace);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }

@@ -34,6 +34,9 @@ long long stamp_b200_launch_count(void) { return sb::g_launches.load(std::memory
 void stamp_b200_reset_launch_count(void) { sb::g_launches.store(0, std::memory_order_relaxed); }
 
 void stamp_b200_gemm_force_mode(int mode) { sb::gemm_force_mode(mode); }
+// development aid (not part of the public header): per-CTA phase cycle counts of the ViT attention
+void stamp_b200_debug_attention_trace(long long* device_buf) { sb::attention_tc_set_trace(device_buf); }
+
 void stamp_b200_attention_tc_enable(int on) {
     sb::attention_tc_enable(on);
     sb::attention_mil_tc_enable(on);
