@@ -26,7 +26,7 @@
 namespace sb {
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;  // TMA warp, MMA warp, 8 softmax warps (two threads per query row)
 constexpr int P_BLOCK_BYTES = 128 * 128;  // 128 rows x 64 keys fp16
 
 struct TcSmem {
@@ -42,11 +42,11 @@ inline TcSmem tc_layout(int nk) {
     s.off_p12 = s.off_k + ((k_region + 1023) / 1024) * 1024;
     s.off_v = s.off_p12 + 2 * P_BLOCK_BYTES;
     s.off_bar = s.off_v + ((kv_bytes + 1023) / 1024) * 1024;
-    s.total = s.off_bar + 64 + 1024;               // barriers + alignment slack
+    s.total = s.off_bar + 64 + 1024 + 1024;        // barriers, [2][128] float exchange buffer, alignment slack
     return s;
 }
 
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                    __half* __restrict__ out, long long out_row_stride, long long out_batch_stride,
                    int S, int H, int D, int nk, float scale_log2, TcSmem L, long long* trace) {
@@ -76,7 +76,7 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         tma_prefetch_desc(&tm_kv);
         mbar_init(bar_load, 1);
         mbar_init(bar_s, 1);
-        mbar_init(bar_p, 4);
+        mbar_init(bar_p, 8);
         mbar_init(bar_o, 1);
         fence_barrier_init();
     }
@@ -123,44 +123,42 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             }
         }
     } else {
-        // ---- softmax / epilogue: thread <-> query row <-> TMEM lane --------------------------
+        // ---- softmax / epilogue: two threads per query row (= TMEM lane); the 32-key chunks of the
+        //      row alternate between them, row statistics are exchanged through shared memory ----
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int r = quarter * 32 + lane;              // row inside the 128-row tile
         const uint32_t t_row = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-        // S row of this thread: nk = 32 * n32 (+ 16) columns; two tcgen05.ld in flight per wait
-        const int n32 = nk >> 5;
-        const bool tail16 = (nk & 16) != 0;
+        const int nch = (nk + 31) >> 5;                 // 32-key chunks, the last one may hold 16 keys
+        // warps whose 32 rows all lie past the last token only keep the barrier protocol alive
+        const bool warp_rows_valid = (q0 + quarter * 32) < S;
+        float* sX = reinterpret_cast<float*>(smem + L.off_bar + 64);   // [2][128] exchange buffer
+        auto load_chunk = [&](uint32_t (&v)[32], int c) {
+            if (nk - c * 32 >= 32) tmem_ld_32x32b_x32(t_row + c * 32, v);
+            else tmem_ld_32x32b_x16(t_row + c * 32, *reinterpret_cast<uint32_t(*)[16]>(v));
+        };
         mbar_wait(bar_s, 0);
         tc_fence_after();
         const long long t_s = clock64();
-        // four independent max / sum accumulators: a single 208-long dependent chain costs ~4 cycles a link
-        // warps whose 32 rows all lie past the last token only keep the barrier protocol alive
-        const bool warp_rows_valid = (q0 + quarter * 32) < S;
+        // four independent max / sum accumulators: one long dependent chain costs ~4 cycles a link
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        for (int c = 0; warp_rows_valid && c < n32; c += 2) {
+        for (int c = half; warp_rows_valid && c < nch; c += 4) {
             uint32_t v0[32], v1[32];
-            const bool two = c + 1 < n32;
-            tmem_ld_32x32b_x32(t_row + c * 32, v0);
-            if (two) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v1);
+            const bool two = c + 2 < nch;
+            load_chunk(v0, c);
+            if (two) load_chunk(v1, c + 2);
             tmem_ld_wait();
+            const int n0 = min(32, min(nk, S) - c * 32), n1 = min(32, min(nk, S) - (c + 2) * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (c * 32 + j < S) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v0[j]));
-            if (two) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if ((c + 1) * 32 + j < S) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v1[j]));
+            for (int j = 0; j < 32; ++j) {
+                if (j < n0) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v0[j]));
+                if (two && j < n1) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v1[j]));
             }
         }
-        if (warp_rows_valid && tail16) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(t_row + n32 * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (n32 * 32 + j < S) mx4[j & 3] = fmaxf(mx4[j & 3], __uint_as_float(v[j]));
-        }
-        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        sX[half * 128 + r] = mx;
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        mx = fmaxf(mx, sX[(half ^ 1) * 128 + r]);
         const float ms = mx * scale_log2;
         const long long t_m = clock64();
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -189,24 +187,18 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             sts_v4(pb + r * 128 + ((ch0 ^ (r & 7)) * 16), w0);
             sts_v4(pb + r * 128 + (((ch0 + 1) ^ (r & 7)) * 16), w1);
         };
-        for (int c = 0; warp_rows_valid && c < n32; c += 2) {
+        for (int c = half; warp_rows_valid && c < nch; c += 4) {
             uint32_t v0[32], v1[32];
-            const bool two = c + 1 < n32;
-            tmem_ld_32x32b_x32(t_row + c * 32, v0);
-            if (two) tmem_ld_32x32b_x32(t_row + (c + 1) * 32, v1);
+            const bool two = c + 2 < nch;
+            load_chunk(v0, c);
+            if (two) load_chunk(v1, c + 2);
             tmem_ld_wait();
             emit16(v0, c * 32);
-            emit16(v0 + 16, c * 32 + 16);
+            if (nk - c * 32 >= 32) emit16(v0 + 16, c * 32 + 16);
             if (two) {
-                emit16(v1, (c + 1) * 32);
-                emit16(v1 + 16, (c + 1) * 32 + 16);
+                emit16(v1, (c + 2) * 32);
+                if (nk - (c + 2) * 32 >= 32) emit16(v1 + 16, (c + 2) * 32 + 16);
             }
-        }
-        if (warp_rows_valid && tail16) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(t_row + n32 * 32, v);
-            tmem_ld_wait();
-            emit16(v, n32 * 32);
         }
         // make the generic-proxy smem writes visible to the tensor core (async proxy), free S in TMEM
         fence_proxy_async();
@@ -214,22 +206,25 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p);
         const long long t_p = clock64();
+        float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");   // everyone has read the max exchange
+        sX[half * 128 + r] = l;
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        l += sX[(half ^ 1) * 128 + r];
 
         mbar_wait(bar_o, 0);
         tc_fence_after();
         const long long t_o = clock64();
-        const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         const float inv = 1.0f / l;
         const int row = q0 + r;
-        __half* o = out + b * out_batch_stride + static_cast<long long>(row) * out_row_stride + h * 64;
+        __half* o = out + b * out_batch_stride + static_cast<long long>(row) * out_row_stride + h * 64 + half * 32;
         {
-            uint32_t v[64];
-            tmem_ld_32x32b_x32(t_row, *reinterpret_cast<uint32_t(*)[32]>(v));
-            tmem_ld_32x32b_x32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(v + 32));
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_row + half * 32, v);   // this thread's 32 of the row's 64 output columns
             tmem_ld_wait();
             if (row < S) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     uint4 w;
                     w.x = pack_f16(__uint_as_float(v[8 * c]) * inv, __uint_as_float(v[8 * c + 1]) * inv);
                     w.y = pack_f16(__uint_as_float(v[8 * c + 2]) * inv, __uint_as_float(v[8 * c + 3]) * inv);
