@@ -66,8 +66,9 @@ int stamp_b200_profile_summary(double* host_ms, double* host_work, long long* ho
 /* tile-shape override for tests / tuning: 0 auto, 1 single-CTA tiles only, 2 CTA-pair
  * (tcgen05 cta_group::2, 256x256) tiles whenever legal */
 void stamp_b200_gemm_force_mode(int mode);
-/* 1 (default): unmasked head_dim-64 attention over <= 256 tokens runs on the tcgen05 kernel;
- * 0: always the general kernel (tests / A-B timing) */
+/* bit 0 (default 1): unmasked head_dim-64 attention runs on the tcgen05 kernels (<= 256 tokens:
+ * single-pass ViT kernel; longer: two-pass long-bag kernel); 0: always the general kernel.
+ * bit 1: prefer the persistent variant of the ViT kernel (tests / A-B timing). */
 void stamp_b200_attention_tc_enable(int on);
 
 int stamp_gemm_tn(const void* A, long long lda, const void* W, long long ldw, void* out,

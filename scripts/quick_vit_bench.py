@@ -9,6 +9,10 @@ from stamp_b200.vit import TileEncoder, UNI_ARCH, VIRCHOW2_ARCH, random_state_di
 
 arch = VIRCHOW2_ARCH if "virchow2" in sys.argv else UNI_ARCH
 dev = torch.device("cuda:0")
+if "persist" in sys.argv:
+    from stamp_b200 import _lib
+    _lib.load().stamp_b200_attention_tc_enable(3)
+    print("attention: persistent single-TMEM-pass kernel")
 sd = random_state_dict(arch)
 for B in [int(a) for a in sys.argv[1:] if a.isdigit()] or [64, 128, 256]:
     enc = TileEncoder(arch, sd, max_batch=B).to(dev).eval()

@@ -403,7 +403,9 @@ int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream) {
         return SB_ERR_BAD_ARG;
     // short unmasked sequences (ViT tiles): tcgen05 kernel; anything else: the general kernel below
     {
-        const int rc = attention_tc_fwd(p, head_dim, stream);
+        int rc = attention_vit_persist_fwd(p, head_dim, stream);   // persistent, single TMEM pass
+        if (rc != SB_ERR_UNSUPPORTED) return rc;
+        rc = attention_tc_fwd(p, head_dim, stream);
         if (rc != SB_ERR_UNSUPPORTED) return rc;
     }
     // long unmasked bags (MIL aggregator, plain or ALiBi): tcgen05 two-pass kernel

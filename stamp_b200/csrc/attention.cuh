@@ -34,6 +34,10 @@ int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 int attention_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 void attention_tc_enable(int on);
 void attention_tc_set_trace(long long* device_buf);  // debug: 5 x int64 per CTA (phase cycle counts)
+// persistent single-TMEM-pass kernel for ViT tiles (attention_vit_persist.cu), tried before attention_tc_fwd
+int attention_vit_persist_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
+void attention_vit_persist_enable(int on);
+void attention_vit_persist_set_trace(long long* device_buf);  // debug: 6 x int64 per CTA
 // tcgen05 two-pass kernel for long unmasked bags, plain or ALiBi (attention_mil_tc.cu)
 int attention_mil_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 void attention_mil_tc_enable(int on);

@@ -101,6 +101,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Spinning wait without the suspend-time hint: for whole warps on a short critical-path hand-off,
+// where wake-up latency matters more than the issue slots of the spin.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (ok == 0);
+}
+
 // ----------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), 2-D tiles, mbarrier completion
 // ----------------------------------------------------------------------------

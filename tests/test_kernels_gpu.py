@@ -252,14 +252,17 @@ def test_attention_tcgen05_vs_general(cuda_device, B, S, H):
     g = torch.Generator(device="cpu").manual_seed(S * 3 + H)
     qkv = torch.randn(B, S, 3 * H * 64, generator=g).to(cuda_device, torch.float16)
     ref = _attn_ref(qkv, H)
-    out_tc = ops.attention(qkv, H)
-    _lib.load().stamp_b200_attention_tc_enable(0)
+    out_tc = ops.attention(qkv, H)          # default: tcgen05 kernel, two CTAs per SM
     try:
-        out_gen = ops.attention(qkv, H)
+        _lib.load().stamp_b200_attention_tc_enable(3)
+        out_tc2 = ops.attention(qkv, H)     # opt-in: persistent single-TMEM-pass kernel (S <= 240)
+        _lib.load().stamp_b200_attention_tc_enable(0)
+        out_gen = ops.attention(qkv, H)     # general (legacy tensor path) kernel
     finally:
         _lib.load().stamp_b200_attention_tc_enable(1)
-    assert torch.isfinite(out_tc).all()
+    assert torch.isfinite(out_tc).all() and torch.isfinite(out_tc2).all()
     assert _rel(out_tc.float(), ref) < 2e-3
+    assert _rel(out_tc2.float(), ref) < 2e-3
     assert _rel(out_gen.float(), ref) < 2e-3
 
 
