@@ -293,6 +293,56 @@ def run_b200(args) -> None:
                    "roofline_frac": (res["value"] / world) * MIL_FLOPS_PER_BAG / 1e12 / peak_tf,
                    "h2d_bytes_per_slide": n_tiles * 1026 * 4}
 
+    # ---- HBM-bound kernels of the path (rank 0): Macenko over an extraction batch, CHIEF pooling
+    hbm_out = None
+    if rank == 0 and not args.skip_mil:
+        from stamp_b200.encoder import GatedAttentionPool
+        from stamp_b200.macenko import macenko_normalize
+
+        hbm_gbs = float(peaks.get("hbm_gbs", 6650.0))
+
+        def timed(fn, n=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        mt = torch.randint(20, 235, (768, 224, 224, 3), dtype=torch.uint8, device=dev)
+        mo_ = torch.empty_like(mt)
+        ms = timed(lambda: macenko_normalize(mt, out=mo_))
+        mac_gbs = 2 * mt.numel() / ms / 1e6
+        gen = torch.Generator().manual_seed(3)
+        chief_sd = {"attention_net.0.weight": torch.randn(512, 768, generator=gen) * 0.04,
+                    "attention_net.0.bias": torch.zeros(512),
+                    "attention_net.3.attention_a.0.weight": torch.randn(256, 512, generator=gen) * 0.05,
+                    "attention_net.3.attention_a.0.bias": torch.zeros(256),
+                    "attention_net.3.attention_b.0.weight": torch.randn(256, 512, generator=gen) * 0.05,
+                    "attention_net.3.attention_b.0.bias": torch.zeros(256),
+                    "attention_net.3.attention_c.weight": torch.randn(1, 256, generator=gen) * 0.06,
+                    "attention_net.3.attention_c.bias": torch.zeros(1)}
+        pool = GatedAttentionPool(chief_sd).to(dev)
+        px = torch.randn(50_000, 768, device=dev)
+        _lib.profile_enable(True)
+        pool(px)
+        pprof = _lib.profile_summary()
+        _lib.profile_enable(False)
+        pool_ms = timed(lambda: pool(px))
+        pool_gbs = pprof["pool"]["work"] / pprof["pool"]["ms"] / 1e6 if pprof["pool"]["ms"] > 0 else 0.0
+        hbm_out = {
+            "macenko": {"tiles_per_s": 768 / ms * 1e3, "batch_tiles": 768, "achieved_GBps": mac_gbs,
+                        "peak_GBps": hbm_gbs, "frac": mac_gbs / hbm_gbs,
+                        "algorithmic_bytes_per_tile": 301056,
+                        "note": "17 launches, 8 passes over an L2-resident batch; bound by smem atomics, not HBM"},
+            "chief_pool_50k": {"slides_per_s": 1e3 / pool_ms, "pool_kernels_GBps": pool_gbs, "peak_GBps": hbm_gbs,
+                               "frac": pool_gbs / hbm_gbs, "algorithmic_bytes": 50_000 * 768 * 4},
+        }
+        del mt, mo_, px
+
     # ---- CPU baseline (rank 0, single GPU runs only): oracle port on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
@@ -312,7 +362,7 @@ def run_b200(args) -> None:
                        "batch": args.batch, "l2": "inputs (1.5 GB/slide) larger than L2, no flush",
                        "sharding": f"slides[rank::{world}], no data-path collective"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "mil": mil_out,
+            "cpu_baseline": cpu, "mil": mil_out, "hbm_kernels": hbm_out,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

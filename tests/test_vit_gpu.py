@@ -74,3 +74,28 @@ def test_tile_encoder_refuses_cpu():
                       vo.make_weights(cfg))
     with pytest.raises(RuntimeError):
         enc(torch.zeros(1, 224, 224, 3, dtype=torch.uint8))
+
+
+def test_macenko_then_virchow2_chain_matches_oracle_chain(cuda_device):
+    """BASELINE configs[2] pipeline on one batch: Macenko over the tile batch -> Virchow2-style
+    encoder (patch 14, SwiGLU, 4 register tokens; depth reduced for CPU-oracle speed)."""
+    import numpy as np
+
+    from oracle import macenko_oracle as mo
+    from oracle import vit_oracle as vo
+    from stamp_b200.macenko import macenko_normalize
+    from stamp_b200.vit import TileEncoder, VitArch
+
+    cfg = vo.VitConfig("virchow2-d3", patch=14, dim=256, depth=3, heads=4, mlp_hidden=1376, mlp="swiglu", reg_tokens=4)
+    w = vo.make_weights(cfg, seed=99)
+    tiles = vo.synthetic_tiles(6, seed=41)
+    norm_ref, *_ = mo.normalize(tiles.numpy())
+    with torch.no_grad():
+        feats_ref = vo.forward(w, cfg, torch.from_numpy(norm_ref))
+    arch = VitArch(cfg.name, patch=14, dim=256, depth=3, heads=4, mlp_hidden=1376, mlp="swiglu", reg_tokens=4)
+    enc = TileEncoder(arch, w).to(cuda_device).eval()
+    norm = macenko_normalize(tiles.to(cuda_device))
+    feats = enc(norm)
+    assert np.abs(norm.cpu().numpy().astype(np.int16) - norm_ref.astype(np.int16)).max() <= 1
+    # features after a <= 1 LSB difference on <2 % of the input bytes + fp16 operands
+    assert _per_tile_rel(feats.float(), feats_ref) < 2e-3
