@@ -216,6 +216,75 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * ALiBi Transformer-MIL training step (forward with checkpoints, backward, loss, optimizer).
+ * replaces: LitTileClassifier.training_step -> _step (src/stamp/modeling/models/__init__.py:239-286:
+ *   logits = model(bags, coords=coords, mask=None); F.cross_entropy(logits, soft targets, class weights)),
+ *   loss.backward() through VisionTransformer.forward (vision_tranformer.py:332-384, incl. nn.Dropout of
+ *   project_features :314-318 and feed_forward :157-169, dropout 0.5 hard-wired :160), the training-mode
+ *   _RunningMeanScaler statistic (:23-31) and optim.AdamW.step (models/__init__.py:133-141).
+ * mask=None branch and use_alibi=1 only (the branch every Lightning step takes).  bf16 tensor-core
+ * operands, fp32 accumulation / residual stream / master parameters / gradients.
+ * The two structs below hold fp32 DEVICE pointers in the reference's layouts; the same struct types
+ * carry the gradients, which the backward ACCUMULATES into (zero them first, like optimizer.zero_grad()).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    float* proj_w;        /* [dim_model, dim_input]  project_features.0.weight */
+    float* proj_b;
+    float* class_token;   /* [dim_model] */
+    float* norm_w;        /* transformer.norm */
+    float* norm_b;
+    float* head_w;        /* [dim_output, dim_model]  mlp_head.0 */
+    float* head_b;
+} StampMilTrainTop;
+
+typedef struct {
+    float *ln1_w, *ln1_b;                 /* layers.l.0.norm */
+    float *qkv_w, *qkv_b;                 /* [3d, d] / [3d]: rows = query heads | key heads | value heads */
+    float* bias_scale;                    /* [H]  mhsa.attentions.h.bias_scale */
+    float *fc_w, *fc_b;                   /* mhsa.fc */
+    float *ln2_w, *ln2_b;                 /* layers.l.1.0 */
+    float *ff1_w, *ff1_b, *ff2_w, *ff2_b; /* layers.l.1.1 / layers.l.1.4 */
+} StampMilTrainLayer;
+
+typedef struct {
+    float p_drop_proj;          /* project_features Dropout(p)            (0 = off) */
+    float p_drop_ff;            /* both feed_forward Dropouts, reference 0.5 (0 = off) */
+    unsigned long long seed;    /* dropout masks = f(seed, site, element): regenerated in the backward */
+    const float* inv_rm;        /* DEVICE [n_layers, H]: 1 / scale_distance.running_mean (after its update) */
+} StampMilTrainStep;
+
+/* bytes of 256-byte-aligned device memory holding checkpoints + scratch between forward and backward
+ * (0 = unsupported configuration: needs use_alibi, head dim 32/64, dims % 8 == 0, dim_model <= 1024) */
+size_t stamp_mil_train_ctx_bytes(const StampMilConfig* cfg, int B, int N);
+int stamp_mil_train_forward(const StampMilConfig* cfg, const StampMilTrainTop* params,
+                            const StampMilTrainLayer* layers, const StampMilTrainStep* step,
+                            const float* bags /* [B,N,F] */, const float* coords /* [B,N,2] */,
+                            float* logits /* [B,C] */, int B, int N, void* ctx, size_t ctx_bytes, void* stream);
+/* dbags: NULL or fp32 [B,N,F] (overwritten) -- the gradient heatmaps need (heatmaps/__init__.py:36-56) */
+int stamp_mil_train_backward(const StampMilConfig* cfg, const StampMilTrainTop* params,
+                             const StampMilTrainLayer* layers, const StampMilTrainStep* step,
+                             const float* dlogits /* [B,C] */, StampMilTrainTop* grads,
+                             StampMilTrainLayer* layer_grads, float* dbags, int B, int N, void* ctx,
+                             size_t ctx_bytes, void* stream);
+/* keep-mask (1 = kept) of dropout site `site` for element indices 0..n-1: site 0 = project_features
+ * ([B*N, d] row-major), 1 + 2l = feed_forward hidden of layer l ([M, ff]), 2 + 2l = its output ([M, d]) */
+int stamp_mil_train_dropout_mask(unsigned long long seed, int site, long long n, float p, uint8_t* keep_out,
+                                 void* stream);
+/* mean of all pairwise token distances of a batch of bags, class token at (0,0) included: the value
+ * torch.cdist(...).mean() feeds the running mean in training mode (vision_tranformer.py:26-29) */
+size_t stamp_pairwise_dist_mean_workspace_bytes(int B, int N);
+int stamp_pairwise_dist_mean(const float* coords, int B, int N, float* mean_out /* device scalar */,
+                             void* workspace, size_t workspace_bytes, void* stream);
+/* loss = 1/B sum_b sum_c -w_c y_bc log softmax(logits_b)_c; dlogits_out (may be NULL) = grad_scale * dloss/dlogits */
+int stamp_cross_entropy(const float* logits, const float* targets, const float* class_weights /* or NULL */,
+                        int B, int C, float grad_scale, float* loss_out /* device scalar */,
+                        float* dlogits_out, void* stream);
+/* torch.optim.AdamW step t (1-based) over flat fp32 buffers; grads are multiplied by grad_scale first */
+int stamp_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                     float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Macenko stain normalisation over a batch of uint8 RGB tiles (in/out [n_tiles,H,W,3]).
  * The reference snapshot has no Macenko code (README.md:35 only): the stage is named by
  * BASELINE.json's north_star; algorithm as specified in SURVEY.md 8c (oracle/macenko_oracle.py).

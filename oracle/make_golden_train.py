@@ -1,0 +1,68 @@
+"""Generates tests/golden/mil_train_step.npz by running the REFERENCE module itself in training mode.
+
+Run in the build container only (``python oracle/make_golden_train.py``).  Imports
+``/root/reference/src/stamp/modeling/models/vision_tranformer.py`` by file path, puts the model in
+``train()`` mode with every nn.Dropout set to p = 0 (random masks cannot be pinned; the dropout sites
+are covered separately against the oracle with explicit masks), and records one optimisation step as
+``LitTileClassifier`` runs it (src/stamp/modeling/models/__init__.py:239-286, :133-141):
+
+    logits = model(bags, coords=coords, mask=None)
+    loss = F.cross_entropy(logits, soft_targets, weight=class_weights); loss.backward()
+    torch.optim.AdamW(model.parameters(), lr=1e-3).step()
+
+Stored: inputs, state dict before, logits, loss, every parameter gradient, the running-mean buffers
+after the forward, and the parameters after the AdamW step.
+"""
+
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from make_golden import OUT, load_reference  # noqa: E402
+
+DIMS = dict(dim_input=64, dim_model=128, n_layers=2, n_heads=2, dim_feedforward=128, dim_output=3)
+
+
+def main() -> None:
+    ref = load_reference()
+    torch.manual_seed(4242)
+    model = ref.VisionTransformer(dropout=0.25, use_alibi=True, **DIMS).train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    g = torch.Generator().manual_seed(77)
+    B, n = 3, 77
+    bags = torch.randn(B, n, DIMS["dim_input"], generator=g).half().float()
+    cells = torch.stack([torch.randperm(100 * 100, generator=g)[:n] for _ in range(B)])
+    coords = torch.stack([(cells % 100).float(), (cells // 100).float()], dim=-1) * 256.0
+    targets = F.one_hot(torch.tensor([0, 2, 1]), 3).float()
+    class_weights = torch.tensor([0.7, 1.1, 1.6])
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    logits = model(bags, coords=coords, mask=None)
+    loss = F.cross_entropy(logits, targets, weight=class_weights)
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+    opt.step()
+    after = model.state_dict()
+
+    arrays = {f"sd/{k}": v.numpy() for k, v in before.items()}
+    arrays.update({f"grad/{k}": v.numpy() for k, v in grads.items()})
+    arrays.update({f"after/{k}": v.detach().numpy() for k, v in after.items()})
+    arrays.update(bags=bags.numpy(), coords=coords.numpy(), targets=targets.numpy(),
+                  class_weights=class_weights.numpy(), logits=logits.detach().numpy(),
+                  loss=loss.detach().numpy(), n_heads=np.int64(DIMS["n_heads"]))
+    np.savez_compressed(OUT / "mil_train_step.npz", **arrays)
+    print("loss", float(loss), "logits", logits[0].tolist())
+    print("running_mean after", float(after["transformer.layers.0.0.mhsa.attentions.0.scale_distance.running_mean"]))
+
+
+if __name__ == "__main__":
+    main()

@@ -101,14 +101,29 @@ def alibi_attention(q, k, v, coords_q, coords_k, bias_scale, running_mean, attn_
     return torch.einsum("bqk,bkf->bqf", w, v)
 
 
+def _drop(x: Tensor, keep: Tensor | None, p: float) -> Tensor:
+    """nn.Dropout in training mode with an explicit keep mask (flattened row-major like x)."""
+    if keep is None or p <= 0.0:
+        return x
+    return x * keep.reshape(x.shape).to(x.dtype) / (1.0 - p)
+
+
 def forward(sd: dict[str, Tensor], bags: Tensor, coords: Tensor, mask: Tensor | None, *,
-            n_heads: int | None = None, exact_dist: bool = False) -> Tensor:
-    """VisionTransformer.forward in eval mode (dropout inactive). Returns logits [B, C]."""
+            n_heads: int | None = None, exact_dist: bool = False,
+            drop_masks: dict[int, Tensor] | None = None, p_proj: float = 0.0, p_ff: float = 0.0) -> Tensor:
+    """VisionTransformer.forward. Returns logits [B, C].
+
+    Default: eval mode (dropout inactive).  With ``drop_masks`` the three nn.Dropout sites run in
+    training mode with the given keep masks (site 0: project_features :314-318; 1+2l / 2+2l: the two
+    Dropouts of feed_forward :157-169 in layer l) -- differentiable, used as the gradient oracle.
+    Running-mean handling of training mode is the caller's (see ``running_mean_update``)."""
     dt = bags.dtype
     sd = {k: v.to(dt) if v.is_floating_point() else v for k, v in sd.items()}
+    dm = drop_masks or {}
     B = bags.shape[0]
     use_alibi = any(".query_encoders." in k for k in sd)
     x = F.gelu(F.linear(bags, sd["project_features.0.weight"], sd["project_features.0.bias"]))
+    x = _drop(x, dm.get(0), p_proj)
     d = x.shape[-1]
     x = torch.cat([sd["class_token"].expand(B, 1, d), x], dim=1)
     coords = torch.cat([torch.zeros(B, 1, 2, dtype=coords.dtype), coords], dim=1)
@@ -156,10 +171,50 @@ def forward(sd: dict[str, Tensor], bags: Tensor, coords: Tensor, mask: Tensor | 
             att = F.linear(o, sd[p + "0.mhsa.out_proj.weight"], sd[p + "0.mhsa.out_proj.bias"])
         x = att + x
         h1 = F.layer_norm(x, (d,), sd[p + "1.0.weight"], sd[p + "1.0.bias"], 1e-5)
-        h1 = F.gelu(F.linear(h1, sd[p + "1.1.weight"], sd[p + "1.1.bias"]))
-        x = F.linear(h1, sd[p + "1.4.weight"], sd[p + "1.4.bias"]) + x
+        h1 = _drop(F.gelu(F.linear(h1, sd[p + "1.1.weight"], sd[p + "1.1.bias"])), dm.get(1 + 2 * l), p_ff)
+        x = _drop(F.linear(h1, sd[p + "1.4.weight"], sd[p + "1.4.bias"]), dm.get(2 + 2 * l), p_ff) + x
     x = F.layer_norm(x, (d,), sd["transformer.norm.weight"], sd["transformer.norm.bias"], 1e-5)
     return F.linear(x[:, 0], sd["mlp_head.0.weight"], sd["mlp_head.0.bias"])
+
+
+def running_mean_update(sd: dict[str, Tensor], coords: Tensor) -> dict[str, Tensor]:
+    """Training-mode side effect of _RunningMeanScaler.forward (vision_tranformer.py:23-31) on every
+    head of every layer: rm <- mean(rm + (dist - rm) / n); n += 1, dist = cdist over tokens incl. the
+    class token at (0,0).  Returns an updated copy of the state dict."""
+    B = coords.shape[0]
+    c = torch.cat([torch.zeros(B, 1, 2, dtype=coords.dtype), coords], dim=1)
+    dist = torch.cdist(c, c)
+    out = dict(sd)
+    for k in sd:
+        if k.endswith("scale_distance.running_mean"):
+            nk = k.replace("running_mean", "items_so_far")
+            out[k] = (sd[k] + (dist - sd[k]) / sd[nk]).mean().reshape(1)
+            out[nk] = sd[nk] + 1
+    return out
+
+
+def cross_entropy(logits: Tensor, targets: Tensor, class_weights: Tensor | None) -> Tensor:
+    """LitTileClassifier._step loss (src/stamp/modeling/models/__init__.py:254-258): soft one-hot
+    targets, class weights, mean over the batch = mean_b(-sum_c w_c y_bc log p_bc)."""
+    logp = torch.log_softmax(logits, dim=1)
+    w = class_weights if class_weights is not None else torch.ones(logits.shape[1], dtype=logits.dtype)
+    return -(w[None, :] * targets * logp).sum(dim=1).mean()
+
+
+def train_grads(sd: dict[str, Tensor], bags: Tensor, coords: Tensor, targets: Tensor,
+                class_weights: Tensor | None, *, drop_masks=None, p_proj: float = 0.0, p_ff: float = 0.0,
+                dtype=torch.float64):
+    """One training-mode forward/backward: returns (logits, loss, grads by state-dict key, updated sd)."""
+    sd2 = running_mean_update(sd, coords)
+    params = {k: v.detach().to(dtype).requires_grad_(True) for k, v in sd2.items()
+              if "scale_distance" not in k}
+    full = {**{k: v.to(dtype) for k, v in sd2.items()}, **params}
+    logits = forward(full, bags.to(dtype), coords.to(dtype), None, drop_masks=drop_masks, p_proj=p_proj,
+                     p_ff=p_ff, exact_dist=True)
+    loss = cross_entropy(logits, targets.to(dtype), None if class_weights is None else class_weights.to(dtype))
+    loss.backward()
+    grads = {k: v.grad.detach() for k, v in params.items()}
+    return logits.detach(), loss.detach(), grads, sd2
 
 
 def synthetic_bag(n_tiles: int, dim_input: int, seed: int, batch: int = 1, grid: int = 100,

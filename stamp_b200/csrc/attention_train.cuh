@@ -1,0 +1,37 @@
+// ALiBi attention forward-for-training and backward (attention_train.cu); bf16 operands.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+struct AttnTrainParams {
+    // packed projections, bf16: head h of token s of bag b at  b*batch_stride + s*row_stride + h*head_dim
+    const uint16_t* q;
+    const uint16_t* k;
+    const uint16_t* v;
+    long long row_stride, batch_stride;
+    // forward outputs / backward inputs, [B, S, H*head_dim] with out_row_stride / out_batch_stride
+    uint16_t* out;          // bf16  O = (P - beta Dhat) V
+    float* osm;             // fp32  P V            (same strides as out)
+    float* lse2;            // [B, H, S] log2-domain log-sum-exp of the scaled logits
+    long long out_row_stride, out_batch_stride;
+    int B, S, H;
+    float scale;            // head_dim^-0.5
+    float scale_log2;       // scale * log2(e)
+    const float2* coords;   // [B, S] token coordinates, or null: plain softmax attention
+    const float* beta;      // [H] bias_scale_h
+    const float* inv_rm;    // [H] 1 / running_mean_h
+    // backward only
+    const uint16_t* dout;   // bf16 dO, strides as out
+    float* delta;           // [B, H, S] scratch: dO . Osm
+    uint16_t* dq;           // bf16, strides as q/k/v
+    uint16_t* dk;
+    uint16_t* dv;
+    float* dbeta;           // [H], accumulated with atomicAdd (caller zeroes / accumulates)
+};
+
+int attention_train_fwd(const AttnTrainParams& p, int head_dim, cudaStream_t stream);
+int attention_train_bwd(const AttnTrainParams& p, int head_dim, cudaStream_t stream);
+
+}  // namespace sb

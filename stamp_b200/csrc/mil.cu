@@ -17,6 +17,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
+#include "mil_common.cuh"
 #include "rowops.cuh"
 #include "stamp_b200.h"
 
@@ -143,6 +144,25 @@ bool make_layout(const StampMilConfig* c, int B, int N, Layout* L) {
 }
 
 }  // namespace
+
+int mil_prepare(const float* coords, const uint8_t* mask, float2* coords_s, uint8_t* mask_s, int B, int N,
+                cudaStream_t stream) {
+    if (B <= 0 || N < 0 || (coords_s != nullptr && coords == nullptr && N > 0)) return SB_ERR_BAD_ARG;
+    mil_prepare_kernel<<<grid_for(static_cast<long long>(B) * (N + 1), 256), 256, 0, stream>>>(coords, mask, coords_s,
+                                                                                          mask_s, B, N);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+int cls_head(const float* x, long long bag_stride, int d, const float* norm_w, const float* norm_b,
+             const float* head_w, const float* head_b, int C, int B, float* logits, cudaStream_t stream) {
+    if (x == nullptr || logits == nullptr || B <= 0 || d <= 0 || C <= 0) return SB_ERR_BAD_ARG;
+    cls_head_kernel<<<B, 256, (d + 32) * sizeof(float), stream>>>(x, bag_stride, d, norm_w, norm_b, head_w, head_b, C,
+                                                                 1e-5f, logits);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
 }  // namespace sb
 
 extern "C" {

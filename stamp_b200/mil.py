@@ -14,8 +14,9 @@ SURVEY.md 8b):
 
 The sub-modules below only hold parameters under the reference's names; the arithmetic is one call
 to ``stamp_mil_forward`` (per-head Q/K/V Linears are packed into one [3d, d] GEMM operand, see
-``_pack``).  Inference only in this round: calling it with autograd enabled on trainable
-parameters raises (the backward kernels are SURVEY.md 8f row N1).
+``_pack``) under ``torch.no_grad()`` / ``inference_mode()``; with autograd enabled the call goes
+through the checkpointing forward and the backward kernels of ``stamp_b200.train`` (bf16 operands,
+mask=None branch, use_alibi=True).
 """
 
 from __future__ import annotations
@@ -129,6 +130,8 @@ class VisionTransformer(nn.Module):
                          dim_ff=dim_feedforward, dim_output=dim_output, use_alibi=int(use_alibi))
         self._packed = None       # (key, tensors kept alive, cfg, weights, layers)
         self._workspace: Tensor | None = None
+        self._train_ctx: Tensor | None = None   # checkpoints between a training forward and its backward
+        self._train_gen = 0
 
     # ---- weight packing: reference layout -> GEMM operands (cached until a parameter changes) ----
     def _pack_key(self):
@@ -195,9 +198,13 @@ class VisionTransformer(nn.Module):
         if not bags.is_cuda or not self.class_token.is_cuda:
             raise RuntimeError("stamp_b200 VisionTransformer runs on a CUDA device only (no CPU fallback)")
         if torch.is_grad_enabled() and (bags.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(
-                "the B200 MIL path is forward-only in this round: wrap the call in torch.no_grad() / "
-                "inference_mode() (validation, predict, deploy); training needs the backward kernels")
+            # training_step / heatmap gradients: checkpointing forward + backward kernels (train.py)
+            if mask is not None:
+                raise NotImplementedError(
+                    "gradients are implemented for the mask=None branch (the one every Lightning step and "
+                    "the heatmap Jacobian take); call masked forwards under torch.no_grad()")
+            from .train import mil_forward_with_grad
+            return mil_forward_with_grad(self, bags, coords)
         lib = _bind()
         _, _, cfg, w, layers = self._pack()
         B, N, _ = bags.shape

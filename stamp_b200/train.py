@@ -1,0 +1,355 @@
+"""MIL training step on the B200 path: autograd binding of ``stamp_mil_train_forward/backward``,
+the Lightning ``_step`` loss, the running-mean statistic of training mode and a fused AdamW.
+
+Mirrors, in the reference (paths relative to its root):
+
+* ``LitTileClassifier._step`` / ``training_step``  src/stamp/modeling/models/__init__.py:239-286
+  -> :func:`training_step`, :func:`cross_entropy`
+* ``Base.configure_optimizers``                    src/stamp/modeling/models/__init__.py:133-141
+  -> :func:`configure_optimizers` (``FusedAdamW`` + ``torch.optim.lr_scheduler.OneCycleLR``)
+* ``_RunningMeanScaler.forward`` (training branch)  src/stamp/modeling/models/vision_tranformer.py:23-31
+  -> :func:`update_running_means`
+* ``_gradcam_per_category``                         src/stamp/heatmaps/__init__.py:36-56
+  -> :func:`gradcam_per_category`
+
+All arithmetic runs in ``libstamp_b200.so``; torch is used for memory, streams and autograd graph
+plumbing (``torch.cat`` of the per-head Linear weights routes the packed gradients back to the
+reference's individual parameters).  There is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from .mil import StampMilConfig, VisionTransformer
+
+_TOP_FIELDS = ("proj_w", "proj_b", "class_token", "norm_w", "norm_b", "head_w", "head_b")
+_LAYER_FIELDS = ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "bias_scale", "fc_w", "fc_b", "ln2_w", "ln2_b",
+                 "ff1_w", "ff1_b", "ff2_w", "ff2_b")
+
+
+class StampMilTrainTop(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _TOP_FIELDS]
+
+
+class StampMilTrainLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _LAYER_FIELDS]
+
+
+class StampMilTrainStep(C.Structure):
+    _fields_ = [("p_drop_proj", C.c_float), ("p_drop_ff", C.c_float), ("seed", C.c_ulonglong),
+                ("inv_rm", C.c_void_p)]
+
+
+def _bind() -> C.CDLL:
+    lib = _lib.load()
+    if getattr(lib, "_train_bound", False):
+        return lib
+    P = C.POINTER
+    vp, i32, f32, sz, ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
+    lib.stamp_mil_train_ctx_bytes.restype = sz
+    lib.stamp_mil_train_ctx_bytes.argtypes = [P(StampMilConfig), i32, i32]
+    lib.stamp_mil_train_forward.restype = i32
+    lib.stamp_mil_train_forward.argtypes = [P(StampMilConfig), P(StampMilTrainTop), P(StampMilTrainLayer),
+                                            P(StampMilTrainStep), vp, vp, vp, i32, i32, vp, sz, vp]
+    lib.stamp_mil_train_backward.restype = i32
+    lib.stamp_mil_train_backward.argtypes = [P(StampMilConfig), P(StampMilTrainTop), P(StampMilTrainLayer),
+                                             P(StampMilTrainStep), vp, P(StampMilTrainTop), P(StampMilTrainLayer),
+                                             vp, i32, i32, vp, sz, vp]
+    lib.stamp_mil_train_dropout_mask.restype = i32
+    lib.stamp_mil_train_dropout_mask.argtypes = [C.c_ulonglong, i32, ll, f32, vp, vp]
+    lib.stamp_pairwise_dist_mean_workspace_bytes.restype = sz
+    lib.stamp_pairwise_dist_mean_workspace_bytes.argtypes = [i32, i32]
+    lib.stamp_pairwise_dist_mean.restype = i32
+    lib.stamp_pairwise_dist_mean.argtypes = [vp, i32, i32, vp, vp, sz, vp]
+    lib.stamp_cross_entropy.restype = i32
+    lib.stamp_cross_entropy.argtypes = [vp, vp, vp, i32, i32, f32, vp, vp, vp]
+    lib.stamp_adamw_step.restype = i32
+    lib.stamp_adamw_step.argtypes = [vp, vp, vp, vp, ll, f32, f32, f32, f32, f32, i32, f32, vp]
+    lib._train_bound = True
+    return lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(t: Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must live on a CUDA device: the B200 training path has no CPU fallback")
+
+
+# ---- training-mode running mean ------------------------------------------------------------------
+def pairwise_dist_mean(coords: Tensor) -> Tensor:
+    """Mean over [B, S, S] of the token distances (class token at (0,0) included), device scalar."""
+    _need_cuda(coords, "coords")
+    lib = _bind()
+    B, N, _ = coords.shape
+    c = coords.detach().float().contiguous()
+    ws = torch.empty(lib.stamp_pairwise_dist_mean_workspace_bytes(B, N), dtype=torch.uint8, device=c.device)
+    out = torch.empty(1, dtype=torch.float32, device=c.device)
+    _lib.check(lib.stamp_pairwise_dist_mean(c.data_ptr(), B, N, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            _stream()), "stamp_pairwise_dist_mean")
+    return out
+
+
+def _scalers(model: VisionTransformer):
+    return [a.scale_distance for att, _ in model.transformer.layers for a in att.mhsa.attentions]
+
+
+@torch.no_grad()
+def update_running_means(model: VisionTransformer, coords: Tensor) -> None:
+    """rm <- mean(rm + (dist - rm) / n) = rm + (mean(dist) - rm) / n;  n += 1  for every head's scaler,
+    without a host synchronisation."""
+    sc = _scalers(model)
+    if not sc:
+        return
+    m = pairwise_dist_mean(coords)
+    rms = [s.running_mean for s in sc]
+    ns = [s.items_so_far for s in sc]
+    rm = torch.cat(rms)
+    new = rm + (m - rm) / torch.cat(ns)
+    torch._foreach_copy_(rms, list(new.split(1)))
+    torch._foreach_add_(ns, 1.0)
+
+
+# ---- autograd binding ------------------------------------------------------------------------------
+def _packed_params(model: VisionTransformer) -> list[Tensor]:
+    """fp32 tensors in C-struct order (7 + 13 per layer).  The per-head Linear weights are concatenated
+    with differentiable torch.cat, so autograd splits the packed gradients back onto the reference's
+    parameters."""
+    out = [model.project_features[0].weight, model.project_features[0].bias, model.class_token,
+           model.transformer.norm.weight, model.transformer.norm.bias, model.mlp_head[0].weight,
+           model.mlp_head[0].bias]
+    for att, ff in model.transformer.layers:
+        m = att.mhsa
+        groups = (m.query_encoders, m.key_encoders, m.value_encoders)
+        out += [att.norm.weight, att.norm.bias,
+                torch.cat([e.weight for grp in groups for e in grp]),
+                torch.cat([e.bias for grp in groups for e in grp]),
+                torch.cat([a.bias_scale for a in m.attentions]),
+                m.fc.weight, m.fc.bias, ff[0].weight, ff[0].bias, ff[1].weight, ff[1].bias,
+                ff[4].weight, ff[4].bias]
+    return out
+
+
+def _structs(tensors: list[Tensor], n_layers: int):
+    top = StampMilTrainTop(*[t.data_ptr() for t in tensors[:7]])
+    layers = (StampMilTrainLayer * n_layers)()
+    for l in range(n_layers):
+        layers[l] = StampMilTrainLayer(*[t.data_ptr() for t in tensors[7 + 13 * l: 20 + 13 * l]])
+    return top, layers
+
+
+class _MilTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model: VisionTransformer, bags: Tensor, coords: Tensor, inv_rm: Tensor, p_proj: float,
+                p_ff: float, seed: int, *params: Tensor) -> Tensor:
+        lib = _bind()
+        cfg = StampMilConfig(**model._cfg)
+        B, N, _ = bags.shape
+        dev = bags.device
+        need = lib.stamp_mil_train_ctx_bytes(C.byref(cfg), B, N)
+        if need == 0:
+            raise ValueError("unsupported MIL configuration for the sm_100a training kernels (needs use_alibi, "
+                             "head dim 32/64, dims % 8 == 0, dim_model <= 1024, at least one tile)")
+        buf = model._train_ctx
+        if buf is None or buf.numel() < need or buf.device != dev:
+            buf = model._train_ctx = torch.empty(need, dtype=torch.uint8, device=dev)
+        model._train_gen += 1
+        tensors = [p.detach().float().contiguous() for p in params]
+        top, layers = _structs(tensors, cfg.n_layers)
+        bags32 = bags.detach().float().contiguous()
+        coords32 = coords.detach().float().contiguous()
+        step = StampMilTrainStep(p_proj, p_ff, seed, inv_rm.data_ptr())
+        logits = torch.empty((B, cfg.dim_output), dtype=torch.float32, device=dev)
+        _lib.check(lib.stamp_mil_train_forward(C.byref(cfg), C.byref(top), layers, C.byref(step), bags32.data_ptr(),
+                                               coords32.data_ptr(), logits.data_ptr(), B, N, buf.data_ptr(),
+                                               buf.numel(), _stream()), "stamp_mil_train_forward")
+        ctx.model, ctx.cfg, ctx.gen, ctx.buf = model, cfg, model._train_gen, buf
+        ctx.tensors, ctx.inv_rm, ctx.step_args = tensors, inv_rm, (p_proj, p_ff, seed)
+        ctx.shape, ctx.bags_dtype = (B, N), bags.dtype
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits: Tensor):
+        lib = _bind()
+        model, cfg = ctx.model, ctx.cfg
+        if model._train_gen != ctx.gen:
+            raise RuntimeError("the checkpoint buffer of this forward was overwritten by a later training-mode "
+                               "forward of the same model; run backward before the next forward")
+        B, N = ctx.shape
+        tensors = ctx.tensors
+        sizes = [t.numel() for t in tensors]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dlogits.device)
+        grads = [g.view_as(t) for g, t in zip(flat.split(sizes), tensors)]
+        top, layers = _structs(tensors, cfg.n_layers)
+        gtop, glayers = _structs(grads, cfg.n_layers)
+        step = StampMilTrainStep(*ctx.step_args, ctx.inv_rm.data_ptr())
+        dbags = None
+        if ctx.needs_input_grad[1]:
+            dbags = torch.empty((B, N, cfg.dim_input), dtype=torch.float32, device=dlogits.device)
+        dl = dlogits.detach().float().contiguous()
+        _lib.check(lib.stamp_mil_train_backward(C.byref(cfg), C.byref(top), layers, C.byref(step), dl.data_ptr(),
+                                                C.byref(gtop), glayers, None if dbags is None else dbags.data_ptr(),
+                                                B, N, ctx.buf.data_ptr(), ctx.buf.numel(), _stream()),
+                   "stamp_mil_train_backward")
+        if dbags is not None:
+            dbags = dbags.to(ctx.bags_dtype)
+        return (None, dbags, None, None, None, None, None, *grads)
+
+
+def mil_forward_with_grad(model: VisionTransformer, bags: Tensor, coords: Tensor) -> Tensor:
+    """``model(bags, coords=coords, mask=None)`` with autograd: training mode applies the reference's
+    dropouts and running-mean update, eval mode (heatmaps) neither."""
+    if not model._cfg["use_alibi"]:
+        raise NotImplementedError("the B200 training kernels cover the ALiBi aggregator (use_alibi=True)")
+    _need_cuda(bags, "bags")
+    _need_cuda(model.class_token, "the model")
+    if bags.shape[1] == 0:
+        raise ValueError("empty bags cannot be trained on")
+    L, H = model._cfg["n_layers"], model._cfg["n_heads"]
+    if model.training:
+        update_running_means(model, coords)
+        p_proj = float(model.project_features[2].p)
+        p_ff = float(model.transformer.layers[0][1][3].p) if L > 0 else 0.0
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (p_proj > 0 or p_ff > 0) else 0
+    else:
+        p_proj = p_ff = 0.0
+        seed = 0
+    with torch.no_grad():
+        inv_rm = (1.0 / torch.cat([s.running_mean for s in _scalers(model)]).float()).reshape(L, H).contiguous()
+    return _MilTrainFn.apply(model, bags, coords, inv_rm, p_proj, p_ff, seed, *_packed_params(model)).to(bags.dtype)
+
+
+def dropout_keep_mask(seed: int, site: int, n: int, p: float, device) -> Tensor:
+    """The keep mask the kernels use at a dropout site (tests build the oracle's masks from it)."""
+    lib = _bind()
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    _lib.check(lib.stamp_mil_train_dropout_mask(seed, site, n, p, out.data_ptr(), _stream()),
+               "stamp_mil_train_dropout_mask")
+    return out
+
+
+# ---- loss --------------------------------------------------------------------------------------------
+class _CrossEntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits: Tensor, targets: Tensor, class_weights: Tensor | None) -> Tensor:
+        lib = _bind()
+        _need_cuda(logits, "logits")
+        B, Cn = logits.shape
+        l32 = logits.detach().float().contiguous()
+        t32 = targets.detach().to(l32.device).float().contiguous()
+        w32 = None if class_weights is None else class_weights.detach().to(l32.device).float().contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=l32.device)
+        dl = torch.empty_like(l32)
+        _lib.check(lib.stamp_cross_entropy(l32.data_ptr(), t32.data_ptr(), None if w32 is None else w32.data_ptr(),
+                                           B, Cn, 1.0, loss.data_ptr(), dl.data_ptr(), _stream()),
+                   "stamp_cross_entropy")
+        ctx.save_for_backward(dl)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        (dl,) = ctx.saved_tensors
+        return dl * g, None, None
+
+
+def cross_entropy(logits: Tensor, targets: Tensor, class_weights: Tensor | None = None) -> Tensor:
+    """``F.cross_entropy(logits, soft_targets, weight=class_weights)`` as the reference's ``_step`` calls it."""
+    return _CrossEntropyFn.apply(logits, targets, class_weights)
+
+
+def training_step(model: VisionTransformer, batch, class_weights: Tensor | None = None) -> Tensor:
+    """``LitTileClassifier._step(step_name='training', use_mask=False)``: batch = (bags, coords, bag_sizes, targets)."""
+    bags, coords, _bag_sizes, targets = batch
+    logits = model(bags, coords=coords, mask=None)
+    return cross_entropy(logits, targets.to(logits.dtype), class_weights)
+
+
+# ---- optimiser -----------------------------------------------------------------------------------------
+class FusedAdamW(torch.optim.Optimizer):
+    """``torch.optim.AdamW`` semantics in one kernel launch per step over a flat fp32 parameter buffer.
+
+    The parameters are re-pointed into one contiguous buffer (``p.data`` become views) and so are their
+    ``.grad``; ``flat_grad`` is also what :class:`stamp_b200.sharding.FlatGradAllReducer` all-reduces.
+    Being a ``torch.optim.Optimizer`` it works with ``OneCycleLR`` (which cycles ``lr`` and ``betas[0]``)."""
+
+    def __init__(self, params: Iterable[Tensor], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2) -> None:
+        params = [p for p in params if p.requires_grad]
+        if not params:
+            raise ValueError("FusedAdamW got no trainable parameters")
+        for p in params:
+            _need_cuda(p, "parameters")
+            if p.dtype != torch.float32:
+                raise TypeError("FusedAdamW keeps fp32 master parameters")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        dev = params[0].device
+        sizes = [p.numel() for p in params]
+        self.flat_param = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros_like(self.flat_param)
+        self.exp_avg = torch.zeros_like(self.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        with torch.no_grad():
+            for p, view, gview in zip(params, self.flat_param.split(sizes), self.flat_grad.split(sizes)):
+                view.copy_(p.data.reshape(-1))
+                p.data = view.view_as(p)
+                p.grad = gview.view_as(p)
+        self._step = 0
+
+    def zero_grad(self, set_to_none: bool = False) -> None:  # grads stay views of flat_grad
+        self.flat_grad.zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _bind()
+        g = self.param_groups[0]
+        self._step += 1
+        _lib.check(lib.stamp_adamw_step(self.flat_param.data_ptr(), self.flat_grad.data_ptr(),
+                                        self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.flat_param.numel(),
+                                        float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                                        float(g["weight_decay"]), self._step, float(grad_scale), _stream()),
+                   "stamp_adamw_step")
+        # the kernel wrote through raw pointers: bump the version counter the parameter views share, so
+        # caches keyed on it (VisionTransformer._pack) see the update
+        self.flat_param[:0].zero_()
+        return loss
+
+
+def configure_optimizers(model: VisionTransformer, *, total_steps: int, max_lr: float = 1e-4,
+                         div_factor: float = 25.0):
+    """``Base.configure_optimizers`` (models/__init__.py:133-141): AdamW(lr=1e-3 placeholder) + OneCycleLR."""
+    opt = FusedAdamW(model.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.OneCycleLR(optimizer=opt, total_steps=total_steps, max_lr=max_lr,
+                                                div_factor=div_factor)
+    return opt, sched
+
+
+# ---- heatmaps ---------------------------------------------------------------------------------------------
+def gradcam_per_category(model: VisionTransformer, feats: Tensor, coords: Tensor) -> Tensor:
+    """``_gradcam_per_category`` (src/stamp/heatmaps/__init__.py:36-56): cam[n, c] =
+    softmax_n(|mean_d(feats * d logit_c / d feats)|).  The reference takes ``jacrev`` of the model; here
+    the C rows of the Jacobian are C backward passes of one checkpointed forward."""
+    was_training = model.training
+    model.eval()
+    try:
+        x = feats.detach().float().requires_grad_(True)
+        with torch.enable_grad():
+            logits = mil_forward_with_grad(model, x[None], coords[None].float())[0]
+            rows = []
+            for c in range(logits.shape[0]):
+                (j,) = torch.autograd.grad(logits[c], x, retain_graph=c + 1 < logits.shape[0])
+                rows.append((x.detach() * j).mean(dim=-1).abs())
+        return torch.softmax(torch.stack(rows), dim=-1).T
+    finally:
+        model.train(was_training)

@@ -113,8 +113,10 @@ def test_mil_refuses_autograd_and_cpu(cuda_device):
         with torch.no_grad():
             m(x, coords=c, mask=None)
     m = m.to(cuda_device)
+    # gradients exist for the mask=None branch only (tests/test_mil_train_gpu.py); masked forwards with
+    # autograd enabled must refuse rather than silently drop the graph
     with pytest.raises(NotImplementedError):
-        m(x.to(cuda_device), coords=c.to(cuda_device), mask=None)
+        m(x.to(cuda_device), coords=c.to(cuda_device), mask=torch.zeros(1, 5, dtype=torch.bool, device=cuda_device))
 
 
 def test_mil_full_scale_permutation_invariance(cuda_device):

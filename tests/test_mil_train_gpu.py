@@ -1,0 +1,285 @@
+"""MIL training step on the GPU (C-ABI: stamp_mil_train_forward/backward, stamp_cross_entropy,
+stamp_adamw_step, stamp_pairwise_dist_mean) against
+
+1. the reference's own training step (tests/golden/mil_train_step.npz, written from the reference
+   module by oracle/make_golden_train.py): logits, loss, every parameter gradient, running means;
+2. the fp64 oracle with the kernels' own dropout masks (dropout sites active, p = 0.25 / 0.5);
+3. the fp64 oracle at the default model size (1024 -> 512, 8 heads, 2 layers), ragged bag lengths;
+4. torch.optim.AdamW / F.cross_entropy / torch.cdist as checkers of the small kernels.
+
+Tolerance: the training path computes in bf16 (BASELINE.json configs[3] "training bf16"; 8-bit
+significand) with fp32 accumulation: logits within 2e-2 relative, per-tensor gradients within
+5e-2 of the tensor norm and cosine > 0.998 against fp32/fp64 references."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mil_oracle
+from test_mil_train_cpu import load_train_golden
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 2e-2
+GRAD_TOL = 5e-2
+COS_TOL = 0.998
+
+
+def _model(sd, n_heads, device, dropout=0.0, p_ff=0.0):
+    from stamp_b200.mil import VisionTransformer
+
+    d_model, d_in = sd["project_features.0.weight"].shape
+    n_layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.layers."))
+    m = VisionTransformer(dim_output=sd["mlp_head.0.weight"].shape[0], dim_input=d_in, dim_model=d_model,
+                          n_layers=n_layers, n_heads=n_heads,
+                          dim_feedforward=sd["transformer.layers.0.1.1.weight"].shape[0], dropout=dropout,
+                          use_alibi=True)
+    m.load_state_dict(sd, strict=True)
+    for _, ff in m.transformer.layers:
+        ff[3].p = p_ff
+        ff[5].p = p_ff
+    return m.to(device).train()
+
+
+def _check_grads(model, ref_grads, what):
+    worst = (0.0, None)
+    named = dict(model.named_parameters())
+    assert set(named) == set(ref_grads)
+    scale = max(float(v.norm()) for v in ref_grads.values())
+    for k, ref in ref_grads.items():
+        g = named[k].grad
+        assert g is not None, k
+        g, ref = g.double().cpu().flatten(), ref.double().flatten()
+        err = float((g - ref).norm())
+        floor = 1e-5 * scale          # analytically-zero gradients (key biases) hold round-off only
+        rel = err / max(float(ref.norm()), floor)
+        if float(ref.norm()) > 10 * floor:
+            cos = float(torch.dot(g, ref) / (g.norm() * ref.norm()))
+            assert cos > COS_TOL, (what, k, cos)
+        assert rel < GRAD_TOL, (what, k, rel)
+        if rel > worst[0]:
+            worst = (rel, k)
+    print(f"[{what}] worst per-tensor gradient error {worst[0]:.3e} ({worst[1]})")
+
+
+def test_training_step_matches_reference_golden(cuda_device):
+    from stamp_b200 import train as T
+
+    g = load_train_golden()
+    model = _model(g["sd"], g["n_heads"], cuda_device)
+    bags, coords = g["bags"].to(cuda_device), g["coords"].to(cuda_device)
+    batch = (bags, coords, None, g["targets"].to(cuda_device))
+    loss = T.training_step(model, batch, g["class_weights"].to(cuda_device))
+    loss.backward()
+    # running means: the reference's training-mode side effect
+    for k, v in model.state_dict().items():
+        if "scale_distance" in k:
+            assert torch.allclose(v.cpu(), g["after"][k], rtol=1e-4), k
+    with torch.no_grad():
+        model.eval()
+        # same weights, updated running means, through the fp16 inference path: sanity of the golden itself
+        ev = model(bags, coords=coords, mask=None).cpu()
+        model.train()
+    rel = ((ev - g["logits"]).norm(dim=1) / g["logits"].norm(dim=1)).max()
+    assert rel < 1e-3, float(rel)
+    assert abs(float(loss) - float(g["loss"])) < LOGIT_TOL * max(1.0, float(g["loss"]))
+    print(f"loss {float(loss):.5f} vs reference {float(g['loss']):.5f}")
+    _check_grads(model, g["grads"], "golden")
+
+
+def test_train_forward_logits_match_golden(cuda_device):
+    g = load_train_golden()
+    model = _model(g["sd"], g["n_heads"], cuda_device)
+    out = model(g["bags"].to(cuda_device), coords=g["coords"].to(cuda_device), mask=None)
+    assert out.requires_grad
+    rel = ((out.detach().cpu() - g["logits"]).norm(dim=1) / g["logits"].norm(dim=1)).max()
+    print(f"training-forward logits rel err {float(rel):.3e}")
+    assert rel < LOGIT_TOL
+
+
+def test_dropout_sites_match_oracle_with_kernel_masks(cuda_device):
+    from stamp_b200 import train as T
+
+    g = load_train_golden()
+    p_proj, p_ff = 0.25, 0.5
+    model = _model(g["sd"], g["n_heads"], cuda_device, dropout=p_proj, p_ff=p_ff)
+    bags, coords = g["bags"].to(cuda_device), g["coords"].to(cuda_device)
+    torch.manual_seed(31337)
+    loss = T.training_step(model, (bags, coords, None, g["targets"].to(cuda_device)), g["class_weights"].to(cuda_device))
+    loss.backward()
+    torch.manual_seed(31337)
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    B, n, _ = bags.shape
+    d, ff, M = 128, 128, B * (n + 1)
+    masks = {0: T.dropout_keep_mask(seed, 0, B * n * d, p_proj, cuda_device).cpu().bool()}
+    for l in range(2):
+        masks[1 + 2 * l] = T.dropout_keep_mask(seed, 1 + 2 * l, M * ff, p_ff, cuda_device).cpu().bool()
+        masks[2 + 2 * l] = T.dropout_keep_mask(seed, 2 + 2 * l, M * d, p_ff, cuda_device).cpu().bool()
+    assert abs(float(masks[0].float().mean()) - (1 - p_proj)) < 0.01
+    assert abs(float(masks[1].float().mean()) - (1 - p_ff)) < 0.01
+    assert not torch.equal(masks[1], masks[3])   # sites draw independent masks
+    _, ref_loss, ref_grads, _ = mil_oracle.train_grads(g["sd"], g["bags"], g["coords"], g["targets"],
+                                                       g["class_weights"], drop_masks=masks, p_proj=p_proj, p_ff=p_ff)
+    assert abs(float(loss) - float(ref_loss)) < LOGIT_TOL * max(1.0, float(ref_loss))
+    _check_grads(model, ref_grads, "dropout")
+    # a different seed gives a different loss (the masks are live)
+    model.zero_grad()
+    torch.manual_seed(1)
+    loss2 = T.training_step(model, (bags, coords, None, g["targets"].to(cuda_device)), g["class_weights"].to(cuda_device))
+    assert abs(float(loss2) - float(loss)) > 1e-4
+
+
+@pytest.mark.parametrize("n_tiles,batch", [(1, 2), (63, 1), (64, 2), (65, 1), (512, 2)])
+def test_default_size_gradients_match_oracle(cuda_device, n_tiles, batch):
+    from stamp_b200 import train as T
+
+    sd = mil_oracle.init_state_dict(dim_input=1024, dim_output=2, seed=3)
+    bags, coords = mil_oracle.synthetic_bag(n_tiles, 1024, seed=10 + n_tiles, batch=batch, signal=True)
+    targets = torch.nn.functional.one_hot(torch.arange(batch) % 2, 2).float()
+    model = _model(sd, 8, cuda_device)
+    loss = T.training_step(model, (bags.to(cuda_device), coords.to(cuda_device), None, targets.to(cuda_device)), None)
+    loss.backward()
+    _, ref_loss, ref_grads, _ = mil_oracle.train_grads(sd, bags, coords, targets, None)
+    assert abs(float(loss) - float(ref_loss)) < LOGIT_TOL * max(1.0, float(ref_loss)), (float(loss), float(ref_loss))
+    _check_grads(model, ref_grads, f"default N={n_tiles}")
+
+
+def test_feature_gradient_and_gradcam_match_oracle(cuda_device):
+    """d logits / d feats (heatmaps' jacrev, src/stamp/heatmaps/__init__.py:36-56) and the class-activation map."""
+    from stamp_b200 import train as T
+
+    sd = mil_oracle.init_state_dict(dim_input=64, dim_output=3, dim_model=128, n_heads=2, dim_feedforward=128,
+                                    seed=5, running_mean=9000.0)
+    feats, coords = mil_oracle.synthetic_bag(150, 64, seed=2)
+    model = _model(sd, 2, cuda_device).eval()
+    cam = T.gradcam_per_category(model, feats[0].to(cuda_device), coords[0].to(cuda_device)).cpu()
+    x = feats[0].double().requires_grad_(True)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    jac = torch.autograd.functional.jacobian(
+        lambda b: mil_oracle.forward(sd64, b[None], coords.double(), None, exact_dist=True)[0], x)
+    ref = torch.softmax((x.detach() * jac).mean(-1).abs(), dim=-1).T
+    assert cam.shape == ref.shape == (150, 3)
+    assert torch.allclose(cam.sum(0), torch.ones(3), atol=1e-4)
+    rel = float((cam.double() - ref).norm() / ref.norm())
+    print(f"gradcam rel err {rel:.3e}")
+    assert rel < GRAD_TOL
+    # eval mode: buffers untouched, no dropout
+    assert float(model.transformer.layers[0][0].mhsa.attentions[0].scale_distance.items_so_far) == 1.0
+
+
+def test_pairwise_dist_mean_matches_cdist(cuda_device):
+    from stamp_b200 import train as T
+
+    _, coords = mil_oracle.synthetic_bag(300, 8, seed=4, batch=3)
+    c = torch.cat([torch.zeros(3, 1, 2), coords], dim=1).double()
+    ref = torch.cdist(c, c).mean()
+    out = T.pairwise_dist_mean(coords.to(cuda_device))
+    assert abs(float(out) - float(ref)) < 1e-5 * float(ref)
+
+
+def test_cross_entropy_kernel_matches_torch(cuda_device):
+    from stamp_b200 import train as T
+
+    g = torch.Generator().manual_seed(0)
+    logits = (3 * torch.randn(37, 5, generator=g)).to(cuda_device).requires_grad_(True)
+    targets = torch.softmax(torch.randn(37, 5, generator=g), dim=1).to(cuda_device)   # soft targets
+    w = torch.rand(5, generator=g).to(cuda_device) + 0.5
+    loss = T.cross_entropy(logits, targets, w)
+    (3.0 * loss).backward()
+    ref_l = logits.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_l, targets, weight=w)
+    (3.0 * ref).backward()
+    assert torch.allclose(loss, ref, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(logits.grad, ref_l.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_fused_adamw_matches_torch_adamw(cuda_device):
+    from stamp_b200 import train as T
+
+    g = torch.Generator().manual_seed(1)
+    shapes = [(128, 64), (128,), (3, 128), (1,)]
+    ours = [torch.nn.Parameter(torch.randn(s, generator=g).to(cuda_device)) for s in shapes]
+    theirs = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    opt = T.FusedAdamW(ours, lr=1e-3)
+    ref = torch.optim.AdamW(theirs, lr=1e-3)
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, total_steps=6, max_lr=1e-2)
+    rsched = torch.optim.lr_scheduler.OneCycleLR(ref, total_steps=6, max_lr=1e-2)
+    for _ in range(5):
+        for p, q in zip(ours, theirs):
+            gr = torch.randn(p.shape, generator=g).to(cuda_device)
+            p.grad.copy_(gr)       # grads are views of the flat buffer
+            q.grad = gr.clone()
+        opt.step(); ref.step(); sched.step(); rsched.step()
+        opt.zero_grad()
+    assert float(opt.flat_grad.abs().sum()) == 0.0
+    for p, q in zip(ours, theirs):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
+
+
+def test_golden_adamw_step(cuda_device):
+    """Parameters after the reference's first AdamW step.  The first Adam update is lr * g / (|g| + eps'):
+    where |g| is far above round-off it is +-lr regardless of small gradient errors."""
+    from stamp_b200 import train as T
+
+    g = load_train_golden()
+    model = _model(g["sd"], g["n_heads"], cuda_device)
+    opt = T.FusedAdamW(model.parameters(), lr=1e-3)
+    loss = T.training_step(model, (g["bags"].to(cuda_device), g["coords"].to(cuda_device), None,
+                                   g["targets"].to(cuda_device)), g["class_weights"].to(cuda_device))
+    loss.backward()
+    opt.step()
+    checked = total = 0
+    for k, p in model.named_parameters():
+        ref_after, ref_g = g["after"][k], g["grads"][k]
+        sel = ref_g.abs() > 1e-6
+        diff = (p.detach().cpu() - ref_after).abs()
+        bad = (diff[sel] > 5e-5).float().mean() if sel.any() else torch.tensor(0.0)
+        assert bad < 0.02, (k, float(bad))     # sign flips of near-zero gradients under bf16 only
+        checked += int(sel.sum()); total += ref_g.numel()
+    assert checked > 0.9 * total
+    # inference after the step sees the new weights (pack cache invalidation through the flat buffer)
+    with torch.no_grad():
+        model.eval()
+        a = model(g["bags"].to(cuda_device), coords=g["coords"].to(cuda_device), mask=None)
+    sd_after = {k: v for k, v in g["after"].items()}
+    ref = mil_oracle.forward(sd_after, g["bags"], g["coords"], None)
+    assert ((a.cpu() - ref).norm(dim=1) / ref.norm(dim=1)).max() < 2e-2
+
+
+def test_loss_decreases_on_planted_signal(cuda_device):
+    """configs[3]-style loop at small scale: 5 % of the tiles of class-1 bags carry a mean shift."""
+    from stamp_b200 import train as T
+    from stamp_b200.mil import VisionTransformer
+
+    torch.manual_seed(0)
+    model = VisionTransformer(dim_output=2, dim_input=64, dim_model=128, n_layers=2, n_heads=2, dim_feedforward=128,
+                              dropout=0.0, use_alibi=True).to(cuda_device).train()
+    steps = 30
+    opt, sched = T.configure_optimizers(model, total_steps=steps, max_lr=3e-3)
+    B, n = 16, 200
+    losses = []
+    for it in range(steps):
+        feats, coords = mil_oracle.synthetic_bag(n, 64, seed=100 + it, batch=B)
+        y = torch.arange(B) % 2
+        feats[y == 1, : n // 20] += 1.5
+        batch = (feats.to(cuda_device), coords.to(cuda_device), None,
+                 torch.nn.functional.one_hot(y, 2).float().to(cuda_device))
+        opt.zero_grad()
+        loss = T.training_step(model, batch, None)
+        loss.backward()
+        opt.step()
+        sched.step()
+        losses.append(float(loss))
+    print("losses", [round(v, 3) for v in losses[::5]])
+    assert np.isfinite(losses).all()
+    assert np.mean(losses[-5:]) < 0.6 * np.mean(losses[:5])
+
+
+def test_stale_checkpoint_is_refused(cuda_device):
+    g = load_train_golden()
+    model = _model(g["sd"], g["n_heads"], cuda_device)
+    bags, coords = g["bags"].to(cuda_device), g["coords"].to(cuda_device)
+    a = model(bags, coords=coords, mask=None).sum()
+    model(bags, coords=coords, mask=None)
+    with pytest.raises(RuntimeError):
+        a.backward()
