@@ -4,11 +4,11 @@
 //              (bias subtracted AFTER the softmax, vision_tranformer.py:58-72; inv_rm_h = 1 / running_mean
 //              of _RunningMeanScaler :23-31, beta_h = _ALiBi.bias_scale :40); mask=None branch only --
 //              the one every Lightning step takes (src/stamp/modeling/models/__init__.py:286,293,300).
-//              Besides O (bf16, operand of mhsa.fc) it stores Osm = P V (fp32) and the row log-sum-exp
-//              (log2 domain) so that the backward never materialises an [S,S] tensor either.
+//              Besides O (bf16, operand of mhsa.fc) it stores Osm = P V and Dhat V (fp32) and the row
+//              log-sum-exp (log2 domain) so that the backward never materialises an [S,S] tensor either.
 //   backward : with dW = dO V^T,  delta_q = dO_q . Osm_q,  dS = P * (dW - delta_q):
 //              dV = (P - beta Dhat)^T dO      dK = scale * dS^T Q      dQ = scale * dS K
-//              dbeta_h = - sum_{b,q,k} Dhat_qk dW_qk
+//              dbeta_h = - sum_{b,q,k} Dhat_qk dW_qk = - sum_{b,q} dO_q . (Dhat V)_q   (forward keeps Dhat V)
 //              (what autograd derives for torch.softmax / einsum / cdist in _ALiBi.forward; coordinates
 //              and running_mean carry no gradient).
 //
@@ -279,36 +279,65 @@ attn_train_fwd_kernel(const AttnTrainParams p) {
             const long long o = obase + static_cast<long long>(row_a) * p.out_row_stride + col;
             *reinterpret_cast<uint32_t*>(p.out + o) = pack_bf16(ya0, ya1);
             *reinterpret_cast<float2*>(p.osm + o) = make_float2(sa0, sa1);
+            if constexpr (ALIBI) *reinterpret_cast<float2*>(p.odv + o) = make_float2(o2[nt][0], o2[nt][1]);
         }
         if (row_b < S) {
             const long long o = obase + static_cast<long long>(row_b) * p.out_row_stride + col;
             *reinterpret_cast<uint32_t*>(p.out + o) = pack_bf16(yb0, yb1);
             *reinterpret_cast<float2*>(p.osm + o) = make_float2(sb0, sb1);
+            if constexpr (ALIBI) *reinterpret_cast<float2*>(p.odv + o) = make_float2(o2[nt][2], o2[nt][3]);
         }
     }
 }
 
-// delta[b,h,q] = sum_c dO[b,q,h,c] * Osm[b,q,h,c]; one warp per (token row), all heads
+// Per token row and head, from the fp32 dO the fc data-gradient GEMM produced:
+//   delta[b,h,q] = dO . Osm        dbeta[h] -= dO . (Dhat V)        dO16 = bf16(dO) for the tensor-core kernels
+// dbeta uses the forward's own fp32 Dhat.V accumulator: exactly the derivative of the computed forward,
+// without a second pass over the [S,S] distances.  One warp per token row; per-CTA partials, then atomics.
 __global__ void __launch_bounds__(256)
-attn_delta_kernel(const uint16_t* __restrict__ dout, const float* __restrict__ osm, long long row_stride,
-                  float* __restrict__ delta, int B, int S, int H, int hd) {
-    const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= static_cast<long long>(B) * S) return;
-    const int b = static_cast<int>(row / S), q = static_cast<int>(row % S);
-    const uint16_t* d = dout + row * row_stride;
-    const float* o = osm + row * row_stride;
-    for (int h = 0; h < H; ++h) {
-        float a = 0.f;
-        for (int c = lane * 2; c < hd; c += 64) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(d + h * hd + c);
-            const float2 ov = *reinterpret_cast<const float2*>(o + h * hd + c);
-            a = fmaf(__uint_as_float(w << 16), ov.x, a);
-            a = fmaf(__uint_as_float(w & 0xffff0000u), ov.y, a);
+attn_delta_kernel(const float* __restrict__ dout32, const float* __restrict__ osm, const float* __restrict__ odv,
+                  long long row_stride, uint16_t* __restrict__ dout16, float* __restrict__ delta,
+                  float* __restrict__ dbeta, int B, int S, int H, int hd) {
+    __shared__ float part[64];   // H <= 64
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) part[i] = 0.f;
+    __syncthreads();
+    const long long rows = static_cast<long long>(B) * S;
+    for (long long row = static_cast<long long>(blockIdx.x) * nwarps + (threadIdx.x >> 5); row < rows;
+         row += static_cast<long long>(gridDim.x) * nwarps) {
+        const int b = static_cast<int>(row / S), q = static_cast<int>(row % S);
+        const float* d = dout32 + row * row_stride;
+        const float* o = osm + row * row_stride;
+        const float* v = (odv != nullptr) ? odv + row * row_stride : nullptr;
+        uint16_t* d16 = dout16 + row * row_stride;
+        for (int h = 0; h < H; ++h) {
+            float a = 0.f, bsum = 0.f;
+            for (int c = lane * 2; c < hd; c += 64) {
+                const float2 dv = *reinterpret_cast<const float2*>(d + h * hd + c);
+                const float2 ov = *reinterpret_cast<const float2*>(o + h * hd + c);
+                // delta must cancel against sum_k P dW, and dW is formed from the bf16-rounded dO:
+                // use the same rounded values here (dS = P (dW - delta) is a difference of near-equal terms)
+                const uint32_t pk = pack_bf16(dv.x, dv.y);
+                a = fmaf(__uint_as_float(pk << 16), ov.x, a);
+                a = fmaf(__uint_as_float(pk & 0xffff0000u), ov.y, a);
+                if (v != nullptr) {
+                    const float2 vv = *reinterpret_cast<const float2*>(v + h * hd + c);
+                    bsum = fmaf(dv.x, vv.x, bsum);
+                    bsum = fmaf(dv.y, vv.y, bsum);
+                }
+                *reinterpret_cast<uint32_t*>(d16 + h * hd + c) = pk;
+            }
+            a = warp_sum(a);
+            bsum = warp_sum(bsum);
+            if (lane == 0) {
+                delta[(static_cast<long long>(b) * H + h) * S + q] = a;
+                if (v != nullptr) atomicAdd(part + h, bsum);
+            }
         }
-        a = warp_sum(a);
-        if (lane == 0) delta[(static_cast<long long>(b) * H + h) * S + q] = a;
     }
+    __syncthreads();
+    if (odv != nullptr)
+        for (int i = threadIdx.x; i < H; i += blockDim.x) atomicAdd(dbeta + i, -part[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -422,7 +451,7 @@ attn_bwd_dq_kernel(const AttnTrainParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: dK, dV, dbeta.  CTA = 64 keys of one (bag, head); streams query tiles.
+// backward: dK, dV.  CTA = 64 keys of one (bag, head); streams query tiles.
 // ------------------------------------------------------------------------------------------------
 template <int HD>
 struct DkvSmem {
@@ -489,7 +518,6 @@ attn_bwd_dkv_kernel(const AttnTrainParams p) {
     float dk[ONT][4], dv[ONT][4];
     zero_acc(dk);
     zero_acc(dv);
-    float dbeta = 0.f;
     const float sl2 = p.scale_log2;
 
     for (int qt = 0; qt < ntiles; ++qt) {
@@ -533,8 +561,6 @@ attn_bwd_dkv_kernel(const AttnTrainParams p) {
                         const float dxb = ck_b.x - cq.x, dyb = ck_b.y - cq.y;
                         const float da = valid ? sqrtf(fmaf(dxa, dxa, dya * dya)) * inv_rm : 0.f;
                         const float db = valid ? sqrtf(fmaf(dxb, dxb, dyb * dyb)) * inv_rm : 0.f;
-                        dbeta = fmaf(da, dwt[nt][e], dbeta);
-                        dbeta = fmaf(db, dwt[nt][2 + e], dbeta);
                         wa = fmaf(-beta, da, pa);
                         wb = fmaf(-beta, db, pb);
                     }
@@ -554,11 +580,6 @@ attn_bwd_dkv_kernel(const AttnTrainParams p) {
         __syncthreads();
     }
     if (!warp_active) return;
-    if constexpr (ALIBI) {
-        // rows of padding keys (>= S) hold zero V, hence zero dW: they add nothing
-        dbeta = warp_sum(dbeta);
-        if (lane == 0) atomicAdd(p.dbeta + h, -dbeta);
-    }
     uint16_t* dkb = p.dk + b * p.batch_stride + h * HD;
     uint16_t* dvb = p.dv + b * p.batch_stride + h * HD;
 #pragma unroll
@@ -622,9 +643,11 @@ int bwd_hd(const AttnTrainParams& p, cudaStream_t stream) {
     }
     {
         const long long rows = static_cast<long long>(p.B) * p.S;
-        ProfScope prof(PROF_ROWOP, rows * p.H * HD * 6.0, stream);
-        attn_delta_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(p.dout, p.osm, p.out_row_stride, p.delta,
-                                                                               p.B, p.S, p.H, HD);
+        long long blocks = (rows + 7) / 8;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        ProfScope prof(PROF_ROWOP, rows * p.H * HD * (alibi ? 14.0 : 10.0), stream);
+        attn_delta_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+            p.dout32, p.osm, alibi ? p.odv : nullptr, p.out_row_stride, p.dout, p.delta, p.dbeta, p.B, p.S, p.H, HD);
         count_launch();
     }
     dim3 grid(p.B * p.H, (p.S + TQ - 1) / TQ);
@@ -640,15 +663,18 @@ int bwd_hd(const AttnTrainParams& p, cudaStream_t stream) {
 }  // namespace
 
 int attention_train_fwd(const AttnTrainParams& p, int head_dim, cudaStream_t stream) {
-    if (!params_ok(p) || p.out == nullptr || p.osm == nullptr || p.lse2 == nullptr) return SB_ERR_BAD_ARG;
+    if (!params_ok(p) || p.out == nullptr || p.osm == nullptr || p.lse2 == nullptr ||
+        (p.coords != nullptr && p.odv == nullptr))
+        return SB_ERR_BAD_ARG;
     if (head_dim == 64) return fwd_hd<64>(p, stream);
     if (head_dim == 32) return fwd_hd<32>(p, stream);
     return SB_ERR_UNSUPPORTED;
 }
 
 int attention_train_bwd(const AttnTrainParams& p, int head_dim, cudaStream_t stream) {
-    if (!params_ok(p) || p.dout == nullptr || p.osm == nullptr || p.lse2 == nullptr || p.delta == nullptr ||
-        p.dq == nullptr || p.dk == nullptr || p.dv == nullptr || (p.coords != nullptr && p.dbeta == nullptr))
+    if (!params_ok(p) || p.dout == nullptr || p.dout32 == nullptr || p.osm == nullptr || p.lse2 == nullptr ||
+        p.delta == nullptr || p.dq == nullptr || p.dk == nullptr || p.dv == nullptr || p.H > 64 ||
+        (p.coords != nullptr && (p.dbeta == nullptr || p.odv == nullptr)))
         return SB_ERR_BAD_ARG;
     if (head_dim == 64) return bwd_hd<64>(p, stream);
     if (head_dim == 32) return bwd_hd<32>(p, stream);

@@ -14,6 +14,7 @@ struct AttnTrainParams {
     // forward outputs / backward inputs, [B, S, H*head_dim] with out_row_stride / out_batch_stride
     uint16_t* out;          // bf16  O = (P - beta Dhat) V
     float* osm;             // fp32  P V            (same strides as out)
+    float* odv;             // fp32  Dhat V         (same strides; ALiBi only)
     float* lse2;            // [B, H, S] log2-domain log-sum-exp of the scaled logits
     long long out_row_stride, out_batch_stride;
     int B, S, H;
@@ -23,7 +24,8 @@ struct AttnTrainParams {
     const float* beta;      // [H] bias_scale_h
     const float* inv_rm;    // [H] 1 / running_mean_h
     // backward only
-    const uint16_t* dout;   // bf16 dO, strides as out
+    const float* dout32;    // fp32 dO, strides as out (input)
+    uint16_t* dout;         // bf16 copy of dO written by the backward's first pass (scratch, strides as out)
     float* delta;           // [B, H, S] scratch: dO . Osm
     uint16_t* dq;           // bf16, strides as q/k/v
     uint16_t* dk;

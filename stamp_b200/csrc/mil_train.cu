@@ -14,7 +14,7 @@
 // Checkpointed activations (ctx; M = B*(N+1) token rows, d = dim_model):
 //   bags16 [B*N,F] bf16   z0 [B*N,d] f32 (pre-GELU)   coords_s [M] float2
 //   x[0..2L] [M,d] f32 residual stream before each LayerNorm / after the last block
-//   per layer: xn1, att, xn2 [M,d] bf16; qkv [M,3d] bf16; osm [M,d] f32; lse2 [B,H,S] f32;
+//   per layer: xn1, att, xn2 [M,d] bf16; qkv [M,3d] bf16; osm, odv [M,d] f32; lse2 [B,H,S] f32;
 //              z1 [M,ff] f32 (pre-GELU); h [M,ff] bf16
 // Dropout masks are never stored: keep(i) = hash(seed, site, i) >= p * 2^32, regenerated in backward.
 #include <math.h>
@@ -651,7 +651,7 @@ struct TrainLayout {
     long long S, M, BN;
     size_t off_bags16, off_z0, off_coords, off_x /* (2L+1) x [M,d] f32 */, x_stride;
     size_t off_layer, layer_stride;   // per layer block, offsets inside:
-    size_t l_xn1, l_qkv, l_att, l_osm, l_lse, l_xn2, l_z1, l_h;
+    size_t l_xn1, l_qkv, l_att, l_osm, l_odv, l_lse, l_xn2, l_z1, l_h;
     size_t l_w_qkv, l_w_qkvT, l_w_fc, l_w_fcT, l_w_ff1, l_w_ff1T, l_w_ff2, l_w_ff2T;
     size_t off_w_proj, off_w_projT;
     size_t off_y32 /* [M, max(d,ff)] f32 scratch */, off_dx /* [M,d] f32 */, off_g16a /* [M, max(d,ff)] bf16 */,
@@ -681,6 +681,7 @@ bool make_train_layout(const StampMilConfig* c, int B, int N, TrainLayout* L) {
     L->l_qkv = q; q = au(q + M * 3 * d * 2);
     L->l_att = q; q = au(q + M * d * 2);
     L->l_osm = q; q = au(q + M * d * 4);
+    L->l_odv = q; q = au(q + M * d * 4);
     L->l_lse = q; q = au(q + static_cast<size_t>(B) * H * L->S * 4);
     L->l_xn2 = q; q = au(q + M * d * 2);
     L->l_z1 = q;  q = au(q + M * ff * 4);
@@ -834,7 +835,7 @@ int stamp_mil_train_forward(const StampMilConfig* cfg, const StampMilTrainTop* t
         AttnTrainParams a{};
         a.q = qkv; a.k = qkv + d; a.v = qkv + 2 * d;
         a.row_stride = 3LL * d; a.batch_stride = 3LL * d * S;
-        a.out = att; a.osm = reinterpret_cast<float*>(lb + L.l_osm); a.lse2 = reinterpret_cast<float*>(lb + L.l_lse);
+        a.out = att; a.osm = reinterpret_cast<float*>(lb + L.l_osm); a.odv = reinterpret_cast<float*>(lb + L.l_odv); a.lse2 = reinterpret_cast<float*>(lb + L.l_lse);
         a.out_row_stride = d; a.out_batch_stride = static_cast<long long>(d) * S;
         a.B = B; a.S = S; a.H = H; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
         a.coords = coords_s; a.beta = y.bias_scale; a.inv_rm = step->inv_rm + static_cast<size_t>(l) * H;
@@ -951,17 +952,17 @@ int stamp_mil_train_backward(const StampMilConfig* cfg, const StampMilTrainTop* 
         SB_TRY(wgrad(g16b, d, att, d, gy.fc_w, d, M, d, d, stream));
         SB_TRY(colsum_bf16(g16b, d, M, d, gy.fc_b, stream));
         {
-            GemmParams p = gp_bf16(M, d, d, ST_16, g16a, d, nullptr);                               // d att [M,d] bf16
+            GemmParams p = gp_bf16(M, d, d, ST_32, g32, d, nullptr);                                // d att [M,d] fp32
             SB_TRY(gemm_tn(g16b, d, lb + L.l_w_fcT, d, p, stream));
         }
         AttnTrainParams a{};
         a.q = qkv; a.k = qkv + d; a.v = qkv + 2 * d;
         a.row_stride = 3LL * d; a.batch_stride = 3LL * d * S;
-        a.out = att; a.osm = reinterpret_cast<float*>(lb + L.l_osm); a.lse2 = reinterpret_cast<float*>(lb + L.l_lse);
+        a.out = att; a.osm = reinterpret_cast<float*>(lb + L.l_osm); a.odv = reinterpret_cast<float*>(lb + L.l_odv); a.lse2 = reinterpret_cast<float*>(lb + L.l_lse);
         a.out_row_stride = d; a.out_batch_stride = static_cast<long long>(d) * S;
         a.B = B; a.S = S; a.H = H; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
         a.coords = coords_s; a.beta = y.bias_scale; a.inv_rm = step->inv_rm + static_cast<size_t>(l) * H;
-        a.dout = g16a; a.delta = delta;
+        a.dout32 = g32; a.dout = g16a; a.delta = delta;
         a.dq = g16c; a.dk = g16c + d; a.dv = g16c + 2 * d;
         a.dbeta = gy.bias_scale;
         SB_TRY(attention_train_bwd(a, hd, stream));

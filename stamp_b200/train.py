@@ -291,16 +291,22 @@ class FusedAdamW(torch.optim.Optimizer):
                 raise TypeError("FusedAdamW keeps fp32 master parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         dev = params[0].device
+        # every parameter starts on a 256-byte boundary: the GEMM / vector kernels need 16-byte aligned bases
         sizes = [p.numel() for p in params]
-        self.flat_param = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total)
+            total += (n + 63) // 64 * 64
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros_like(self.flat_param)
         self.exp_avg = torch.zeros_like(self.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
         with torch.no_grad():
-            for p, view, gview in zip(params, self.flat_param.split(sizes), self.flat_grad.split(sizes)):
+            for p, o, n in zip(params, offs, sizes):
+                view = self.flat_param[o:o + n]
                 view.copy_(p.data.reshape(-1))
                 p.data = view.view_as(p)
-                p.grad = gview.view_as(p)
+                p.grad = self.flat_grad[o:o + n].view_as(p)
         self._step = 0
 
     def zero_grad(self, set_to_none: bool = False) -> None:  # grads stay views of flat_grad
