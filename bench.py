@@ -34,6 +34,7 @@ WORKLOAD = "UNI ViT-L/16 tile feature extraction, synthetic 10k-tile slide per G
 SLIDE_TILES = 10_000
 FLOPS_PER_TILE = 123.107e9  # SURVEY.md 8a row a4 / VitArch.flops_per_tile()
 MIL_FLOPS_PER_BAG = 98.8e9  # SURVEY.md 8d, 4096 x 1024 bag, reference math
+MIL_TRAIN_FLOPS_PER_BAG = 296.0e9  # forward + backward ~ 3 x forward, reference math
 
 
 def load_peaks() -> tuple[dict, str]:
@@ -293,6 +294,68 @@ def run_b200(args) -> None:
                    "roofline_frac": (res["value"] / world) * MIL_FLOPS_PER_BAG / 1e12 / peak_tf,
                    "h2d_bytes_per_slide": n_tiles * 1026 * 4}
 
+    # ---- MIL training step (BASELINE configs[3]: ALiBi Transformer-MIL, bf16, 4096 x 1024 bags, global
+    #      batch 8 bags per GPU = 64 on the 8-GPU box): forward + backward + ONE all-reduce of the flat
+    #      gradient buffer over NCCL + fused AdamW.  value: bags resident in HBM; e2e: pinned host bags in,
+    #      loss read back, every step.
+    train_out = None
+    if not args.skip_mil:
+        from stamp_b200 import train as T
+
+        per_gpu, n_tiles = 8, 4096
+        torch.manual_seed(0)   # identical replicas on every rank
+        tmodel = VisionTransformer(dim_output=2, dim_input=1024, dim_model=512, n_layers=2, n_heads=8,
+                                   dim_feedforward=512, dropout=0.0, use_alibi=True).to(dev).train()
+        opt, sched = T.configure_optimizers(tmodel, total_steps=1000)
+        gb = torch.Generator(device=dev).manual_seed(11 + rank)
+        tb = torch.randn(per_gpu, n_tiles, 1024, device=dev, generator=gb).half().float()
+        tc = torch.randint(0, 100, (per_gpu, n_tiles, 2), device=dev, generator=gb).float() * 256.0
+        ty = torch.nn.functional.one_hot(torch.arange(per_gpu, device=dev) % 2, 2).float()
+        tb_host, tc_host = tb.cpu().pin_memory(), tc.cpu().pin_memory()
+
+        def train_step_device():
+            return T.data_parallel_step(tmodel, opt, (tb, tc, None, ty), None, sched)
+
+        def train_step_e2e():
+            b = tb_host.to(dev, non_blocking=True)
+            c = tc_host.to(dev, non_blocking=True)
+            return float(T.data_parallel_step(tmodel, opt, (b, c, None, ty), None, sched).cpu())
+
+        tres = {}
+        n_train = 5
+        for name, fn in (("value", train_step_device), ("e2e", train_step_e2e)):
+            for _ in range(3):
+                fn()
+            barrier()
+            _lib.reset_launch_count()
+            e0.record()
+            for _ in range(n_train):
+                fn()
+            e1.record()
+            barrier()
+            tres[name + "_launches"] = _lib.launch_count()
+            tres[name] = world * per_gpu * n_train / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+        _lib.profile_enable(True)
+        train_step_device()
+        tprof = _lib.profile_summary()
+        _lib.profile_enable(False)
+        ttot = sum(v["ms"] for v in tprof.values()) or 1.0
+        att = tprof["attention"]
+        train_out = {
+            "metric": "MIL training bags/sec (ALiBi Transformer-MIL, 4096x1024 bags, fwd+bwd+all-reduce+AdamW)",
+            "value": tres["value"], "e2e": tres["e2e"], "unit": "bags/s", "dtype": "bf16 operands / fp32 accumulate, "
+            "master weights and gradients", "per_gpu_batch": per_gpu, "global_batch": per_gpu * world,
+            "collective": "1 all-reduce of the flat fp32 gradient buffer per step" if world > 1 else "none (1 GPU)",
+            "grad_bytes_per_step": int(opt.flat_grad.numel() * 4),
+            "h2d_bytes_per_step": int(tb_host.numel() * 4 + tc_host.numel() * 4), "d2h_bytes_per_step": 4,
+            "gpu_launches_per_step": tres["value_launches"] / n_train,
+            "roofline_frac": (tres["value"] / world) * MIL_TRAIN_FLOPS_PER_BAG / 1e12 / peak_tf,
+            "kernel_share_of_step": {k: v["ms"] / ttot for k, v in tprof.items() if v["count"]},
+            "attention_kernels_TFLOPs": att["work"] / (att["ms"] * 1e-3) / 1e12 if att["ms"] > 0 else 0.0,
+        }
+        del tb, tc, tb_host, tc_host, tmodel, opt
+        torch.cuda.empty_cache()
+
     # ---- HBM-bound kernels of the path (rank 0): Macenko over an extraction batch, CHIEF pooling
     hbm_out = None
     if rank == 0 and not args.skip_mil:
@@ -362,7 +425,7 @@ def run_b200(args) -> None:
                        "batch": args.batch, "l2": "inputs (1.5 GB/slide) larger than L2, no flush",
                        "sharding": f"slides[rank::{world}], no data-path collective"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "mil": mil_out, "hbm_kernels": hbm_out,
+            "cpu_baseline": cpu, "mil": mil_out, "mil_train": train_out, "hbm_kernels": hbm_out,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -99,6 +99,18 @@ class FlatGradAllReducer:
 
 
 @torch.no_grad()
+def all_reduce_flat_sum(flat: Tensor) -> float:
+    """Sum one flat gradient buffer over the ranks in place (the single collective of a data-parallel
+    MIL step when the optimiser already keeps its gradients flat, ``train.FusedAdamW.flat_grad``).
+    Returns the factor that turns the sum into the mean; the caller folds it into the optimiser step
+    instead of spending another pass over the buffer."""
+    _, ws = world()
+    if ws > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return 1.0 / ws
+
+
+@torch.no_grad()
 def sync_alibi_running_mean(model: nn.Module) -> None:
     """Ranks see different bags, so the ``scale_distance.running_mean`` buffers the reference
     updates inside forward (vision_tranformer.py:23-31) would diverge: average them."""

@@ -341,6 +341,25 @@ def configure_optimizers(model: VisionTransformer, *, total_steps: int, max_lr: 
     return opt, sched
 
 
+def data_parallel_step(model: VisionTransformer, opt: FusedAdamW, batch, class_weights: Tensor | None = None,
+                       scheduler=None) -> Tensor:
+    """One optimiser step of data-parallel MIL training: every rank runs
+    :func:`training_step` on its own bags, then ONE all-reduce of the flat gradient buffer (NCCL over
+    NVLink; 14.7 MB for the default model) and the average of the ALiBi running means keep the replicas
+    identical.  With a single process it is the plain training step.  Returns the local loss."""
+    from .sharding import all_reduce_flat_sum, sync_alibi_running_mean
+
+    opt.zero_grad()
+    loss = training_step(model, batch, class_weights)
+    loss.backward()
+    scale = all_reduce_flat_sum(opt.flat_grad)
+    sync_alibi_running_mean(model)
+    opt.step(grad_scale=scale)
+    if scheduler is not None:
+        scheduler.step()
+    return loss.detach()
+
+
 # ---- heatmaps ---------------------------------------------------------------------------------------------
 def gradcam_per_category(model: VisionTransformer, feats: Tensor, coords: Tensor) -> Tensor:
     """``_gradcam_per_category`` (src/stamp/heatmaps/__init__.py:36-56): cam[n, c] =

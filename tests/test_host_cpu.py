@@ -63,7 +63,8 @@ def _worker(rank: int, world_size: int, port: int, q) -> None:
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
 
-    from stamp_b200.sharding import FlatGradAllReducer, gather_to_rank0, shard_round_robin, sync_alibi_running_mean
+    from stamp_b200.sharding import (FlatGradAllReducer, all_reduce_flat_sum, gather_to_rank0, shard_round_robin,
+                                     sync_alibi_running_mean)
     from stamp_b200.mil import VisionTransformer
 
     dist.init_process_group("gloo", rank=rank, world_size=world_size)
@@ -74,6 +75,9 @@ def _worker(rank: int, world_size: int, port: int, q) -> None:
         p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
     FlatGradAllReducer(list(model.parameters())).all_reduce_mean()
     ok = all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(model.parameters()))
+    flat = torch.full((1000,), float(rank + 1))
+    scale = all_reduce_flat_sum(flat)          # the FusedAdamW.flat_grad exchange of train.data_parallel_step
+    ok = ok and scale == 0.5 and torch.allclose(flat * scale, torch.full((1000,), 1.5))
     for n, b in model.named_buffers():
         if n.endswith("running_mean"):
             b.fill_(100.0 * (rank + 1))
