@@ -67,7 +67,8 @@ int stamp_b200_profile_summary(double* host_ms, double* host_work, long long* ho
  * (tcgen05 cta_group::2, 256x256) tiles whenever legal */
 void stamp_b200_gemm_force_mode(int mode);
 /* bit 0 (default 1): unmasked head_dim-64 attention runs on the tcgen05 kernels (<= 256 tokens:
- * single-pass ViT kernel; longer: two-pass long-bag kernel); 0: always the general kernel.
+ * single-pass ViT kernel; longer: two-pass long-bag kernel, incl. the training forward / backward);
+ * 0: always the general (mma.sync) kernels.
  * bit 1: prefer the persistent variant of the ViT kernel (tests / A-B timing). */
 void stamp_b200_attention_tc_enable(int on);
 

@@ -18,6 +18,7 @@
 #include <math.h>
 
 #include "attention.cuh"
+#include "attention_train.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -56,10 +57,28 @@ struct MtSmem {
     static constexpr int total = off_bar + 128 + 1024;
 };
 
-template <bool ALIBI>
+// Training variant (TRAIN): bf16 operands; Dhat = dist * inv_rm_h, O = O1 / l - beta_h * O2; besides O (bf16)
+// it stores what the backward needs -- Osm = O1 / l and Dhat V = O2 in fp32 and the row log-sum-exp (log2
+// domain) -- see attention_train.cu.
+struct MilTrainOut {
+    uint16_t* out16;
+    float* osm;
+    float* odv;
+    float* lse2;
+    const float* beta;
+    const float* inv_rm;
+};
+
+template <bool TRAIN>
+__device__ __forceinline__ uint32_t pack_op(float a, float b) {
+    if constexpr (TRAIN) return pack_bf16(a, b);
+    else return pack_f16(a, b);
+}
+
+template <bool ALIBI, bool TRAIN>
 __global__ void __launch_bounds__(MT_THREADS, 1)
 mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_v,
-                   const AttnParams p, int k_col0) {
+                   const AttnParams p, int k_col0, const MilTrainOut t) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -130,8 +149,8 @@ mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_const
     } else if (warp == 1) {
         // ------------------------------------ MMA issuer --------------------------------------
         if (lane == 0) {
-            const uint32_t idesc_s = umma_idesc_f16(128, 128, false, false, false);
-            const uint32_t idesc_o = umma_idesc_f16(128, 64, false, false, true);  // V: MN-major B
+            const uint32_t idesc_s = umma_idesc_f16(128, 128, TRAIN, false, false);
+            const uint32_t idesc_o = umma_idesc_f16(128, 64, TRAIN, false, true);  // V: MN-major B
             const uint64_t q_desc = umma_desc_k128(smem_u32(sQ));
             mbar_wait(qfull, 0);
             int is = 0;  // S tiles issued so far (both passes)
@@ -219,8 +238,13 @@ mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_const
         if constexpr (ALIBI) {
             cb = reinterpret_cast<const float2*>(p.coords) + static_cast<long long>(b) * S;
             if (row < S) cq = __ldg(cb + row);
-            slope = __ldg(p.slope + h) * __ldg(p.dscale + 2 * b);
-            descale = __ldg(p.dscale + 2 * b + 1);
+            if constexpr (TRAIN) {
+                slope = __ldg(t.inv_rm + h);
+                descale = __ldg(t.beta + h);
+            } else {
+                slope = __ldg(p.slope + h) * __ldg(p.dscale + 2 * b);
+                descale = __ldg(p.dscale + 2 * b + 1);
+            }
         }
         float l = 0.f;
         const uint32_t pb = sP_addr + half * TILE_BYTES + r * 128;
@@ -259,8 +283,8 @@ mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_const
                             dv[e] = valid ? sqrt_approx(fmaf(dx, dx, dy * dy)) * slope : 0.f;
                         }
                     }
-                    pw[j >> 1] = pack_f16(pv[0], pv[1]);
-                    if constexpr (ALIBI) dw[j >> 1] = pack_f16(dv[0], dv[1]);
+                    pw[j >> 1] = pack_op<TRAIN>(pv[0], pv[1]);
+                    if constexpr (ALIBI) dw[j >> 1] = pack_op<TRAIN>(dv[0], dv[1]);
                 }
                 // 32 keys = four 16-byte chunks of row r inside this thread's 64-key block
 #pragma unroll
@@ -293,7 +317,31 @@ mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_const
             tmem_ld_32x32b_x32(t_lane + COL_O1 + half * 32, o1);
             if constexpr (ALIBI) tmem_ld_32x32b_x32(t_lane + COL_O2 + half * 32, o2);
             tmem_ld_wait();
-            if (row < S) {
+            if constexpr (TRAIN) {
+                if (row < S) {
+                    if (half == 0) t.lse2[(static_cast<long long>(b) * p.H + h) * S + row] = ms + log2f(l);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float sm[8], y[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            sm[e] = __uint_as_float(o1[j + e]) * inv;
+                            y[e] = sm[e];
+                            if constexpr (ALIBI) y[e] = fmaf(-descale, __uint_as_float(o2[j + e]), sm[e]);
+                        }
+                        *reinterpret_cast<uint4*>(t.out16 + obase + j) =
+                            make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+                        *reinterpret_cast<float4*>(t.osm + obase + j) = make_float4(sm[0], sm[1], sm[2], sm[3]);
+                        *reinterpret_cast<float4*>(t.osm + obase + j + 4) = make_float4(sm[4], sm[5], sm[6], sm[7]);
+                        if constexpr (ALIBI) {
+                            *reinterpret_cast<float4*>(t.odv + obase + j) =
+                                make_float4(__uint_as_float(o2[j]), __uint_as_float(o2[j + 1]), __uint_as_float(o2[j + 2]), __uint_as_float(o2[j + 3]));
+                            *reinterpret_cast<float4*>(t.odv + obase + j + 4) =
+                                make_float4(__uint_as_float(o2[j + 4]), __uint_as_float(o2[j + 5]), __uint_as_float(o2[j + 6]), __uint_as_float(o2[j + 7]));
+                        }
+                    }
+                }
+            } else if (row < S) {
                 float y[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -329,17 +377,18 @@ mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_const
     }
 }
 
-template <bool ALIBI>
-int launch_mil(const CUtensorMap& tm_qk, const CUtensorMap& tm_v, const AttnParams& p, int k_col0, cudaStream_t stream) {
+template <bool ALIBI, bool TRAIN>
+int launch_mil(const CUtensorMap& tm_qk, const CUtensorMap& tm_v, const AttnParams& p, int k_col0,
+               const MilTrainOut& t, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(mil_attn_tc_kernel<ALIBI>, cudaFuncAttributeMaxDynamicSharedMemorySize, MtSmem::total) != cudaSuccess)
+        if (cudaFuncSetAttribute(mil_attn_tc_kernel<ALIBI, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MtSmem::total) != cudaSuccess)
             return SB_ERR_CUDA;
         configured = true;
     }
     dim3 grid(p.B * p.H, (p.S + 127) / 128);
     ProfScope prof(PROF_ATTN, 4.0 * p.B * p.H * static_cast<double>(p.S) * p.S * 64, stream);
-    mil_attn_tc_kernel<ALIBI><<<grid, MT_THREADS, MtSmem::total, stream>>>(tm_qk, tm_v, p, k_col0);
+    mil_attn_tc_kernel<ALIBI, TRAIN><<<grid, MT_THREADS, MtSmem::total, stream>>>(tm_qk, tm_v, p, k_col0, t);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
@@ -369,8 +418,37 @@ int attention_mil_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream)
     if (rc != SB_OK) return rc;
     rc = make_tmap_3d_f16(&tm_v, p.v, static_cast<int>(v_rs), p.S, p.B, v_rs, v_bs, 64, 128);
     if (rc != SB_OK) return rc;
-    return alibi ? launch_mil<true>(tm_qk, tm_v, p, static_cast<int>(koff), stream)
-                 : launch_mil<false>(tm_qk, tm_v, p, static_cast<int>(koff), stream);
+    const MilTrainOut none{};
+    return alibi ? launch_mil<true, false>(tm_qk, tm_v, p, static_cast<int>(koff), none, stream)
+                 : launch_mil<false, false>(tm_qk, tm_v, p, static_cast<int>(koff), none, stream);
+}
+
+// training forward on the same kernel (bf16, extra outputs); SB_ERR_UNSUPPORTED -> mma.sync kernel
+int attention_mil_tc_train_fwd(const AttnTrainParams& tp, int head_dim, cudaStream_t stream) {
+    if (!g_mil_tc_enabled || head_dim != 64 || tp.S <= 256) return SB_ERR_UNSUPPORTED;
+    const long long koff = tp.k - tp.q, voff = tp.v - tp.q;
+    if (koff < 0 || koff + static_cast<long long>(tp.H) * 64 > tp.row_stride || (koff % 8) != 0 || voff < 0 ||
+        (reinterpret_cast<uintptr_t>(tp.q) & 15) != 0 || (reinterpret_cast<uintptr_t>(tp.v) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(tp.out) & 15) != 0 || (reinterpret_cast<uintptr_t>(tp.osm) & 15) != 0 ||
+        (tp.odv != nullptr && (reinterpret_cast<uintptr_t>(tp.odv) & 15) != 0) || (tp.out_row_stride % 8) != 0 ||
+        (tp.out_batch_stride % 8) != 0 || (tp.S + 127) / 128 > 65535)
+        return SB_ERR_UNSUPPORTED;
+    AttnParams p{};
+    p.q = reinterpret_cast<const __half*>(tp.q);
+    p.k = reinterpret_cast<const __half*>(tp.k);
+    p.v = reinterpret_cast<const __half*>(tp.v);
+    p.row_stride = tp.row_stride; p.batch_stride = tp.batch_stride;
+    p.out = tp.out; p.out_row_stride = tp.out_row_stride; p.out_batch_stride = tp.out_batch_stride;
+    p.B = tp.B; p.S = tp.S; p.H = tp.H; p.scale_log2 = tp.scale_log2;
+    p.coords = reinterpret_cast<const float*>(tp.coords);
+    const MilTrainOut t{tp.out, tp.osm, tp.odv, tp.lse2, tp.beta, tp.inv_rm};
+    CUtensorMap tm_qk, tm_v;
+    int rc = make_tmap_3d_f16(&tm_qk, tp.q, static_cast<int>(tp.row_stride), tp.S, tp.B, tp.row_stride, tp.batch_stride, 64, 128);
+    if (rc != SB_OK) return rc;
+    rc = make_tmap_3d_f16(&tm_v, tp.v, static_cast<int>(tp.row_stride), tp.S, tp.B, tp.row_stride, tp.batch_stride, 64, 128);
+    if (rc != SB_OK) return rc;
+    return tp.coords != nullptr ? launch_mil<true, true>(tm_qk, tm_v, p, static_cast<int>(koff), t, stream)
+                                : launch_mil<false, true>(tm_qk, tm_v, p, static_cast<int>(koff), t, stream);
 }
 
 }  // namespace sb

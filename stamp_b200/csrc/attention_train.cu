@@ -650,6 +650,10 @@ int bwd_hd(const AttnTrainParams& p, cudaStream_t stream) {
             p.dout32, p.osm, alibi ? p.odv : nullptr, p.out_row_stride, p.dout, p.delta, p.dbeta, p.B, p.S, p.H, HD);
         count_launch();
     }
+    {
+        const int rc = attention_train_tc_bwd(p, HD, stream);   // long bags, head_dim 64: tcgen05 kernels
+        if (rc != SB_ERR_UNSUPPORTED) return rc;
+    }
     dim3 grid(p.B * p.H, (p.S + TQ - 1) / TQ);
     // algorithmic FLOPs of the reference backward: dV, dW, dQ, dK = four [S,S]x[S,hd] products per head
     ProfScope prof(PROF_ATTN, 8.0 * p.B * p.H * static_cast<double>(p.S) * p.S * HD, stream);
@@ -666,6 +670,10 @@ int attention_train_fwd(const AttnTrainParams& p, int head_dim, cudaStream_t str
     if (!params_ok(p) || p.out == nullptr || p.osm == nullptr || p.lse2 == nullptr ||
         (p.coords != nullptr && p.odv == nullptr))
         return SB_ERR_BAD_ARG;
+    {
+        const int rc = attention_mil_tc_train_fwd(p, head_dim, stream);
+        if (rc != SB_ERR_UNSUPPORTED) return rc;
+    }
     if (head_dim == 64) return fwd_hd<64>(p, stream);
     if (head_dim == 32) return fwd_hd<32>(p, stream);
     return SB_ERR_UNSUPPORTED;

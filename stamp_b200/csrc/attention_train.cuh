@@ -34,6 +34,12 @@ struct AttnTrainParams {
 };
 
 int attention_train_fwd(const AttnTrainParams& p, int head_dim, cudaStream_t stream);
+// tcgen05 two-pass forward for long bags (attention_mil_tc.cu, training variant of the inference kernel);
+// SB_ERR_UNSUPPORTED = outside its envelope (head_dim != 64, <= 256 tokens)
+int attention_mil_tc_train_fwd(const AttnTrainParams& p, int head_dim, cudaStream_t stream);
+// tcgen05 dK/dV + dQ kernels (attention_train_tc.cu); need p.dout / p.delta filled; SB_ERR_UNSUPPORTED = not applicable
+int attention_train_tc_bwd(const AttnTrainParams& p, int head_dim, cudaStream_t stream);
+void attention_train_tc_enable(int on);   // tests: 0 forces the mma.sync kernels
 int attention_train_bwd(const AttnTrainParams& p, int head_dim, cudaStream_t stream);
 
 }  // namespace sb

@@ -5,6 +5,7 @@
 #include <atomic>
 
 #include "attention.cuh"
+#include "attention_train.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 #include "rowops.cuh"
@@ -43,6 +44,7 @@ void stamp_b200_debug_attention_trace(long long* device_buf) {
 void stamp_b200_attention_tc_enable(int on) {
     sb::attention_tc_enable(on);
     sb::attention_mil_tc_enable(on);
+    sb::attention_train_tc_enable(on & 1);
     // bit 1: prefer the persistent single-TMEM-pass ViT kernel (measured equal to the default
     // two-CTA-per-SM kernel on B200, kept as an opt-in alternative)
     sb::attention_vit_persist_enable((on & 2) != 0);

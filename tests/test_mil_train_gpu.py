@@ -146,7 +146,7 @@ def test_dropout_sites_match_oracle_with_kernel_masks(cuda_device):
     assert abs(float(loss2) - float(loss)) > 1e-4
 
 
-@pytest.mark.parametrize("n_tiles,batch", [(1, 2), (63, 1), (64, 2), (65, 1), (512, 2)])
+@pytest.mark.parametrize("n_tiles,batch", [(1, 2), (63, 1), (64, 2), (65, 1), (300, 1), (512, 2), (777, 1)])
 def test_default_size_gradients_match_oracle(cuda_device, n_tiles, batch):
     from stamp_b200 import train as T
 
