@@ -1,6 +1,6 @@
 // tcgen05 backward of the MIL training attention for long bags (head_dim 64, S > 256); same math as the
 // mma.sync kernels in attention_train.cu (see its header), same warp-specialised skeleton as the forward in
-// attention_mil_tc.cu (warp 0 TMA, warp 1 MMA issue, warps 2-9: two threads per TMEM lane).
+// attention_mil_tc.cu (warp 0 TMA, warp 1 MMA issue, warps 2..: NPART threads per TMEM lane).
 //
 // One kernel template, two roles.  A CTA owns a block of 128 rows (TMEM lanes) and streams 64-row tiles:
 //
@@ -26,7 +26,9 @@
 namespace sb {
 namespace {
 
-constexpr int BT_THREADS = 320;
+constexpr int NPART = 4;                       // compute threads per row (TMEM lane): 64 / NPART streamed columns each
+constexpr int CW = 64 / NPART;                 // columns per compute thread
+constexpr int BT_THREADS = 64 + NPART * 128;
 constexpr int BLK_BYTES = 128 * 128;   // 128 rows x 64 bf16
 constexpr int STR_BYTES = 64 * 128;    // 64 rows x 64 bf16
 
@@ -46,6 +48,9 @@ __device__ __forceinline__ float sqrt_apx(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;\n" : "=f"(r) : "f"(x));
     return r;
 }
+
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32b_x32(taddr, r); }
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x32b_x16(taddr, r); }
 
 struct BtSmem {
     static constexpr int off_b0 = 0;                              // block tile 0 (K or Q)
@@ -101,9 +106,9 @@ attn_bwd_tc_kernel(const __grid_constant__ BtMaps tm, const AttnTrainParams p, i
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], 1);
             mbar_init(&sfull[i], 1);
-            mbar_init(&sempty[i], 8);
+            mbar_init(&sempty[i], NPART * 4);
         }
-        mbar_init(pfull, 8);
+        mbar_init(pfull, NPART * 4);
         mbar_init(pempty, 1);
         mbar_init(ofull, 1);
         mbar_init(bfull, 1);
@@ -189,11 +194,11 @@ attn_bwd_tc_kernel(const __grid_constant__ BtMaps tm, const AttnTrainParams p, i
             umma_commit(ofull);
         }
     } else {
-        // ---------- compute: two threads per row (= TMEM lane), 32 streamed columns each ----------
+        // ---------- compute: NPART threads per row (= TMEM lane), CW streamed columns each ----------
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - 2) >> 2;          // which CW-column part of the 64 streamed columns
         const int r = quarter * 32 + lane;
-        const int st = threadIdx.x - 64;           // 0..255 among the compute threads
+        const int st = threadIdx.x - 64;           // 0 .. NPART*128-1 among the compute threads
         const int row = r0 + r;
         const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
         const float sl2 = p.scale_log2;
@@ -218,7 +223,7 @@ attn_bwd_tc_kernel(const __grid_constant__ BtMaps tm, const AttnTrainParams p, i
 
         for (int j = 0; j < nt; ++j) {
             const int s = j & 1;
-            const int c_valid = min(64, S - j * 64) - half * 32;   // valid columns in this thread's 32
+            const int c_valid = min(64, S - j * 64) - half * CW;   // valid columns among this thread's CW
             if constexpr (DKV) {
                 if (st < 64) {
                     const int q = j * 64 + st;
@@ -233,18 +238,17 @@ attn_bwd_tc_kernel(const __grid_constant__ BtMaps tm, const AttnTrainParams p, i
                     }
                     sts_f4(col_addr + ((j & 1) * 64 + st) * 16, v);
                 }
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                asm volatile("bar.sync 1, %0;\n" ::"n"(NPART * 128) : "memory");
             }
             mbar_wait(&sfull[s], (j >> 1) & 1);
-            mbar_wait(pempty, (j & 1) ^ 1);
             tc_fence_after();
-            uint32_t x[32], y[32];
-            tmem_ld_32x32b_x32(t_lane + s * 128 + half * 32, x);
-            tmem_ld_32x32b_x32(t_lane + s * 128 + 64 + half * 32, y);
+            uint32_t x[CW], y[CW];
+            tmem_ld_cols(t_lane + s * 128 + half * CW, x);
+            tmem_ld_cols(t_lane + s * 128 + 64 + half * CW, y);
             tmem_ld_wait();
-            uint32_t ww[16], dw[16];
+            uint32_t ww[CW / 2], dw[CW / 2];
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
+            for (int c = 0; c < CW; c += 2) {
                 float wv[2], dv[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -252,7 +256,7 @@ attn_bwd_tc_kernel(const __grid_constant__ BtMaps tm, const AttnTrainParams p, i
                     float lse = lse_r, dl = dl_r;
                     float4 cv;
                     if constexpr (DKV) {
-                        cv = lds_f4(col_addr + ((j & 1) * 64 + half * 32 + c + e) * 16);
+                        cv = lds_f4(col_addr + ((j & 1) * 64 + half * CW + c + e) * 16);
                         lse = cv.x; dl = cv.y;
                     }
                     const float pv = valid ? ex2_approx(fmaf(__uint_as_float(x[c + e]), sl2, -lse)) : 0.f;
@@ -270,10 +274,13 @@ attn_bwd_tc_kernel(const __grid_constant__ BtMaps tm, const AttnTrainParams p, i
                 dw[c >> 1] = pack_bf16(dv[0], dv[1]);
                 if constexpr (DKV) ww[c >> 1] = pack_bf16(wv[0], wv[1]);
             }
-            // 32 columns = four 16-byte chunks of row r (128 B per row, 128B swizzle)
+            // the W / dS tiles are free once the accumulating products of the previous tile have retired;
+            // waiting here (not before the arithmetic) lets them overlap this tile's exp / sqrt work
+            mbar_wait(pempty, (j & 1) ^ 1);
+            // CW columns = CW/8 16-byte chunks of row r (128 B per row, 128B swizzle)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int off = ((half * 4 + q) ^ (r & 7)) * 16;
+            for (int q = 0; q < CW / 8; ++q) {
+                const int off = ((half * (CW / 8) + q) ^ (r & 7)) * 16;
                 sts_u4b(ds_row + off, make_uint4(dw[4 * q], dw[4 * q + 1], dw[4 * q + 2], dw[4 * q + 3]));
                 if constexpr (DKV)
                     sts_u4b(w_row + off, make_uint4(ww[4 * q], ww[4 * q + 1], ww[4 * q + 2], ww[4 * q + 3]));
@@ -287,18 +294,18 @@ attn_bwd_tc_kernel(const __grid_constant__ BtMaps tm, const AttnTrainParams p, i
             }
         }
 
-        // ---- epilogue: accumulators -> bf16 global; this thread stores 32 of the row's 64 columns ----
+        // ---- epilogue: accumulators -> bf16 global; this thread stores CW of the row's 64 columns ----
         mbar_wait(ofull, 0);
         tc_fence_after();
-        uint32_t a1[32], a0[32];
-        tmem_ld_32x32b_x32(t_lane + COL_A1 + half * 32, a1);
-        if constexpr (DKV) tmem_ld_32x32b_x32(t_lane + COL_A0 + half * 32, a0);
+        uint32_t a1[CW], a0[CW];
+        tmem_ld_cols(t_lane + COL_A1 + half * CW, a1);
+        if constexpr (DKV) tmem_ld_cols(t_lane + COL_A0 + half * CW, a0);
         tmem_ld_wait();
         if (row < S) {
-            const long long o = b * p.batch_stride + static_cast<long long>(row) * p.row_stride + h * 64 + half * 32;
+            const long long o = b * p.batch_stride + static_cast<long long>(row) * p.row_stride + h * 64 + half * CW;
             uint16_t* d1 = (DKV ? p.dk : p.dq) + o;
 #pragma unroll
-            for (int jj = 0; jj < 32; jj += 8) {
+            for (int jj = 0; jj < CW; jj += 8) {
                 float v[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(a1[jj + e]) * p.scale;
