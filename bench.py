@@ -172,6 +172,8 @@ def run_b200(args) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the JSON line only
+        os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier() -> None:

@@ -223,7 +223,9 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w,
  *   loss.backward() through VisionTransformer.forward (vision_tranformer.py:332-384, incl. nn.Dropout of
  *   project_features :314-318 and feed_forward :157-169, dropout 0.5 hard-wired :160), the training-mode
  *   _RunningMeanScaler statistic (:23-31) and optim.AdamW.step (models/__init__.py:133-141).
- * mask=None branch and use_alibi=1 only (the branch every Lightning step takes).  bf16 tensor-core
+ * mask=None branch only (the branch every Lightning step takes); use_alibi=1 (MultiHeadALiBi) or 0
+ * (nn.MultiheadAttention without attention dropout: qkv_w = in_proj_weight, fc = out_proj, bias_scale and
+ * inv_rm unused).  bf16 tensor-core
  * operands, fp32 accumulation / residual stream / master parameters / gradients.
  * The two structs below hold fp32 DEVICE pointers in the reference's layouts; the same struct types
  * carry the gradients, which the backward ACCUMULATES into (zero them first, like optimizer.zero_grad()).
@@ -255,7 +257,7 @@ typedef struct {
 } StampMilTrainStep;
 
 /* bytes of 256-byte-aligned device memory holding checkpoints + scratch between forward and backward
- * (0 = unsupported configuration: needs use_alibi, head dim 32/64, dims % 8 == 0, dim_model <= 1024) */
+ * (0 = unsupported configuration: needs head dim 32/64, dims % 8 == 0, dim_model <= 1024) */
 size_t stamp_mil_train_ctx_bytes(const StampMilConfig* cfg, int B, int N);
 int stamp_mil_train_forward(const StampMilConfig* cfg, const StampMilTrainTop* params,
                             const StampMilTrainLayer* layers, const StampMilTrainStep* step,

@@ -1,4 +1,4 @@
-"""Generates tests/golden/mil_train_step.npz by running the REFERENCE module itself in training mode.
+"""Generates tests/golden/mil_train_step*.npz by running the REFERENCE module itself in training mode.
 
 Run in the build container only (``python oracle/make_golden_train.py``).  Imports
 ``/root/reference/src/stamp/modeling/models/vision_tranformer.py`` by file path, puts the model in
@@ -31,8 +31,14 @@ DIMS = dict(dim_input=64, dim_model=128, n_layers=2, n_heads=2, dim_feedforward=
 
 def main() -> None:
     ref = load_reference()
-    torch.manual_seed(4242)
-    model = ref.VisionTransformer(dropout=0.25, use_alibi=True, **DIMS).train()
+    one_case(ref, use_alibi=True, name="mil_train_step", seed=4242)
+    # the reference's default backbone (VitModelParams.use_alibi = False, dropout = 0.0): nn.MultiheadAttention
+    one_case(ref, use_alibi=False, name="mil_train_step_mha", seed=4343)
+
+
+def one_case(ref, *, use_alibi: bool, name: str, seed: int) -> None:
+    torch.manual_seed(seed)
+    model = ref.VisionTransformer(dropout=0.25 if use_alibi else 0.0, use_alibi=use_alibi, **DIMS).train()
     for m in model.modules():
         if isinstance(m, torch.nn.Dropout):
             m.p = 0.0
@@ -59,9 +65,9 @@ def main() -> None:
     arrays.update(bags=bags.numpy(), coords=coords.numpy(), targets=targets.numpy(),
                   class_weights=class_weights.numpy(), logits=logits.detach().numpy(),
                   loss=loss.detach().numpy(), n_heads=np.int64(DIMS["n_heads"]))
-    np.savez_compressed(OUT / "mil_train_step.npz", **arrays)
-    print("loss", float(loss), "logits", logits[0].tolist())
-    print("running_mean after", float(after["transformer.layers.0.0.mhsa.attentions.0.scale_distance.running_mean"]))
+    arrays["use_alibi"] = np.bool_(use_alibi)
+    np.savez_compressed(OUT / f"{name}.npz", **arrays)
+    print(name, "loss", float(loss), "logits", logits[0].tolist())
 
 
 if __name__ == "__main__":

@@ -203,14 +203,14 @@ def cross_entropy(logits: Tensor, targets: Tensor, class_weights: Tensor | None)
 
 def train_grads(sd: dict[str, Tensor], bags: Tensor, coords: Tensor, targets: Tensor,
                 class_weights: Tensor | None, *, drop_masks=None, p_proj: float = 0.0, p_ff: float = 0.0,
-                dtype=torch.float64):
+                dtype=torch.float64, n_heads: int | None = None):
     """One training-mode forward/backward: returns (logits, loss, grads by state-dict key, updated sd)."""
     sd2 = running_mean_update(sd, coords)
     params = {k: v.detach().to(dtype).requires_grad_(True) for k, v in sd2.items()
               if "scale_distance" not in k}
     full = {**{k: v.to(dtype) for k, v in sd2.items()}, **params}
     logits = forward(full, bags.to(dtype), coords.to(dtype), None, drop_masks=drop_masks, p_proj=p_proj,
-                     p_ff=p_ff, exact_dist=True)
+                     p_ff=p_ff, exact_dist=True, n_heads=n_heads)
     loss = cross_entropy(logits, targets.to(dtype), None if class_weights is None else class_weights.to(dtype))
     loss.backward()
     grads = {k: v.grad.detach() for k, v in params.items()}

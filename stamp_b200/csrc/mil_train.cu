@@ -663,7 +663,7 @@ inline size_t au(size_t v) { return (v + 255) / 256 * 256; }
 bool make_train_layout(const StampMilConfig* c, int B, int N, TrainLayout* L) {
     if (c == nullptr || B <= 0 || N <= 0 || c->dim_input <= 0 || (c->dim_input % 8) != 0 || (c->dim_model % 8) != 0 ||
         (c->dim_ff % 8) != 0 || c->dim_model > 1024 || c->n_heads <= 0 || (c->dim_model % c->n_heads) != 0 ||
-        c->dim_output <= 0 || c->n_layers <= 0 || !c->use_alibi)
+        c->dim_output <= 0 || c->n_layers <= 0)
         return false;
     const int hd = c->dim_model / c->n_heads;
     if (hd != 64 && hd != 32) return false;
@@ -767,8 +767,8 @@ int stamp_mil_train_forward(const StampMilConfig* cfg, const StampMilTrainTop* t
     using namespace sb;
     TrainLayout L;
     if (!make_train_layout(cfg, B, N, &L) || top == nullptr || layers == nullptr || step == nullptr ||
-        bags == nullptr || coords == nullptr || logits == nullptr || ctx == nullptr || step->inv_rm == nullptr ||
-        step->p_drop_proj < 0.f || step->p_drop_proj >= 1.f || step->p_drop_ff < 0.f || step->p_drop_ff >= 1.f)
+        bags == nullptr || coords == nullptr || logits == nullptr || ctx == nullptr ||
+        (cfg->use_alibi && step->inv_rm == nullptr) || step->p_drop_proj < 0.f || step->p_drop_proj >= 1.f || step->p_drop_ff < 0.f || step->p_drop_ff >= 1.f)
         return SB_ERR_BAD_ARG;
     if (ctx_bytes < L.total) return SB_ERR_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(ctx) & 255) != 0) return SB_ERR_BAD_ARG;
@@ -838,7 +838,9 @@ int stamp_mil_train_forward(const StampMilConfig* cfg, const StampMilTrainTop* t
         a.out = att; a.osm = reinterpret_cast<float*>(lb + L.l_osm); a.odv = reinterpret_cast<float*>(lb + L.l_odv); a.lse2 = reinterpret_cast<float*>(lb + L.l_lse);
         a.out_row_stride = d; a.out_batch_stride = static_cast<long long>(d) * S;
         a.B = B; a.S = S; a.H = H; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
-        a.coords = coords_s; a.beta = y.bias_scale; a.inv_rm = step->inv_rm + static_cast<size_t>(l) * H;
+        if (cfg->use_alibi) {   // else: plain softmax attention (nn.MultiheadAttention, vision_tranformer.py:191,218-228)
+            a.coords = coords_s; a.beta = y.bias_scale; a.inv_rm = step->inv_rm + static_cast<size_t>(l) * H;
+        }
         SB_TRY(attention_train_fwd(a, hd, stream));
         // x_mid = x_in + fc(att)
         if (cudaMemcpyAsync(x_mid, x_in, static_cast<size_t>(M) * d * 4, cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
@@ -883,7 +885,8 @@ int stamp_mil_train_backward(const StampMilConfig* cfg, const StampMilTrainTop* 
     using namespace sb;
     TrainLayout L;
     if (!make_train_layout(cfg, B, N, &L) || top == nullptr || layers == nullptr || step == nullptr ||
-        dlogits == nullptr || gtop == nullptr || glayers == nullptr || ctx == nullptr || step->inv_rm == nullptr)
+        dlogits == nullptr || gtop == nullptr || glayers == nullptr || ctx == nullptr ||
+        (cfg->use_alibi && step->inv_rm == nullptr))
         return SB_ERR_BAD_ARG;
     if (ctx_bytes < L.total) return SB_ERR_WORKSPACE;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -961,10 +964,12 @@ int stamp_mil_train_backward(const StampMilConfig* cfg, const StampMilTrainTop* 
         a.out = att; a.osm = reinterpret_cast<float*>(lb + L.l_osm); a.odv = reinterpret_cast<float*>(lb + L.l_odv); a.lse2 = reinterpret_cast<float*>(lb + L.l_lse);
         a.out_row_stride = d; a.out_batch_stride = static_cast<long long>(d) * S;
         a.B = B; a.S = S; a.H = H; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
-        a.coords = coords_s; a.beta = y.bias_scale; a.inv_rm = step->inv_rm + static_cast<size_t>(l) * H;
+        if (cfg->use_alibi) {
+            a.coords = coords_s; a.beta = y.bias_scale; a.inv_rm = step->inv_rm + static_cast<size_t>(l) * H;
+            a.dbeta = gy.bias_scale;
+        }
         a.dout32 = g32; a.dout = g16a; a.delta = delta;
         a.dq = g16c; a.dk = g16c + d; a.dv = g16c + 2 * d;
-        a.dbeta = gy.bias_scale;
         SB_TRY(attention_train_bwd(a, hd, stream));
         SB_TRY(wgrad(g16c, 3LL * d, xn1, d, gy.qkv_w, d, M, 3 * d, d, stream));
         SB_TRY(colsum_bf16(g16c, 3LL * d, M, 3 * d, gy.qkv_b, stream));

@@ -16,7 +16,7 @@ The sub-modules below only hold parameters under the reference's names; the arit
 to ``stamp_mil_forward`` (per-head Q/K/V Linears are packed into one [3d, d] GEMM operand, see
 ``_pack``) under ``torch.no_grad()`` / ``inference_mode()``; with autograd enabled the call goes
 through the checkpointing forward and the backward kernels of ``stamp_b200.train`` (bf16 operands,
-mask=None branch, use_alibi=True).
+mask=None branch, ALiBi or nn.MultiheadAttention variant).
 """
 
 from __future__ import annotations

@@ -126,14 +126,18 @@ def _packed_params(model: VisionTransformer) -> list[Tensor]:
     out = [model.project_features[0].weight, model.project_features[0].bias, model.class_token,
            model.transformer.norm.weight, model.transformer.norm.bias, model.mlp_head[0].weight,
            model.mlp_head[0].bias]
+    H = model._cfg["n_heads"]
     for att, ff in model.transformer.layers:
         m = att.mhsa
-        groups = (m.query_encoders, m.key_encoders, m.value_encoders)
-        out += [att.norm.weight, att.norm.bias,
-                torch.cat([e.weight for grp in groups for e in grp]),
-                torch.cat([e.bias for grp in groups for e in grp]),
-                torch.cat([a.bias_scale for a in m.attentions]),
-                m.fc.weight, m.fc.bias, ff[0].weight, ff[0].bias, ff[1].weight, ff[1].bias,
+        if model._cfg["use_alibi"]:
+            groups = (m.query_encoders, m.key_encoders, m.value_encoders)
+            attn = [torch.cat([e.weight for grp in groups for e in grp]),
+                    torch.cat([e.bias for grp in groups for e in grp]),
+                    torch.cat([a.bias_scale for a in m.attentions]), m.fc.weight, m.fc.bias]
+        else:   # nn.MultiheadAttention: in_proj rows are already q | k | v with the heads side by side
+            attn = [m.in_proj_weight, m.in_proj_bias, torch.zeros(H, device=m.in_proj_weight.device),
+                    m.out_proj.weight, m.out_proj.bias]
+        out += [att.norm.weight, att.norm.bias, *attn, ff[0].weight, ff[0].bias, ff[1].weight, ff[1].bias,
                 ff[4].weight, ff[4].bias]
     return out
 
@@ -156,8 +160,8 @@ class _MilTrainFn(torch.autograd.Function):
         dev = bags.device
         need = lib.stamp_mil_train_ctx_bytes(C.byref(cfg), B, N)
         if need == 0:
-            raise ValueError("unsupported MIL configuration for the sm_100a training kernels (needs use_alibi, "
-                             "head dim 32/64, dims % 8 == 0, dim_model <= 1024, at least one tile)")
+            raise ValueError("unsupported MIL configuration for the sm_100a training kernels (needs head dim "
+                             "32/64, dims % 8 == 0, dim_model <= 1024, at least one tile)")
         buf = model._train_ctx
         if buf is None or buf.numel() < need or buf.device != dev:
             buf = model._train_ctx = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -207,15 +211,18 @@ class _MilTrainFn(torch.autograd.Function):
 def mil_forward_with_grad(model: VisionTransformer, bags: Tensor, coords: Tensor) -> Tensor:
     """``model(bags, coords=coords, mask=None)`` with autograd: training mode applies the reference's
     dropouts and running-mean update, eval mode (heatmaps) neither."""
-    if not model._cfg["use_alibi"]:
-        raise NotImplementedError("the B200 training kernels cover the ALiBi aggregator (use_alibi=True)")
+    alibi = bool(model._cfg["use_alibi"])
+    if not alibi and model.training and any(att.mhsa.dropout > 0 for att, _ in model.transformer.layers):
+        raise NotImplementedError("dropout on the attention weights of nn.MultiheadAttention (use_alibi=False with "
+                                  "dropout > 0) is not implemented in the B200 training kernels")
     _need_cuda(bags, "bags")
     _need_cuda(model.class_token, "the model")
     if bags.shape[1] == 0:
         raise ValueError("empty bags cannot be trained on")
     L, H = model._cfg["n_layers"], model._cfg["n_heads"]
     if model.training:
-        update_running_means(model, coords)
+        if alibi:
+            update_running_means(model, coords)
         p_proj = float(model.project_features[2].p)
         p_ff = float(model.transformer.layers[0][1][3].p) if L > 0 else 0.0
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (p_proj > 0 or p_ff > 0) else 0
@@ -223,7 +230,10 @@ def mil_forward_with_grad(model: VisionTransformer, bags: Tensor, coords: Tensor
         p_proj = p_ff = 0.0
         seed = 0
     with torch.no_grad():
-        inv_rm = (1.0 / torch.cat([s.running_mean for s in _scalers(model)]).float()).reshape(L, H).contiguous()
+        if alibi:
+            inv_rm = (1.0 / torch.cat([s.running_mean for s in _scalers(model)]).float()).reshape(L, H).contiguous()
+        else:
+            inv_rm = torch.ones(L, H, device=bags.device)
     return _MilTrainFn.apply(model, bags, coords, inv_rm, p_proj, p_ff, seed, *_packed_params(model)).to(bags.dtype)
 
 

@@ -8,27 +8,31 @@ reproduce them to fp32 round-off; the GPU tests then compare the CUDA path with 
 from pathlib import Path
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import mil_oracle
 
-GOLD = Path(__file__).resolve().parent / "golden" / "mil_train_step.npz"
+GOLD_DIR = Path(__file__).resolve().parent / "golden"
+TRAIN_GOLDENS = ["mil_train_step", "mil_train_step_mha"]
 
 
-def load_train_golden():
-    z = np.load(GOLD)
+def load_train_golden(name: str = "mil_train_step"):
+    z = np.load(GOLD_DIR / f"{name}.npz")
     sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
     grads = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad/")}
     after = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("after/")}
     t = lambda k: torch.from_numpy(z[k])
     return dict(sd=sd, grads=grads, after=after, bags=t("bags"), coords=t("coords"), targets=t("targets"),
-                class_weights=t("class_weights"), logits=t("logits"), loss=t("loss"), n_heads=int(z["n_heads"]))
+                class_weights=t("class_weights"), logits=t("logits"), loss=t("loss"), n_heads=int(z["n_heads"]),
+                use_alibi=bool(z["use_alibi"]) if "use_alibi" in z.files else True)
 
 
-def test_train_oracle_matches_reference_step():
-    g = load_train_golden()
+@pytest.mark.parametrize("name", TRAIN_GOLDENS)
+def test_train_oracle_matches_reference_step(name):
+    g = load_train_golden(name)
     logits, loss, grads, sd2 = mil_oracle.train_grads(g["sd"], g["bags"], g["coords"], g["targets"],
-                                                      g["class_weights"])
+                                                      g["class_weights"], n_heads=g["n_heads"])
     assert torch.allclose(logits.float(), g["logits"], rtol=2e-4, atol=2e-5)
     assert abs(float(loss) - float(g["loss"])) < 1e-5
     assert set(grads) == set(g["grads"])

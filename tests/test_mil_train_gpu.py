@@ -16,7 +16,7 @@ import pytest
 import torch
 
 from oracle import mil_oracle
-from test_mil_train_cpu import load_train_golden
+from test_mil_train_cpu import TRAIN_GOLDENS, load_train_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -34,7 +34,7 @@ def _model(sd, n_heads, device, dropout=0.0, p_ff=0.0):
     m = VisionTransformer(dim_output=sd["mlp_head.0.weight"].shape[0], dim_input=d_in, dim_model=d_model,
                           n_layers=n_layers, n_heads=n_heads,
                           dim_feedforward=sd["transformer.layers.0.1.1.weight"].shape[0], dropout=dropout,
-                          use_alibi=True)
+                          use_alibi=any(".query_encoders." in k for k in sd))
     m.load_state_dict(sd, strict=True)
     for _, ff in m.transformer.layers:
         ff[3].p = p_ff
@@ -78,10 +78,11 @@ def _check_grads(model, ref_grads, what):
     print(f"[{what}] worst per-tensor gradient error {worst[0]:.3e} ({worst[1]})")
 
 
-def test_training_step_matches_reference_golden(cuda_device):
+@pytest.mark.parametrize("name", TRAIN_GOLDENS)
+def test_training_step_matches_reference_golden(cuda_device, name):
     from stamp_b200 import train as T
 
-    g = load_train_golden()
+    g = load_train_golden(name)
     model = _model(g["sd"], g["n_heads"], cuda_device)
     bags, coords = g["bags"].to(cuda_device), g["coords"].to(cuda_device)
     batch = (bags, coords, None, g["targets"].to(cuda_device))
@@ -101,7 +102,7 @@ def test_training_step_matches_reference_golden(cuda_device):
     loss = loss.detach()
     assert abs(float(loss) - float(g["loss"])) < LOGIT_TOL * max(1.0, float(g["loss"]))
     print(f"loss {float(loss):.5f} vs reference {float(g['loss']):.5f}")
-    _check_grads(model, g["grads"], "golden")
+    _check_grads(model, g["grads"], name)
 
 
 def test_train_forward_logits_match_golden(cuda_device):
@@ -159,6 +160,21 @@ def test_default_size_gradients_match_oracle(cuda_device, n_tiles, batch):
     _, ref_loss, ref_grads, _ = mil_oracle.train_grads(sd, bags, coords, targets, None)
     assert abs(float(loss) - float(ref_loss)) < LOGIT_TOL * max(1.0, float(ref_loss)), (float(loss), float(ref_loss))
     _check_grads(model, ref_grads, f"default N={n_tiles}")
+
+
+def test_default_size_mha_variant_matches_oracle(cuda_device):
+    """use_alibi=False (the reference's default backbone): long bag -> tcgen05 forward / backward, plain softmax."""
+    from stamp_b200 import train as T
+
+    sd = mil_oracle.init_state_dict(dim_input=1024, dim_output=2, seed=4, use_alibi=False)
+    bags, coords = mil_oracle.synthetic_bag(400, 1024, seed=21, batch=2, signal=True)
+    targets = torch.nn.functional.one_hot(torch.arange(2) % 2, 2).float()
+    model = _model(sd, 8, cuda_device)
+    loss = T.training_step(model, (bags.to(cuda_device), coords.to(cuda_device), None, targets.to(cuda_device)), None)
+    loss.backward()
+    _, ref_loss, ref_grads, _ = mil_oracle.train_grads(sd, bags, coords, targets, None, n_heads=8)
+    assert abs(float(loss.detach()) - float(ref_loss)) < LOGIT_TOL * max(1.0, float(ref_loss))
+    _check_grads(model, ref_grads, "mha default N=400")
 
 
 def test_feature_gradient_and_gradcam_match_oracle(cuda_device):
