@@ -358,6 +358,74 @@ def run_b200(args) -> None:
         del tb, tc, tb_host, tc_host, tmodel, opt
         torch.cuda.empty_cache()
 
+    # ---- BASELINE configs[2] per-GPU rate: Macenko stain normalisation + Virchow2 ViT-H/14 (slides shard one
+    #      per GPU exactly like configs[1], so the per-GPU rate is what scales) and configs[4]: one 50k-tile
+    #      slide through the MIL aggregator + its class-activation map (C backward passes), rank 0 only
+    extra_out = None
+    if rank == 0 and not args.skip_mil:
+        from stamp_b200 import train as T
+        from stamp_b200.extractor import virchow2
+        from stamp_b200.macenko import macenko_normalize
+        from stamp_b200.vit import VIRCHOW2_ARCH
+
+        ext_h = virchow2(weights="random", max_batch=96)
+        model_h = ext_h.model.to(dev).eval()
+        n_h = 96 * 21
+        tiles_h = torch.randint(20, 235, (n_h, 224, 224, 3), dtype=torch.uint8, device=dev)
+        norm_h = torch.empty_like(tiles_h)
+
+        def virchow_step():
+            macenko_normalize(tiles_h, out=norm_h)      # one stain fit over the batch of tiles
+            return model_h(norm_h)
+
+        for _ in range(2):
+            virchow_step()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(2):
+            virchow_step()
+        e1.record()
+        torch.cuda.synchronize()
+        v_tps = 2 * n_h / (e0.elapsed_time(e1) * 1e-3)
+        del tiles_h, norm_h, model_h, ext_h
+        torch.cuda.empty_cache()
+
+        n50 = 50_000
+        hm = VisionTransformer(dim_output=2, dim_input=768, dim_model=512, n_layers=2, n_heads=8, dim_feedforward=512,
+                               dropout=0.25, use_alibi=True).to(dev).eval()
+        for att, _ in hm.transformer.layers:           # a trained model's distance scale (mean tile distance)
+            for a in att.mhsa.attentions:
+                a.scale_distance.running_mean.fill_(20000.0)
+        gh = torch.Generator(device=dev).manual_seed(5)
+        f50 = torch.randn(n50, 768, device=dev, generator=gh)
+        cell = torch.randperm(250 * 200, device=dev, generator=gh)[:n50]
+        c50 = torch.stack([(cell % 250).float(), (cell // 250).float()], dim=-1) * 256.0
+
+        def heatmap_step():
+            with torch.inference_mode():
+                logits = hm(f50[None], coords=c50[None], mask=None)
+            cam = T.gradcam_per_category(hm, f50, c50)
+            return logits, cam
+
+        heatmap_step()
+        torch.cuda.synchronize()
+        e0.record()
+        heatmap_step()
+        e1.record()
+        torch.cuda.synchronize()
+        hm_ms = e0.elapsed_time(e1)
+        # reference math for S = 50 001: forward 2 layers x 8 heads x 4 S^2 hd, each Jacobian row a backward (2x)
+        hm_flops = 2 * 8 * 4.0 * (n50 + 1) ** 2 * 64 * (1 + 1 + 2 * 2)
+        extra_out = {
+            "virchow2_macenko": {"metric": "tiles/sec, Macenko + Virchow2 ViT-H/14 (BASELINE configs[2], per GPU)",
+                                 "value": v_tps, "unit": "tiles/s", "batch": 96,
+                                 "roofline_frac": v_tps * VIRCHOW2_ARCH.flops_per_tile() / 1e12 / peak_tf},
+            "heatmap_50k": {"metric": "50k-tile slide: whole-bag MIL forward + grad-CAM over 2 classes (BASELINE configs[4])",
+                            "ms_per_slide": hm_ms, "unit": "ms", "attention_roofline_frac": hm_flops / (hm_ms * 1e-3) / 1e12 / peak_tf},
+        }
+        del f50, c50, hm
+        torch.cuda.empty_cache()
+
     # ---- HBM-bound kernels of the path (rank 0): Macenko over an extraction batch, CHIEF pooling
     hbm_out = None
     if rank == 0 and not args.skip_mil:
@@ -427,7 +495,8 @@ def run_b200(args) -> None:
                        "batch": args.batch, "l2": "inputs (1.5 GB/slide) larger than L2, no flush",
                        "sharding": f"slides[rank::{world}], no data-path collective"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "mil": mil_out, "mil_train": train_out, "hbm_kernels": hbm_out,
+            "cpu_baseline": cpu, "mil": mil_out, "mil_train": train_out, "other_configs": extra_out,
+            "hbm_kernels": hbm_out,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -132,6 +132,7 @@ class VisionTransformer(nn.Module):
         self._workspace: Tensor | None = None
         self._train_ctx: Tensor | None = None   # checkpoints between a training forward and its backward
         self._train_gen = 0
+        self._train_state = None
 
     # ---- weight packing: reference layout -> GEMM operands (cached until a parameter changes) ----
     def _pack_key(self):

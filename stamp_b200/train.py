@@ -150,9 +150,63 @@ def _structs(tensors: list[Tensor], n_layers: int):
     return top, layers
 
 
+class _TrainState:
+    """What one checkpointing forward leaves for its backward(s) (not a pytree: functorch passes it through)."""
+
+    __slots__ = ("model", "cfg", "gen", "buf", "tensors", "inv_rm", "step_args", "shape", "bags_dtype")
+
+
+def _run_backward(st: _TrainState, dlogits: Tensor, want_dbags: bool) -> tuple[Tensor | None, list[Tensor]]:
+    lib = _bind()
+    model, cfg = st.model, st.cfg
+    if model._train_gen != st.gen:
+        raise RuntimeError("the checkpoint buffer of this forward was overwritten by a later training-mode "
+                           "forward of the same model; run backward before the next forward")
+    B, N = st.shape
+    sizes = [t.numel() for t in st.tensors]
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dlogits.device)
+    grads = [g.view_as(t) for g, t in zip(flat.split(sizes), st.tensors)]
+    top, layers = _structs(st.tensors, cfg.n_layers)
+    gtop, glayers = _structs(grads, cfg.n_layers)
+    step = StampMilTrainStep(*st.step_args, st.inv_rm.data_ptr())
+    dbags = torch.empty((B, N, cfg.dim_input), dtype=torch.float32, device=dlogits.device) if want_dbags else None
+    dl = dlogits.detach().float().contiguous()
+    _lib.check(lib.stamp_mil_train_backward(C.byref(cfg), C.byref(top), layers, C.byref(step), dl.data_ptr(),
+                                            C.byref(gtop), glayers, None if dbags is None else dbags.data_ptr(),
+                                            B, N, st.buf.data_ptr(), st.buf.numel(), _stream()),
+               "stamp_mil_train_backward")
+    return dbags, grads
+
+
+class _MilBwdFn(torch.autograd.Function):
+    """The backward as a Function of its own, so that functorch can vmap it: ``torch.func.jacrev(model)``
+    (heatmaps, src/stamp/heatmaps/__init__.py:41-52) maps the C one-hot cotangents through :meth:`vmap`,
+    which runs the C backward passes of the one checkpointed forward one after the other."""
+
+    @staticmethod
+    def forward(dlogits: Tensor, st: _TrainState, want_dbags: bool):
+        dbags, grads = _run_backward(st, dlogits, want_dbags)
+        if dbags is None:
+            dbags = dlogits.new_zeros(0)
+        return (dbags.to(st.bags_dtype), *grads)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        pass
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise NotImplementedError("double backward through the B200 MIL kernels is not implemented")
+
+    @staticmethod
+    def vmap(info, in_dims, dlogits, st, want_dbags):
+        rows = [_MilBwdFn.apply(dlogits.select(in_dims[0], i), st, want_dbags) for i in range(info.batch_size)]
+        return tuple(torch.stack(r) for r in zip(*rows)), tuple(0 for _ in rows[0])
+
+
 class _MilTrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model: VisionTransformer, bags: Tensor, coords: Tensor, inv_rm: Tensor, p_proj: float,
+    def forward(model: VisionTransformer, bags: Tensor, coords: Tensor, inv_rm: Tensor, p_proj: float,
                 p_ff: float, seed: int, *params: Tensor) -> Tensor:
         lib = _bind()
         cfg = StampMilConfig(**model._cfg)
@@ -175,37 +229,23 @@ class _MilTrainFn(torch.autograd.Function):
         _lib.check(lib.stamp_mil_train_forward(C.byref(cfg), C.byref(top), layers, C.byref(step), bags32.data_ptr(),
                                                coords32.data_ptr(), logits.data_ptr(), B, N, buf.data_ptr(),
                                                buf.numel(), _stream()), "stamp_mil_train_forward")
-        ctx.model, ctx.cfg, ctx.gen, ctx.buf = model, cfg, model._train_gen, buf
-        ctx.tensors, ctx.inv_rm, ctx.step_args = tensors, inv_rm, (p_proj, p_ff, seed)
-        ctx.shape, ctx.bags_dtype = (B, N), bags.dtype
+        st = _TrainState()
+        st.model, st.cfg, st.gen, st.buf = model, cfg, model._train_gen, buf
+        st.tensors, st.inv_rm, st.step_args = tensors, inv_rm, (p_proj, p_ff, seed)
+        st.shape, st.bags_dtype = (B, N), bags.dtype
+        model._train_state = st          # handed to setup_context (the functorch-compatible Function protocol)
         return logits
 
     @staticmethod
+    def setup_context(ctx, inputs, output):
+        # functorch calls this twice for one forward (once per transform level): the hand-over slot stays set
+        ctx.st = inputs[0]._train_state
+
+    @staticmethod
     def backward(ctx, dlogits: Tensor):
-        lib = _bind()
-        model, cfg = ctx.model, ctx.cfg
-        if model._train_gen != ctx.gen:
-            raise RuntimeError("the checkpoint buffer of this forward was overwritten by a later training-mode "
-                               "forward of the same model; run backward before the next forward")
-        B, N = ctx.shape
-        tensors = ctx.tensors
-        sizes = [t.numel() for t in tensors]
-        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dlogits.device)
-        grads = [g.view_as(t) for g, t in zip(flat.split(sizes), tensors)]
-        top, layers = _structs(tensors, cfg.n_layers)
-        gtop, glayers = _structs(grads, cfg.n_layers)
-        step = StampMilTrainStep(*ctx.step_args, ctx.inv_rm.data_ptr())
-        dbags = None
-        if ctx.needs_input_grad[1]:
-            dbags = torch.empty((B, N, cfg.dim_input), dtype=torch.float32, device=dlogits.device)
-        dl = dlogits.detach().float().contiguous()
-        _lib.check(lib.stamp_mil_train_backward(C.byref(cfg), C.byref(top), layers, C.byref(step), dl.data_ptr(),
-                                                C.byref(gtop), glayers, None if dbags is None else dbags.data_ptr(),
-                                                B, N, ctx.buf.data_ptr(), ctx.buf.numel(), _stream()),
-                   "stamp_mil_train_backward")
-        if dbags is not None:
-            dbags = dbags.to(ctx.bags_dtype)
-        return (None, dbags, None, None, None, None, None, *grads)
+        want = bool(ctx.needs_input_grad[1])
+        dbags, *grads = _MilBwdFn.apply(dlogits, ctx.st, want)
+        return (None, dbags if want else None, None, None, None, None, None, *grads)
 
 
 def mil_forward_with_grad(model: VisionTransformer, bags: Tensor, coords: Tensor) -> Tensor:

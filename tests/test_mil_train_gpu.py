@@ -204,6 +204,16 @@ def test_feature_gradient_and_gradcam_match_oracle(cuda_device):
     rel = float((cam.double() - ref).norm() / ref.norm())
     print(f"gradcam rel err {rel:.3e}")
     assert rel < GRAD_TOL
+    # the reference's own call (heatmaps/__init__.py:41-52): torch.func.jacrev straight through the module
+    from torch.func import jacrev
+    fd, cd = feats[0].to(cuda_device), coords[0].to(cuda_device)
+    jf = jacrev(lambda b: model.forward(b.unsqueeze(0), coords=cd.unsqueeze(0), mask=None).squeeze(0))(fd)
+    assert jf.shape == (3, 150, 64)
+    jfrel = float((jf.double().cpu() - jac).norm() / jac.norm())
+    print(f"jacrev Jacobian rel err {jfrel:.3e}")
+    assert jfrel < GRAD_TOL
+    cam_ref_style = torch.softmax((fd * jf).mean(-1).abs(), dim=-1).permute(-1, -2)
+    assert torch.allclose(cam_ref_style.cpu(), cam, atol=1e-6)
     # eval mode: buffers untouched, no dropout
     assert float(model.transformer.layers[0][0].mhsa.attentions[0].scale_distance.items_so_far) == 1.0
 
