@@ -55,6 +55,9 @@ class VitConfig:
     mlp: str = "gelu"           # "gelu" | "swiglu"
     reg_tokens: int = 0
     ln_eps: float = 1e-6
+    no_embed_class: bool = False  # timm: pos_embed covers the patch tokens only, prefix tokens get none
+    mean: tuple = IMAGENET_MEAN
+    std: tuple = IMAGENET_STD
 
     @property
     def n_patches(self) -> int:
@@ -83,12 +86,23 @@ class VitConfig:
 UNI = VitConfig("uni")  # ViT-L/16
 VIRCHOW2 = VitConfig("virchow2", patch=14, dim=1280, depth=32, heads=16, mlp_hidden=6832,
                      mlp="swiglu", reg_tokens=4)  # ViT-H/14, int(1280 * 5.3375) = 6832
+# SURVEY.md 8f row N4 -- same kernels, other configs (all [external]: timm / HF model cards):
+# UNI2-h, src/stamp/preprocessing/extractor/uni2.py:18-32 (ViT-H/14, 8 register tokens, SwiGLUPacked,
+# no_embed_class, int(1536 * 5.33334) = 8192)
+UNI2 = VitConfig("uni2", patch=14, dim=1536, depth=24, heads=24, mlp_hidden=8192, mlp="swiglu", reg_tokens=8,
+                 no_embed_class=True)
+# H-optimus-0 / -1, h_optimus_0.py:14-28: timm vit_giant_patch14_reg4_dinov2 at 224 px, own mean / std
+H_OPTIMUS = VitConfig("h_optimus_0", patch=14, dim=1536, depth=40, heads=24, mlp_hidden=8192, mlp="swiglu",
+                      reg_tokens=4, no_embed_class=True, mean=(0.707223, 0.578729, 0.703617),
+                      std=(0.211883, 0.230117, 0.177517))
 
 
-def tiny_config(mlp: str = "gelu", reg_tokens: int = 0, patch: int = 16, depth: int = 2) -> VitConfig:
+def tiny_config(mlp: str = "gelu", reg_tokens: int = 0, patch: int = 16, depth: int = 2,
+                no_embed_class: bool = False, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> VitConfig:
     """A small architecture-complete ViT for CPU-speed tests (configs[0] plumbing)."""
     return VitConfig(f"tiny-{mlp}-r{reg_tokens}-p{patch}", patch=patch, dim=128, depth=depth, heads=2,
-                     mlp_hidden=512 if mlp == "gelu" else 688, mlp=mlp, reg_tokens=reg_tokens)
+                     mlp_hidden=512 if mlp == "gelu" else 688, mlp=mlp, reg_tokens=reg_tokens,
+                     no_embed_class=no_embed_class, mean=mean, std=std)
 
 
 def make_weights(cfg: VitConfig, seed: int = 1234, dtype=torch.float32) -> dict[str, Tensor]:
@@ -108,7 +122,7 @@ def make_weights(cfg: VitConfig, seed: int = 1234, dtype=torch.float32) -> dict[
     w["cls_token"] = tn(1, 1, D)
     if cfg.reg_tokens:
         w["reg_token"] = tn(1, cfg.reg_tokens, D)
-    w["pos_embed"] = 0.02 * torch.randn(1, cfg.n_tokens, D, generator=g)
+    w["pos_embed"] = 0.02 * torch.randn(1, cfg.n_patches if cfg.no_embed_class else cfg.n_tokens, D, generator=g)
     w["patch_embed.proj.weight"] = tn(D, 3, cfg.patch, cfg.patch)
     w["patch_embed.proj.bias"] = tn(D)
     for i in range(cfg.depth):
@@ -125,11 +139,12 @@ def make_weights(cfg: VitConfig, seed: int = 1234, dtype=torch.float32) -> dict[
     return {k: v.to(dtype) for k, v in w.items()}
 
 
-def transform_u8(tiles_u8: Tensor, dtype=torch.float32) -> Tensor:
-    """uint8 [B,H,W,3] -> normalised CHW float (ToTensor + Normalize, ImageNet constants)."""
+def transform_u8(tiles_u8: Tensor, dtype=torch.float32, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> Tensor:
+    """uint8 [B,H,W,3] -> normalised CHW float (ToTensor + Normalize; ImageNet constants for UNI / Virchow2,
+    explicit ones for e.g. H-optimus, h_optimus_0.py:26-28)."""
     x = tiles_u8.permute(0, 3, 1, 2).to(dtype) / 255.0
-    mean = torch.tensor(IMAGENET_MEAN, dtype=dtype).view(1, 3, 1, 1)
-    std = torch.tensor(IMAGENET_STD, dtype=dtype).view(1, 3, 1, 1)
+    mean = torch.tensor(mean, dtype=dtype).view(1, 3, 1, 1)
+    std = torch.tensor(std, dtype=dtype).view(1, 3, 1, 1)
     return (x - mean) / std
 
 
@@ -162,7 +177,12 @@ def forward_tokens(w: dict[str, Tensor], cfg: VitConfig, x: Tensor) -> Tensor:
     prefix = [w["cls_token"].expand(B, -1, -1)]
     if cfg.reg_tokens:
         prefix.append(w["reg_token"].expand(B, -1, -1))
-    x = torch.cat(prefix + [x], dim=1) + w["pos_embed"]
+    if cfg.no_embed_class:
+        # timm VisionTransformer._pos_embed, no_embed_class=True (UNI2-h, H-optimus: uni2.py:27,
+        # timm vit_giant_patch14_reg4_dinov2): position table added to the patch tokens BEFORE the concat
+        x = torch.cat(prefix + [x + w["pos_embed"]], dim=1)
+    else:
+        x = torch.cat(prefix + [x], dim=1) + w["pos_embed"]
     for i in range(cfg.depth):
         x = block_forward(w, f"blocks.{i}.", x, cfg)
     return F.layer_norm(x, (cfg.dim,), w["norm.weight"], w["norm.bias"], cfg.ln_eps)
@@ -171,7 +191,7 @@ def forward_tokens(w: dict[str, Tensor], cfg: VitConfig, x: Tensor) -> Tensor:
 def forward(w: dict[str, Tensor], cfg: VitConfig, tiles_u8: Tensor) -> Tensor:
     """uint8 HWC tiles -> class-token features [B, D] (what ``extract_`` stores, before .half())."""
     dt = w["norm.weight"].dtype
-    return forward_tokens(w, cfg, transform_u8(tiles_u8, dt))[:, 0]
+    return forward_tokens(w, cfg, transform_u8(tiles_u8, dt, cfg.mean, cfg.std))[:, 0]
 
 
 def synthetic_tiles(n: int, seed: int, img: int = 224) -> Tensor:

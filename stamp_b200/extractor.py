@@ -23,7 +23,8 @@ import numpy as np
 import torch
 from torch import Tensor, nn
 
-from .vit import UNI_ARCH, VIRCHOW2_ARCH, TileEncoder, VitArch, random_state_dict
+from .vit import (H_OPTIMUS_ARCH, UNI2_ARCH, UNI_ARCH, VIRCHOW2_ARCH, TileEncoder, VitArch,
+                  random_state_dict)
 
 ExtractorModel = TypeVar("ExtractorModel", bound=nn.Module)
 
@@ -88,6 +89,31 @@ def virchow2(weights=None, max_batch: int = 96) -> Extractor[TileEncoder]:
 
         hub_kwargs = dict(mlp_layer=SwiGLUPacked, act_layer=torch.nn.SiLU)
     return _make(VIRCHOW2_ARCH, "virchow2", weights, "hf-hub:paige-ai/Virchow2", hub_kwargs, max_batch)
+
+
+def uni2(weights=None, max_batch: int = 96) -> Extractor[TileEncoder]:
+    """UNI2-h ViT-H/14 with 8 register tokens (reference: .../extractor/uni2.py:16-46)."""
+    hub_kwargs: dict = {}
+    if weights is None:
+        from timm.layers import SwiGLUPacked
+
+        hub_kwargs = dict(img_size=224, patch_size=14, depth=24, num_heads=24, init_values=1e-5, embed_dim=1536,
+                          mlp_ratio=2.66667 * 2, num_classes=0, no_embed_class=True, mlp_layer=SwiGLUPacked,
+                          act_layer=torch.nn.SiLU, reg_tokens=8, dynamic_img_size=True)
+    return _make(UNI2_ARCH, "uni2", weights, "hf-hub:MahmoodLab/UNI2-h", hub_kwargs, max_batch)
+
+
+def h_optimus_0(weights=None, max_batch: int = 64) -> Extractor[TileEncoder]:
+    """H-optimus-0 ViT-g/14 (reference: .../extractor/h_optimus_0.py:14-34; its Resize(224) is the identity
+    on STAMP's 224 px tiles, mean / std are the model card's)."""
+    return _make(H_OPTIMUS_ARCH, "h_optimus_0", weights, "hf-hub:bioptimus/H-optimus-0",
+                 dict(init_values=1e-5, dynamic_img_size=False), max_batch)
+
+
+def h_optimus_1(weights=None, max_batch: int = 64) -> Extractor[TileEncoder]:
+    """H-optimus-1, same architecture and preprocessing (reference: .../extractor/h_optimus_1.py)."""
+    return _make(H_OPTIMUS_ARCH, "h_optimus_1", weights, "hf-hub:bioptimus/H-optimus-1",
+                 dict(init_values=1e-5, dynamic_img_size=False), max_batch)
 
 
 def extract_slide_features(extractor: Extractor, tiles_u8: Tensor, device: torch.device | str = "cuda",

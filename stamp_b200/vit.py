@@ -38,6 +38,7 @@ class VitArch:
     ln_eps: float = 1e-6
     mean: tuple = IMAGENET_MEAN
     std: tuple = IMAGENET_STD
+    no_embed_class: bool = False  # timm: pos_embed has n_patches rows, prefix tokens get no position
 
     @property
     def n_patches(self) -> int:
@@ -72,6 +73,15 @@ class VitArch:
 UNI_ARCH = VitArch("uni")
 VIRCHOW2_ARCH = VitArch("virchow2", patch=14, dim=1280, depth=32, heads=16, mlp_hidden=6832,
                         mlp="swiglu", reg_tokens=4)
+# uni2.py:18-32 -> ViT-H/14, embed 1536, depth 24, 24 heads, 8 register tokens, SwiGLUPacked
+# (int(1536 * 2.66667 * 2) = 8192), no_embed_class
+UNI2_ARCH = VitArch("uni2", patch=14, dim=1536, depth=24, heads=24, mlp_hidden=8192, mlp="swiglu",
+                    reg_tokens=8, no_embed_class=True)
+# h_optimus_0.py:14-28 / h_optimus_1.py: timm vit_giant_patch14_reg4_dinov2 (embed 1536, depth 40, 24 heads,
+# 4 register tokens, SwiGLUPacked, no_embed_class) at 224 px with the model card's mean / std
+H_OPTIMUS_ARCH = VitArch("h_optimus", patch=14, dim=1536, depth=40, heads=24, mlp_hidden=8192, mlp="swiglu",
+                         reg_tokens=4, no_embed_class=True, mean=(0.707223, 0.578729, 0.703617),
+                         std=(0.211883, 0.230117, 0.177517))
 
 
 class StampVitConfig(C.Structure):
@@ -109,7 +119,7 @@ def random_state_dict(arch: VitArch, seed: int = 1234) -> dict[str, Tensor]:
     D = arch.dim
     sd: dict[str, Tensor] = {
         "cls_token": 0.02 * torch.randn(1, 1, D, generator=g),
-        "pos_embed": 0.02 * torch.randn(1, arch.n_tokens, D, generator=g),
+        "pos_embed": 0.02 * torch.randn(1, arch.n_patches if arch.no_embed_class else arch.n_tokens, D, generator=g),
         "patch_embed.proj.weight": 0.02 * torch.randn(D, 3, arch.patch, arch.patch, generator=g),
         "patch_embed.proj.bias": torch.zeros(D),
         "norm.weight": torch.ones(D), "norm.bias": torch.zeros(D),
@@ -154,9 +164,13 @@ class TileEncoder(nn.Module):
         if arch.reg_tokens:
             prefix.append(sd["reg_token"].reshape(arch.reg_tokens, D))
         pos = sd["pos_embed"].reshape(-1, D)
-        if pos.shape[0] != arch.n_tokens:
-            raise ValueError(f"pos_embed has {pos.shape[0]} rows, expected {arch.n_tokens} "
-                             "(no_embed_class / dynamic resampling are not supported)")
+        if pos.shape[0] == arch.n_patches and (arch.no_embed_class or arch.n_prefix == 0):
+            # timm no_embed_class=True: the table covers the patch tokens only (UNI2-h, H-optimus)
+            pos = torch.cat([torch.zeros(arch.n_prefix, D), pos], 0)
+        elif pos.shape[0] != arch.n_tokens or arch.no_embed_class:
+            raise ValueError(f"pos_embed has {pos.shape[0]} rows, expected "
+                             f"{arch.n_patches if arch.no_embed_class else arch.n_tokens} "
+                             "(dynamic resampling of the position table is not supported)")
         self._names: list[str] = []
 
         def reg(name: str, t: Tensor, half: bool = False) -> None:

@@ -153,3 +153,22 @@ def test_extractor_interface_and_identifiers():
     assert e.identifier == "uni" and e.transform is pil_to_u8_hwc
     with pytest.raises(RuntimeError):
         e.model(torch.zeros(1, 224, 224, 3, dtype=torch.uint8))  # no CPU fallback
+
+
+def test_uni2_and_h_optimus_architectures_follow_reference_kwargs():
+    """extractor configs the reference spells out (uni2.py:18-32, h_optimus_0.py:14-28)."""
+    from stamp_b200.vit import H_OPTIMUS_ARCH, UNI2_ARCH, TileEncoder, VitArch, random_state_dict
+
+    assert (UNI2_ARCH.patch, UNI2_ARCH.dim, UNI2_ARCH.depth, UNI2_ARCH.heads, UNI2_ARCH.reg_tokens) == (14, 1536, 24, 24, 8)
+    assert UNI2_ARCH.mlp_hidden == int(1536 * 2.66667 * 2) and UNI2_ARCH.no_embed_class
+    assert UNI2_ARCH.n_tokens == 256 + 9 and H_OPTIMUS_ARCH.n_tokens == 256 + 5
+    assert H_OPTIMUS_ARCH.mean == (0.707223, 0.578729, 0.703617)
+    # no_embed_class packing: prefix rows carry no position, patch rows carry the whole table
+    arch = VitArch("t", patch=14, dim=64, depth=1, heads=1, mlp_hidden=128, mlp="swiglu", reg_tokens=2, no_embed_class=True)
+    sd = random_state_dict(arch)
+    assert sd["pos_embed"].shape == (1, 256, 64)
+    enc = TileEncoder(arch, sd)
+    assert torch.equal(enc.prefix[0], sd["cls_token"].reshape(-1)) and torch.equal(enc.pos, sd["pos_embed"][0])
+    bad = dict(sd, pos_embed=torch.zeros(1, 100, 64))
+    with pytest.raises(ValueError):
+        TileEncoder(arch, bad)

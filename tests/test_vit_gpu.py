@@ -24,12 +24,34 @@ def _run(cfg_o, n_tiles, device, seed=3, max_batch=256):
         ref = vo.forward(w, cfg_o, tiles)
     arch = VitArch(cfg_o.name, img=cfg_o.img, patch=cfg_o.patch, dim=cfg_o.dim, depth=cfg_o.depth,
                    heads=cfg_o.heads, mlp_hidden=cfg_o.mlp_hidden, mlp=cfg_o.mlp,
-                   reg_tokens=cfg_o.reg_tokens, ln_eps=cfg_o.ln_eps)
+                   reg_tokens=cfg_o.reg_tokens, ln_eps=cfg_o.ln_eps, no_embed_class=cfg_o.no_embed_class,
+                   mean=cfg_o.mean, std=cfg_o.std)
     enc = TileEncoder(arch, w, max_batch=max_batch).to(device).eval()
     out = enc(tiles.to(device))
     assert out.dtype == torch.float16 and out.shape == ref.shape
     assert torch.isfinite(out).all()
     return _per_tile_rel(out.float(), ref)
+
+
+def test_tiny_no_embed_class_and_custom_normalisation(cuda_device):
+    """UNI2-h / H-optimus style: position table on the patch tokens only, 8 register tokens, own mean / std."""
+    from oracle import vit_oracle as vo
+
+    cfg = vo.tiny_config(mlp="swiglu", reg_tokens=8, patch=14, depth=3, no_embed_class=True,
+                         mean=vo.H_OPTIMUS.mean, std=vo.H_OPTIMUS.std)
+    err = _run(cfg, 5, cuda_device)
+    assert err < 1e-3, err
+
+
+def test_uni2_and_h_optimus_blocks_match_oracle(cuda_device):
+    """Full-width UNI2-h / H-optimus blocks (dim 1536, 24 heads of 64, SwiGLU 8192), two blocks deep."""
+    from dataclasses import replace
+
+    from oracle import vit_oracle as vo
+
+    for full in (vo.UNI2, vo.H_OPTIMUS):
+        err = _run(replace(full, depth=2), 4, cuda_device)
+        assert err < 1e-3, (full.name, err)
 
 
 @pytest.mark.parametrize("mlp,reg,patch", [("gelu", 0, 16), ("swiglu", 4, 14), ("gelu", 2, 14)])
