@@ -302,6 +302,17 @@ int stamp_macenko_u8(const uint8_t* in, uint8_t* out, int n_tiles, int H, int W,
                      int* valid_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Tissue-texture filter of the tiling stage: per tile the number of Canny edge pixels of its grayscale
+ * image, bit-exact with the reference's Pillow / OpenCV calls.
+ * replaces: _has_enough_texture, src/stamp/preprocessing/tiling.py:279-291
+ *   (tile.convert("L") -> cv2.Canny(gray, 40, 100) -> edges.mean() / 255 >= cutoff).
+ * tiles uint8 [n_tiles, H, W, 3] RGB; edge_count int32 [n_tiles]; edges_out NULL or uint8 [n_tiles, H, W]
+ * (0 / 255, cv2.Canny's output).  One tile must fit one SM's shared memory (224 x 224 tiles use 200 KB; up to about 240 x 224 pixels).
+ * ------------------------------------------------------------------------------------------- */
+int stamp_tile_texture_u8(const uint8_t* tiles, int n_tiles, int H, int W, int low, int high,
+                          int* edge_count, uint8_t* edges_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Slide-level pooling.
  * stamp_gated_attn_pool -- CHIEF's gated-attention MIL pooling:
  *   h = ReLU(W1 x + b1); A_raw = Wc (tanh(Wa h + ba) * sigmoid(Wb h + bb)) + bc;

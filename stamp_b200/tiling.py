@@ -1,0 +1,61 @@
+"""Tile-level tissue filter of the tiling stage on the GPU.
+
+Mirrors ``_has_enough_texture`` (src/stamp/preprocessing/tiling.py:279-291), which the reference runs per
+tile on the CPU inside its tiling workers (``tile.convert("L")`` -> ``cv2.Canny(gray, 40, 100)`` ->
+``edges.mean() / 255 >= cutoff``): here a whole batch of decoded uint8 tiles is scored by one kernel launch
+(``stamp_tile_texture_u8``), bit-exact with Pillow + OpenCV, so exactly the same tiles survive the filter.
+No CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+CANNY_LOW, CANNY_HIGH = 40, 100   # "hardcoded thresholds", tiling.py:284-285
+
+
+def _bind() -> C.CDLL:
+    lib = _lib.load()
+    if not getattr(lib, "_texture_bound", False):
+        lib.stamp_tile_texture_u8.restype = C.c_int
+        lib.stamp_tile_texture_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]
+        lib._texture_bound = True
+    return lib
+
+
+def canny_edge_counts(tiles: Tensor, *, return_edges: bool = False):
+    """uint8 ``[B, H, W, 3]`` CUDA tiles -> int32 ``[B]`` Canny edge-pixel counts (and the uint8 0/255 edge maps)."""
+    if not tiles.is_cuda:
+        raise RuntimeError("canny_edge_counts runs on a CUDA device only (no CPU fallback)")
+    if tiles.dtype != torch.uint8 or tiles.dim() != 4 or tiles.shape[-1] != 3 or not tiles.is_contiguous():
+        raise TypeError("tiles must be a contiguous uint8 [B,H,W,3] tensor")
+    B, H, W, _ = tiles.shape
+    counts = torch.empty(B, dtype=torch.int32, device=tiles.device)
+    edges = torch.empty((B, H, W), dtype=torch.uint8, device=tiles.device) if return_edges else None
+    if B > 0:
+        code = _bind().stamp_tile_texture_u8(tiles.data_ptr(), B, H, W, CANNY_LOW, CANNY_HIGH, counts.data_ptr(),
+                                             None if edges is None else edges.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream)
+        _lib.check(code, "stamp_tile_texture_u8")
+    return (counts, edges) if return_edges else counts
+
+
+def edge_scores(tiles: Tensor) -> Tensor:
+    """``np.array(edges).mean() / 255`` per tile, in the same double arithmetic as NumPy (fp64 ``[B]``)."""
+    counts = canny_edge_counts(tiles)
+    # tensor / tensor is an IEEE division; tensor / python-scalar may be turned into a multiplication by the
+    # reciprocal, which differs from NumPy in the last bit (and the result is compared with a cutoff)
+    hw = torch.tensor(float(tiles.shape[1] * tiles.shape[2]), dtype=torch.float64, device=tiles.device)
+    c255 = torch.tensor(255.0, dtype=torch.float64, device=tiles.device)
+    return (counts.double() * c255 / hw) / c255
+
+
+def has_enough_texture(tiles: Tensor, cutoff: float) -> Tensor:
+    """``_has_enough_texture`` for a batch: bool ``[B]``, True where the tile is likely to contain tissue."""
+    return edge_scores(tiles) >= cutoff
