@@ -69,7 +69,9 @@ void stamp_b200_gemm_force_mode(int mode);
 /* bit 0 (default 1): unmasked head_dim-64 attention runs on the tcgen05 kernels (<= 256 tokens:
  * single-pass ViT kernel; longer: two-pass long-bag kernel, incl. the training forward / backward);
  * 0: always the general (mma.sync) kernels.
- * bit 1: prefer the persistent variant of the ViT kernel (tests / A-B timing). */
+ * bit 1: prefer the persistent variant of the ViT kernel (tests / A-B timing).
+ * bit 2: long-bag forward on the older two-pass kernel instead of the single-pass one (A-B timing).
+ * bit 3: single-pass kernel rescales its accumulator whenever the row maximum grows (tests of that path). */
 void stamp_b200_attention_tc_enable(int on);
 
 int stamp_gemm_tn(const void* A, long long lda, const void* W, long long ldw, void* out,
