@@ -206,3 +206,26 @@ def test_mil_full_scale_permutation_invariance(cuda_device):
                         slope=slopes.to(cuda_device))
     got = out[0, rows][:, h * hd:(h + 1) * hd].double().cpu()
     assert ((got - ref).norm() / ref.norm()).item() < 2e-3  # fp16 q/k/v operands at S = 50 001
+
+
+def test_predict_bags_pipeline_matches_per_bag_forward(cuda_device):
+    """deploy._predict mirror: ragged bags, fp16 (feature-file dtype) and fp32 inputs, probabilities per patient."""
+    from oracle import mil_oracle
+    from stamp_b200.deploy import predict_bags, predict_patients
+
+    sd = mil_oracle.init_state_dict(dim_input=64, dim_output=3, dim_model=128, n_heads=2, dim_feedforward=128, seed=2,
+                                    running_mean=7000.0)
+    model = _model_from_sd(sd, 2, cuda_device)
+    sizes = [5, 300, 64, 1, 129, 700, 33]
+    bags = [mil_oracle.synthetic_bag(n, 64, seed=40 + n) for n in sizes]
+    host = [(f[0].half() if i % 2 == 0 else f[0], c[0]) for i, (f, c) in enumerate(bags)]   # mixed dtypes
+    probs = predict_bags(model, iter(host), cuda_device)
+    assert probs.shape == (len(sizes), 3) and torch.allclose(probs.sum(1), torch.ones(len(sizes)), atol=1e-5)
+    for i, (f, c) in enumerate(bags):
+        ref = torch.softmax(mil_oracle.forward(sd, f, c, None), dim=1)[0]
+        assert torch.allclose(probs[i], ref, atol=2e-4), (i, probs[i], ref)
+    named = predict_patients(model, [f"p{i}" for i in range(len(sizes))], iter(host), cuda_device)
+    assert list(named) == [f"p{i}" for i in range(len(sizes))] and torch.equal(named["p3"], probs[3])
+    assert predict_bags(model, iter([]), cuda_device).shape == (0, 3)
+    with pytest.raises(RuntimeError):
+        predict_bags(model, iter(host), "cpu")
