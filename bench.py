@@ -280,13 +280,16 @@ def run_b200(args) -> None:
         res = {}
         for name, fn in (("value", mil_step_device), ("e2e", mil_step_e2e)):
             fn()
-            barrier()
-            e0.record()
-            for _ in range(2):
-                fn()
-            e1.record()
-            barrier()
-            res[name] = world * n_bags * 2 / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+            reps = []
+            for _ in range(3):      # median of three timed repetitions: the host side of the e2e loop is noisy
+                barrier()
+                e0.record()
+                for _ in range(2):
+                    fn()
+                e1.record()
+                barrier()
+                reps.append(world * n_bags * 2 / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3))
+            res[name] = sorted(reps)[1]
         mil_out = {"metric": "MIL slide predictions/sec (ALiBi Transformer-MIL, 4096x1024 bag, batch 1)",
                    "value": res["value"], "e2e": res["e2e"], "unit": "slides/s",
                    "roofline_frac": (res["value"] / world) * MIL_FLOPS_PER_BAG / 1e12 / peak_tf,
@@ -311,13 +314,13 @@ def run_b200(args) -> None:
         tb = torch.randn(per_gpu, n_tiles, 1024, device=dev, generator=gb).half().float()
         tc = torch.randint(0, 100, (per_gpu, n_tiles, 2), device=dev, generator=gb).float() * 256.0
         ty = torch.nn.functional.one_hot(torch.arange(per_gpu, device=dev) % 2, 2).float()
-        tb_host, tc_host = tb.cpu().pin_memory(), tc.cpu().pin_memory()
+        tb_host, tc_host = tb.half().cpu().pin_memory(), tc.cpu().pin_memory()   # features as the .h5 files hold them
 
         def train_step_device():
             return T.data_parallel_step(tmodel, opt, (tb, tc, None, ty), None, sched)
 
         def train_step_e2e():
-            b = tb_host.to(dev, non_blocking=True)
+            b = tb_host.to(dev, non_blocking=True).float()
             c = tc_host.to(dev, non_blocking=True)
             return float(T.data_parallel_step(tmodel, opt, (b, c, None, ty), None, sched).cpu())
 
@@ -347,7 +350,7 @@ def run_b200(args) -> None:
             "master weights and gradients", "per_gpu_batch": per_gpu, "global_batch": per_gpu * world,
             "collective": "1 all-reduce of the flat fp32 gradient buffer per step" if world > 1 else "none (1 GPU)",
             "grad_bytes_per_step": int(opt.flat_grad.numel() * 4),
-            "h2d_bytes_per_step": int(tb_host.numel() * 4 + tc_host.numel() * 4), "d2h_bytes_per_step": 4,
+            "h2d_bytes_per_step": int(tb_host.numel() * 2 + tc_host.numel() * 4), "d2h_bytes_per_step": 4,
             "gpu_launches_per_step": tres["value_launches"] / n_train,
             "roofline_frac": (tres["value"] / world) * MIL_TRAIN_FLOPS_PER_BAG / 1e12 / peak_tf,
             "kernel_share_of_step": {k: v["ms"] / ttot for k, v in tprof.items() if v["count"]},
