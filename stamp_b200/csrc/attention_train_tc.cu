@@ -14,7 +14,10 @@
 //
 // The streamed tile is used twice from the same shared-memory bytes: as K-major B operand of X / Y
 // (contraction over head_dim) and as MN-major B operand of the accumulating products (contraction over
-// the 64 streamed rows).  TMEM: X0 Y0 X1 Y1 (4 x 64 columns) | acc0 | acc1 (64 each) = 384 columns.
+// the 64 streamed rows).  TMEM: X | Y | acc0 | acc1 (64 columns each) = 256 columns and <= 102 registers per
+// thread, so TWO CTAs share an SM: X / Y are single-buffered inside a CTA (read into registers, stage released
+// before the arithmetic) and the other CTA's arithmetic covers the hand-offs -- one CTA alone left every
+// pipe below 55 % (issue, MUFU, tensor) because each tile is a chain MMA -> TMEM load -> math -> smem -> MMA.
 // Per (row, column) pair the CUDA cores spend one ex2 (+ one sqrt for ALiBi in DKV) -- as in the
 // forward, the MUFU pipe bounds the kernel, the four tensor-core products hide under it.
 #include <math.h>
@@ -26,7 +29,7 @@
 namespace sb {
 namespace {
 
-constexpr int NPART = 4;                       // compute threads per row (TMEM lane): 64 / NPART streamed columns each
+constexpr int NPART = 2;                       // compute threads per row (TMEM lane): 64 / NPART streamed columns each
 constexpr int CW = 64 / NPART;                 // columns per compute thread
 constexpr int BT_THREADS = 64 + NPART * 128;
 constexpr int BLK_BYTES = 128 * 128;   // 128 rows x 64 bf16
@@ -69,7 +72,7 @@ struct BtMaps {
 };
 
 template <bool DKV, bool ALIBI>
-__global__ void __launch_bounds__(BT_THREADS, 1)
+__global__ void __launch_bounds__(BT_THREADS, 2)
 attn_bwd_tc_kernel(const __grid_constant__ BtMaps tm, const AttnTrainParams p, int k_col0, int v_col0) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -115,14 +118,14 @@ attn_bwd_tc_kernel(const __grid_constant__ BtMaps tm, const AttnTrainParams p, i
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, 256);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t COL_A0 = 256, COL_A1 = 320;
+    constexpr uint32_t COL_Y = 64, COL_A0 = 128, COL_A1 = 192;   // X at column 0 (single stage, see header)
 
     if (warp == 0) {
         // ------------------------------------ TMA producer ------------------------------------
@@ -159,18 +162,17 @@ attn_bwd_tc_kernel(const __grid_constant__ BtMaps tm, const AttnTrainParams p, i
             const uint64_t ds_desc = umma_desc_k128(smem_u32(sDS));
             mbar_wait(bfull, 0);
             auto issue_xy = [&](int j) {
-                const int s = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                mbar_wait(&tfull[s], ph);
-                mbar_wait(&sempty[s], ph ^ 1);
+                const int s = j & 1;                       // streamed smem tiles: two stages
+                mbar_wait(&tfull[s], (j >> 1) & 1);
+                mbar_wait(&sempty[0], (j & 1) ^ 1);        // X / Y in TMEM: one stage, read into registers early
                 tc_fence_after();
                 const uint64_t s0_desc = umma_desc_k128(smem_u32(sS0 + s * STR_BYTES));
                 const uint64_t s1_desc = umma_desc_k128(smem_u32(sS1 + s * STR_BYTES));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16_ss(tmem + s * 128, b0_desc + 2 * k, s0_desc + 2 * k, idesc_xy, k != 0);
+                for (int k = 0; k < 4; ++k) umma_f16_ss(tmem, b0_desc + 2 * k, s0_desc + 2 * k, idesc_xy, k != 0);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16_ss(tmem + s * 128 + 64, b1_desc + 2 * k, s1_desc + 2 * k, idesc_xy, k != 0);
-                umma_commit(&sfull[s]);
+                for (int k = 0; k < 4; ++k) umma_f16_ss(tmem + COL_Y, b1_desc + 2 * k, s1_desc + 2 * k, idesc_xy, k != 0);
+                umma_commit(&sfull[0]);
             };
             issue_xy(0);
             for (int j = 0; j < nt; ++j) {
@@ -240,58 +242,63 @@ attn_bwd_tc_kernel(const __grid_constant__ BtMaps tm, const AttnTrainParams p, i
                 }
                 asm volatile("bar.sync 1, %0;\n" ::"n"(NPART * 128) : "memory");
             }
-            mbar_wait(&sfull[s], (j >> 1) & 1);
+            mbar_wait(&sfull[0], j & 1);
             tc_fence_after();
-            uint32_t x[CW], y[CW];
-            tmem_ld_cols(t_lane + s * 128 + half * CW, x);
-            tmem_ld_cols(t_lane + s * 128 + 64 + half * CW, y);
-            tmem_ld_wait();
-            uint32_t ww[CW / 2], dw[CW / 2];
 #pragma unroll
-            for (int c = 0; c < CW; c += 2) {
-                float wv[2], dv[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const bool valid = (c + e) < c_valid;
-                    float lse = lse_r, dl = dl_r;
-                    float4 cv;
-                    if constexpr (DKV) {
-                        cv = lds_f4(col_addr + ((j & 1) * 64 + half * CW + c + e) * 16);
-                        lse = cv.x; dl = cv.y;
-                    }
-                    const float pv = valid ? ex2_approx(fmaf(__uint_as_float(x[c + e]), sl2, -lse)) : 0.f;
-                    dv[e] = pv * (__uint_as_float(y[c + e]) - dl);
-                    if constexpr (DKV) {
-                        float w = pv;
-                        if constexpr (ALIBI) {
-                            const float dx = ck.x - cv.z, dy = ck.y - cv.w;
-                            const float dh = valid ? sqrt_apx(fmaf(dx, dx, dy * dy)) * inv_rm : 0.f;
-                            w = fmaf(-beta, dh, pv);
-                        }
-                        wv[e] = w;
-                    }
+            for (int ch = 0; ch < CW / 16; ++ch) {      // 16 columns at a time: registers for two CTAs per SM
+                uint32_t x[16], y[16];
+                const int col0 = half * CW + ch * 16;
+                tmem_ld_32x32b_x16(t_lane + col0, x);
+                tmem_ld_32x32b_x16(t_lane + COL_Y + col0, y);
+                tmem_ld_wait();
+                if (ch == CW / 16 - 1) {                 // X / Y of this tile are in registers: free the TMEM stage
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sempty[0]);
                 }
-                dw[c >> 1] = pack_bf16(dv[0], dv[1]);
-                if constexpr (DKV) ww[c >> 1] = pack_bf16(wv[0], wv[1]);
-            }
-            // the W / dS tiles are free once the accumulating products of the previous tile have retired;
-            // waiting here (not before the arithmetic) lets them overlap this tile's exp / sqrt work
-            mbar_wait(pempty, (j & 1) ^ 1);
-            // CW columns = CW/8 16-byte chunks of row r (128 B per row, 128B swizzle)
+                uint32_t ww[8], dw[8];
 #pragma unroll
-            for (int q = 0; q < CW / 8; ++q) {
-                const int off = ((half * (CW / 8) + q) ^ (r & 7)) * 16;
-                sts_u4b(ds_row + off, make_uint4(dw[4 * q], dw[4 * q + 1], dw[4 * q + 2], dw[4 * q + 3]));
-                if constexpr (DKV)
-                    sts_u4b(w_row + off, make_uint4(ww[4 * q], ww[4 * q + 1], ww[4 * q + 2], ww[4 * q + 3]));
+                for (int c = 0; c < 16; c += 2) {
+                    float wv[2], dv[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const bool valid = (ch * 16 + c + e) < c_valid;
+                        float lse = lse_r, dl = dl_r;
+                        float4 cv;
+                        if constexpr (DKV) {
+                            cv = lds_f4(col_addr + ((j & 1) * 64 + col0 + c + e) * 16);
+                            lse = cv.x; dl = cv.y;
+                        }
+                        const float pv = valid ? ex2_approx(fmaf(__uint_as_float(x[c + e]), sl2, -lse)) : 0.f;
+                        dv[e] = pv * (__uint_as_float(y[c + e]) - dl);
+                        if constexpr (DKV) {
+                            float w = pv;
+                            if constexpr (ALIBI) {
+                                const float dx = ck.x - cv.z, dy = ck.y - cv.w;
+                                const float dh = valid ? sqrt_apx(fmaf(dx, dx, dy * dy)) * inv_rm : 0.f;
+                                w = fmaf(-beta, dh, pv);
+                            }
+                            wv[e] = w;
+                        }
+                    }
+                    dw[c >> 1] = pack_bf16(dv[0], dv[1]);
+                    if constexpr (DKV) ww[c >> 1] = pack_bf16(wv[0], wv[1]);
+                }
+                // the W / dS tiles are free once the accumulating products of the previous tile have retired;
+                // waiting here (not before the arithmetic) lets them overlap this tile's exp / sqrt work
+                if (ch == 0) mbar_wait(pempty, (j & 1) ^ 1);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int off = (((col0 >> 3) + q) ^ (r & 7)) * 16;   // 128 B per row, 128B swizzle
+                    sts_u4b(ds_row + off, make_uint4(dw[4 * q], dw[4 * q + 1], dw[4 * q + 2], dw[4 * q + 3]));
+                    if constexpr (DKV)
+                        sts_u4b(w_row + off, make_uint4(ww[4 * q], ww[4 * q + 1], ww[4 * q + 2], ww[4 * q + 3]));
+                }
             }
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(pfull);
-                mbar_arrive(&sempty[s]);
-            }
+            if (lane == 0) mbar_arrive(pfull);
         }
 
         // ---- epilogue: accumulators -> bf16 global; this thread stores CW of the row's 64 columns ----
@@ -324,7 +331,7 @@ attn_bwd_tc_kernel(const __grid_constant__ BtMaps tm, const AttnTrainParams p, i
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem, 512);
+        tmem_dealloc(tmem, 256);
     }
 }
 
