@@ -71,7 +71,8 @@ void stamp_b200_gemm_force_mode(int mode);
  * 0: always the general (mma.sync) kernels.
  * bit 1: prefer the persistent variant of the ViT kernel (tests / A-B timing).
  * bit 2: long-bag forward on the older two-pass kernel instead of the single-pass one (A-B timing).
- * bit 3: single-pass kernel rescales its accumulator whenever the row maximum grows (tests of that path). */
+ * bit 3: single-pass kernel rescales its accumulator whenever the row maximum grows (tests of that path).
+ * bit 4: single-pass kernel with 128-key tiles and one CTA per SM instead of 64-key tiles and two (A-B timing). */
 void stamp_b200_attention_tc_enable(int on);
 
 int stamp_gemm_tn(const void* A, long long lda, const void* W, long long ldw, void* out,
