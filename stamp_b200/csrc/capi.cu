@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "rowops.cuh"
+#include "wgrad_tc.cuh"
 
 namespace sb {
 static std::atomic<long long> g_launches{0};
@@ -45,6 +46,7 @@ void stamp_b200_attention_tc_enable(int on) {
     sb::attention_tc_enable(on);
     sb::attention_mil_tc_enable(on);        // bit 0 on/off, bit 2 two-pass kernel, bit 3 eager rescale (tests)
     sb::attention_train_tc_enable(on & 1);
+    sb::wgrad_tc_enable(on & 1);
     // bit 1: prefer the persistent single-TMEM-pass ViT kernel (measured equal to the default
     // two-CTA-per-SM kernel on B200, kept as an opt-in alternative)
     sb::attention_vit_persist_enable((on & 2) != 0);

@@ -25,6 +25,7 @@
 #include "mil_common.cuh"
 #include "rowops.cuh"
 #include "stamp_b200.h"
+#include "wgrad_tc.cuh"
 
 namespace sb {
 namespace {
@@ -578,9 +579,17 @@ wgrad_kernel(const uint16_t* __restrict__ dY, long long ldy, const uint16_t* __r
 
 inline int last_status() { return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA; }
 
+float* g_wgrad_scratch = nullptr;      // set by stamp_mil_train_backward for the duration of the call (one stream)
+size_t g_wgrad_scratch_bytes = 0;
+
 int wgrad(const uint16_t* dY, long long ldy, const uint16_t* X, long long ldx, float* dW, long long ldw, int M,
           int Nout, int Kin, cudaStream_t stream) {
     if (M <= 0 || (Nout % 8) != 0 || (Kin % 8) != 0 || (ldy % 8) != 0 || (ldx % 8) != 0) return SB_ERR_BAD_ARG;
+    {
+        const int rc = wgrad_tc(dY, ldy, X, ldx, dW, ldw, M, Nout, Kin, g_wgrad_scratch, g_wgrad_scratch_bytes,
+                                stream);   // long token dimension: tcgen05
+        if (rc != SB_ERR_UNSUPPORTED) return rc;
+    }
     const int tiles = ((Nout + WG_T - 1) / WG_T) * ((Kin + WG_T - 1) / WG_T);
     int splits = (2 * 148 + tiles - 1) / tiles;
     const int max_splits = (M + 4 * WG_BK - 1) / (4 * WG_BK);
@@ -655,7 +664,7 @@ struct TrainLayout {
     size_t l_w_qkv, l_w_qkvT, l_w_fc, l_w_fcT, l_w_ff1, l_w_ff1T, l_w_ff2, l_w_ff2T;
     size_t off_w_proj, off_w_projT;
     size_t off_y32 /* [M, max(d,ff)] f32 scratch */, off_dx /* [M,d] f32 */, off_g16a /* [M, max(d,ff)] bf16 */,
-        off_g16b /* [M,d] bf16 */, off_g16c /* [M,3d] bf16 */, off_delta, off_dsum, total;
+        off_g16b /* [M,d] bf16 */, off_g16c /* [M,3d] bf16 */, off_delta, off_dsum, off_wscratch, wscratch_bytes, total;
 };
 
 inline size_t au(size_t v) { return (v + 255) / 256 * 256; }
@@ -705,6 +714,14 @@ bool make_train_layout(const StampMilConfig* c, int B, int N, TrainLayout* L) {
     L->off_g16c = o; o = au(o + M * 3 * d * 2);
     L->off_delta = o; o = au(o + static_cast<size_t>(B) * H * L->S * 4);
     L->off_dsum = o;  o = au(o + 64);
+    {   // per-split partial tiles of the largest weight gradient (wgrad_tc.cu)
+        size_t w = wgrad_tc_scratch_bytes(static_cast<int>(3 * d), static_cast<int>(d));
+        const size_t cand[4] = {wgrad_tc_scratch_bytes(static_cast<int>(d), static_cast<int>(F)), wgrad_tc_scratch_bytes(static_cast<int>(d), static_cast<int>(d)),
+                                wgrad_tc_scratch_bytes(static_cast<int>(ff), static_cast<int>(d)), wgrad_tc_scratch_bytes(static_cast<int>(d), static_cast<int>(ff))};
+        for (size_t c : cand) w = c > w ? c : w;
+        L->wscratch_bytes = w;
+    }
+    L->off_wscratch = o; o = au(o + L->wscratch_bytes);
     L->total = o;
     return true;
 }
@@ -904,6 +921,8 @@ int stamp_mil_train_backward(const StampMilConfig* cfg, const StampMilTrainTop* 
     float* delta = reinterpret_cast<float*>(ws + L.off_delta);
     auto xbuf = [&](int i) { return reinterpret_cast<float*>(ws + L.off_x + L.x_stride * i); };
     const long long Md = static_cast<long long>(M) * d;
+    g_wgrad_scratch = reinterpret_cast<float*>(ws + L.off_wscratch);
+    g_wgrad_scratch_bytes = L.wscratch_bytes;
     const uint32_t th_ff = drop_thresh(step->p_drop_ff);
     const float ik_ff = inv_keep(step->p_drop_ff);
 

@@ -177,6 +177,22 @@ def test_default_size_mha_variant_matches_oracle(cuda_device):
     _check_grads(model, ref_grads, "mha default N=400")
 
 
+def test_small_model_long_bag_gradients_match_oracle(cuda_device):
+    """dim_input 64 / dim_model 128 with enough tokens for the tcgen05 weight-gradient kernel: its 128 x 128
+    tiles are only partly inside dW here (Kin = 64, Nout = 128 / 384), the rest comes from TMA zero fill."""
+    from stamp_b200 import train as T
+
+    sd = mil_oracle.init_state_dict(dim_input=64, dim_output=3, dim_model=128, n_heads=2, dim_feedforward=128, seed=9)
+    bags, coords = mil_oracle.synthetic_bag(333, 64, seed=77, batch=3, signal=True)
+    targets = torch.nn.functional.one_hot(torch.arange(3) % 3, 3).float()
+    model = _model(sd, 2, cuda_device)
+    loss = T.training_step(model, (bags.to(cuda_device), coords.to(cuda_device), None, targets.to(cuda_device)), None)
+    loss.backward()
+    _, ref_loss, ref_grads, _ = mil_oracle.train_grads(sd, bags, coords, targets, None)
+    assert abs(float(loss.detach()) - float(ref_loss)) < LOGIT_TOL * max(1.0, float(ref_loss))
+    _check_grads(model, ref_grads, "small model N=333")
+
+
 def test_feature_gradient_and_gradcam_match_oracle(cuda_device):
     """d logits / d feats (heatmaps' jacrev, src/stamp/heatmaps/__init__.py:36-56) and the class-activation map."""
     from stamp_b200 import train as T
