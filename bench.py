@@ -501,9 +501,9 @@ def run_b200(args) -> None:
     # ---- CPU baseline (rank 0, single GPU runs only): oracle port on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-        tps, cores, dt = cpu_vit_tiles_per_s(16, reps=2, warm=1)
+        tps, cores, dt = cpu_vit_tiles_per_s(16, reps=8, warm=1)
         cpu = {"value": tps, "unit": "tiles/s", "cores": cores, "kind": "port",
-               "sample": f"2 x 16 synthetic tiles ({dt:.1f} s), ViT-L/16 fp32 oracle port of the timm path"}
+               "sample": f"8 x 16 synthetic tiles ({dt:.1f} s), ViT-L/16 fp32 oracle port of the timm path"}
         if mil_out is not None:
             cpu["mil_slides_per_s"] = cpu_mil_slides_per_s(4096, reps=3)
 
