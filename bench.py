@@ -250,8 +250,11 @@ def run_b200(args) -> None:
         "traffic": None,
     }
     traffic_file = ROOT / "profiles" / "gemm_traffic.json"
-    if traffic_file.exists():
-        roofline["traffic"] = json.loads(traffic_file.read_text())
+    if traffic_file.exists():      # dram__bytes_read.sum + dram__bytes_write.sum per launch from one ncu --set full capture
+        tj = json.loads(traffic_file.read_text())
+        roofline["traffic"] = tj.get("bytes_per_launch")
+        roofline["traffic_unit"] = tj.get("unit", "bytes")
+        roofline["traffic_source"] = tj.get("source")
 
     # ---- end to end through the public API: pinned host tiles -> host fp16 features
     tiles_host = tiles_dev.cpu().pin_memory()
