@@ -1,0 +1,70 @@
+"""The whole hot path composed on the GPU with synthetic data (BASELINE configs[0] plumbing, on the device):
+
+  uint8 tiles -> tissue-texture filter -> Macenko -> tile encoder (small ViT, all kernels of the ViT path)
+  -> fp16 features + coordinates -> fixed-size bags -> MIL training steps (FusedAdamW + OneCycleLR)
+  -> patient-level deploy -> grad-CAM + top-k tiles
+
+Checks the dtype / shape contracts between the stages and that nothing leaves the device except through the
+documented interfaces; the arithmetic of every stage has its own parity test."""
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_tiles_to_heatmap_pipeline(cuda_device):
+    from oracle import vit_oracle as vo
+    from stamp_b200 import train as T
+    from stamp_b200.bags import collate_bags, to_fixed_size_bag
+    from stamp_b200.deploy import predict_patients
+    from stamp_b200.encoder import topk
+    from stamp_b200.extractor import Extractor, extract_slide_features, pil_to_u8_hwc
+    from stamp_b200.macenko import macenko_normalize
+    from stamp_b200.mil import VisionTransformer
+    from stamp_b200.tiling import has_enough_texture
+    from stamp_b200.vit import TileEncoder, VitArch
+
+    cfg = vo.tiny_config(depth=2)
+    arch = VitArch(cfg.name, patch=cfg.patch, dim=cfg.dim, depth=cfg.depth, heads=cfg.heads,
+                   mlp_hidden=cfg.mlp_hidden, mlp=cfg.mlp, reg_tokens=cfg.reg_tokens)
+    ext = Extractor(model=TileEncoder(arch, vo.make_weights(cfg), max_batch=32).to(cuda_device).eval(),
+                    transform=pil_to_u8_hwc, identifier="tiny")
+
+    slides = {}
+    for pid in range(6):
+        tiles = vo.synthetic_tiles(40, seed=pid)                       # H&E-like uint8 [40, 224, 224, 3]
+        tiles[-4:] = 240                                                # four blank background tiles
+        dev_tiles = tiles.to(cuda_device)
+        keep = has_enough_texture(dev_tiles, 0.02)
+        assert keep.dtype == torch.bool and int(keep.sum()) == 36 and not bool(keep[-4:].any())
+        kept = macenko_normalize(dev_tiles[keep].contiguous())
+        assert kept.dtype == torch.uint8 and kept.shape == (36, 224, 224, 3)
+        feats = extract_slide_features(ext, kept.cpu(), cuda_device, batch_size=16)
+        assert feats.dtype == torch.float16 and feats.shape == (36, arch.dim) and not feats.is_cuda
+        cells = torch.randperm(100, generator=torch.Generator().manual_seed(pid))[:36]
+        coords = torch.stack([(cells % 10).float(), (cells // 10).float()], dim=-1) * 256.0
+        slides[f"p{pid}"] = (feats, coords, pid % 2)
+
+    model = VisionTransformer(dim_output=2, dim_input=arch.dim, dim_model=128, n_layers=2, n_heads=2,
+                              dim_feedforward=128, dropout=0.1, use_alibi=True).to(cuda_device).train()
+    opt, sched = T.configure_optimizers(model, total_steps=6, max_lr=1e-3)
+    items = []
+    for feats, coords, label in slides.values():
+        bag, c, size = to_fixed_size_bag(feats.float().to(cuda_device), coords.to(cuda_device), bag_size=32)
+        items.append((bag, c, size, torch.nn.functional.one_hot(torch.tensor(label), 2).float().to(cuda_device)))
+    batch = collate_bags(items)
+    assert batch[0].shape == (6, 32, arch.dim) and batch[3].shape == (6, 2)
+    losses = [float(T.data_parallel_step(model, opt, batch, torch.tensor([1.0, 1.2], device=cuda_device), sched))
+              for _ in range(6)]
+    assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0]
+
+    preds = predict_patients(model, list(slides), ((f, c) for f, c, _ in slides.values()), cuda_device)
+    assert list(preds) == list(slides)
+    assert all(p.shape == (2,) and abs(float(p.sum()) - 1.0) < 1e-5 for p in preds.values())
+
+    feats, coords, _ = slides["p0"]
+    cam = T.gradcam_per_category(model, feats.float().to(cuda_device), coords.to(cuda_device))
+    assert cam.shape == (36, 2) and torch.allclose(cam.sum(0), torch.ones(2, device=cuda_device), atol=1e-4)
+    vals, idx = topk(cam[:, 1].contiguous(), 8)
+    assert idx.shape == (8,) and torch.equal(idx.cpu(), cam[:, 1].cpu().topk(8).indices)
