@@ -7,8 +7,9 @@
 // 48 bytes per thread iteration), optical densities come from a 256-entry shared-memory table
 // (OD depends on the byte value only), reductions are warp shuffles + one fp64 atomic per CTA, and
 // the four exact percentiles (two of the stain angle, two of the stain concentrations, each needing
-// the k-th and (k+1)-th order statistic for NumPy's linear interpolation) are found with a 3-pass
-// radix select (11 + 11 + 10 bits) over order-preserving float keys: shared-memory histograms,
+// the k-th and (k+1)-th order statistic for NumPy's linear interpolation) are found with a 2-pass
+// radix select (11 + 11 of the 32 key bits; the last 10 bits are below output resolution) over
+// order-preserving fixed-point keys: shared-memory histograms,
 // no sort, no per-pixel intermediate in HBM.  A batch of tiles (<= ~800) stays in the 126 MB L2
 // after the first pass, so DRAM traffic stays close to the algorithmic one read + one write.
 //
@@ -26,6 +27,7 @@ constexpr int NBINS = 2048;
 constexpr int MAC_THREADS = 256;
 constexpr int PIX_PER_ITER = 16;  // 48 bytes
 constexpr int MIN_TISSUE = 16;
+constexpr int MAC_PASSES = 2;     // radix passes per order statistic: 11 + 11 key bits (a third would add the last 10)
 
 struct MacGroup {
     double sum[3];
@@ -320,7 +322,7 @@ mac_hist_kernel(const uint8_t* __restrict__ img, long long n_chunks, long long c
 
 // ---- after each histogram pass: locate the bin holding each rank, extend the prefix, clear hist
 __global__ void __launch_bounds__(NSEL * 32)
-mac_select_kernel(MacGroup* __restrict__ grp, unsigned int* __restrict__ hist, int pass, int stage) {
+mac_select_kernel(MacGroup* __restrict__ grp, unsigned int* __restrict__ hist, int pass, int stage, int last) {
     MacGroup& g = grp[blockIdx.x];
     unsigned int* hg = hist + static_cast<long long>(blockIdx.x) * (NSEL * NBINS);
     const int s = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -353,7 +355,11 @@ mac_select_kernel(MacGroup* __restrict__ grp, unsigned int* __restrict__ hist, i
                 cum += c;
             }
             g.rank[s] = r - cum;
-            g.prefix[s] = (g.prefix[s] << nbits) | static_cast<unsigned int>(bin);
+            unsigned int pre = (g.prefix[s] << nbits) | static_cast<unsigned int>(bin);
+            // two radix passes resolve the 22 high key bits (2^-20 of the pseudo-angle range, 3e-5 in
+            // concentration units -- far below what moves an output byte): the 10 low bits get their midpoint
+            if (last && pass == 1) pre = (pre << 10) | 0x200u;
+            g.prefix[s] = pre;
         }
     }
     __syncthreads();
@@ -488,19 +494,19 @@ int stamp_macenko_u8(const uint8_t* in, uint8_t* out, int n_tiles, int H, int W,
         ProfScope prof(PROF_MACENKO, 2.0 * bytes, stream);  // algorithmic traffic: one read + one write
         mac_stats_kernel<<<grid, MAC_THREADS, 0, stream>>>(in, n_chunks, chunks_per_group, Io, beta, grp);
         mac_eig_kernel<<<G, 32, 0, stream>>>(grp, pixels_per_group, n_pixels, alpha);
-        for (int pass = 0; pass < 3; ++pass) {
+        for (int pass = 0; pass < MAC_PASSES; ++pass) {
             mac_hist_kernel<0><<<grid, MAC_THREADS, 0, stream>>>(in, n_chunks, chunks_per_group, Io, beta, grp, hist, pass);
-            mac_select_kernel<<<G, NSEL * 32, 0, stream>>>(grp, hist, pass, 0);
+            mac_select_kernel<<<G, NSEL * 32, 0, stream>>>(grp, hist, pass, 0, pass == MAC_PASSES - 1);
         }
         mac_vectors_kernel<<<G, 32, 0, stream>>>(grp);
-        for (int pass = 0; pass < 3; ++pass) {
+        for (int pass = 0; pass < MAC_PASSES; ++pass) {
             mac_hist_kernel<1><<<grid, MAC_THREADS, 0, stream>>>(in, n_chunks, chunks_per_group, Io, beta, grp, hist, pass);
-            mac_select_kernel<<<G, NSEL * 32, 0, stream>>>(grp, hist, pass, 1);
+            mac_select_kernel<<<G, NSEL * 32, 0, stream>>>(grp, hist, pass, 1, pass == MAC_PASSES - 1);
         }
         mac_finalize_kernel<<<G, 32, 0, stream>>>(grp, he_out, maxc_out, valid_out);
         const int agrid = static_cast<int>(min(static_cast<long long>(sms) * 8, (n_chunks + MAC_THREADS - 1) / MAC_THREADS));
         mac_apply_kernel<<<agrid, MAC_THREADS, 0, stream>>>(in, out, n_chunks, chunks_per_group, Io, grp);
-        count_launch(17);
+        count_launch(5 + 4 * MAC_PASSES);
     }
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
