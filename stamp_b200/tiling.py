@@ -10,7 +10,13 @@ No CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import json
+import re
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+from zipfile import ZipFile
 
+import numpy as np
 import torch
 from torch import Tensor
 
@@ -59,3 +65,51 @@ def edge_scores(tiles: Tensor) -> Tensor:
 def has_enough_texture(tiles: Tensor, cutoff: float) -> Tensor:
     """``_has_enough_texture`` for a batch: bool ``[B]``, True where the tile is likely to contain tissue."""
     return edge_scores(tiles) >= cutoff
+
+
+def tiles_from_cache_file(cache_file_path: str | Path, *, max_workers: int = 8,
+                          pin_memory: bool = True) -> tuple[Tensor, Tensor, dict]:
+    """Reads a STAMP tile cache (``_tiles_from_cache_file``, src/stamp/preprocessing/tiling.py:380-406: a zip with
+    ``tiler_params.json`` and one ``tile_(x_um, y_um).<ext>`` image per tile) into ONE uint8 ``[N, H, W, 3]`` host
+    tensor (pinned, so ``extract_slide_features`` can stream it to the GPU) plus the ``[N, 2]`` coordinates in
+    microns and the tiler parameters.  Decoding is Pillow's, like the reference's (bit-identical pixels), on a
+    thread pool; tiles come back in zip order, which is the order the reference iterates them in."""
+    from PIL import Image
+
+    path = Path(cache_file_path)
+    with ZipFile(path, "r") as zf:
+        params = json.loads(zf.read("tiler_params.json").decode())
+        ext = params.get("tile_ext", "jpg")          # "jpg as default for backwards compatibility"
+        pat = re.compile(rf"tile_\((\d+\.\d+), (\d+\.\d+)\)\.{re.escape(ext)}")
+        names, coords = [], []
+        for name in zf.namelist():
+            m = pat.fullmatch(name)
+            if m is not None:
+                names.append(name)
+                coords.append((float(m.group(1)), float(m.group(2))))
+        blobs = [zf.read(n) for n in names]
+    if not names:
+        return torch.empty((0, 0, 0, 3), dtype=torch.uint8), torch.empty((0, 2)), params
+
+    def decode(blob: bytes) -> np.ndarray:
+        import io
+
+        with Image.open(io.BytesIO(blob)) as im:
+            return np.asarray(im.convert("RGB"), dtype=np.uint8)
+
+    first = decode(blobs[0])
+    out = torch.empty((len(blobs), *first.shape), dtype=torch.uint8)
+    if pin_memory and torch.cuda.is_available():
+        out = out.pin_memory()
+    dst = out.numpy()
+    dst[0] = first
+
+    def work(i: int) -> None:
+        a = decode(blobs[i])
+        if a.shape != first.shape:
+            raise ValueError(f"tile {names[i]!r} has shape {a.shape}, expected {first.shape}")
+        dst[i] = a
+
+    with ThreadPoolExecutor(max_workers=max_workers) as ex:
+        list(ex.map(work, range(1, len(blobs))))
+    return out, torch.tensor(coords, dtype=torch.float32), params

@@ -172,3 +172,37 @@ def test_uni2_and_h_optimus_architectures_follow_reference_kwargs():
     bad = dict(sd, pos_embed=torch.zeros(1, 100, 64))
     with pytest.raises(ValueError):
         TileEncoder(arch, bad)
+
+
+def test_tile_cache_reader_matches_pillow(tmp_path):
+    """tiles_from_cache_file mirrors _tiles_from_cache_file (tiling.py:380-406): same tiles, coordinates, order."""
+    import io
+    import json
+    from zipfile import ZipFile
+
+    import numpy as np
+    from PIL import Image
+
+    from stamp_b200.tiling import tiles_from_cache_file
+
+    rng = np.random.default_rng(0)
+    for ext, fmt in (("jpg", "JPEG"), ("png", "PNG")):
+        tiles = rng.integers(0, 256, (5, 32, 32, 3), dtype=np.uint8)
+        coords = [(256.0 * i, 512.5 + i) for i in range(5)]
+        path = tmp_path / f"cache_{ext}.zip"
+        with ZipFile(path, "w") as zf:
+            zf.writestr("tiler_params.json", json.dumps({"tile_size_um": 256.0, "tile_size_px": 32, "tile_ext": ext}))
+            zf.writestr("notes.txt", "ignored")
+            for t, (x, y) in zip(tiles, coords):
+                buf = io.BytesIO()
+                Image.fromarray(t).save(buf, format=fmt)
+                zf.writestr(f"tile_({x}, {y}).{ext}", buf.getvalue())
+        got, c, params = tiles_from_cache_file(path, pin_memory=False)
+        assert got.shape == (5, 32, 32, 3) and got.dtype == torch.uint8 and params["tile_size_um"] == 256.0
+        assert torch.allclose(c, torch.tensor(coords))
+        with ZipFile(path) as zf:          # the reference's decode: PIL on the zip member
+            for i, (x, y) in enumerate(coords):
+                ref = np.asarray(Image.open(io.BytesIO(zf.read(f"tile_({x}, {y}).{ext}"))).convert("RGB"))
+                assert np.array_equal(got[i].numpy(), ref)
+        if fmt == "PNG":
+            assert np.array_equal(got.numpy(), tiles)
