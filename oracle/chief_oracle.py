@@ -7,9 +7,12 @@ Follows src/stamp/encoding/encoder/chief.py: ``CHIEFModel.__init__`` :27-65 (siz
 [768, 512, 256]; attention_net = Sequential(Linear, ReLU, Dropout(0.25), Attn_Net_Gated)),
 ``CHIEFModel.forward`` :74-89, ``Attn_Net_Gated`` :255-275, ``initialize_weights`` :211-219
 (xavier_normal weights, zero biases); and src/stamp/encoding/encoder/eagle.py:104-120.
-PARITY UNPINNED: ``chief.py`` cannot be imported offline (top-level ``gdown`` / package imports) and
-the pretrained weights live on Google Drive; the reference's tests at this boundary
-(tests/test_encoders.py) are smoke tests.  State-dict keys follow the reference module tree.
+Parity pin: ``chief.py`` cannot be imported as a package member offline (top-level ``gdown`` / ``stamp.*``
+imports), but its model classes are plain torch: ``oracle/make_golden_chief.py`` loads the file by path with
+inert stand-ins for those imports, runs the reference ``CHIEFModel(size_arg="small")`` and EAGLE's selection
+lines on seeded inputs and commits the outputs as ``tests/golden/chief_pool.npz``; ``tests/test_oracle_cpu.py``
+checks this restatement against them.  Weights are synthetic (the pretrained ones live on Google Drive);
+state-dict keys follow the reference module tree.
 """
 
 from __future__ import annotations

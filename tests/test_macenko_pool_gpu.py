@@ -134,3 +134,25 @@ def test_topk_heatmap_fixture_and_ties(cuda_device):
     t = torch.tensor([1.0, 2.0, 2.0, 2.0, 0.5], device=cuda_device)
     assert topk(t, 3, True)[1].tolist() == [1, 2, 3]
     assert topk(torch.zeros(40, device=cuda_device), 5, True)[1].tolist() == [0, 1, 2, 3, 4]
+
+
+def test_chief_and_eagle_match_reference_model_golden(cuda_device):
+    """The CUDA pooling path against outputs of the reference's own CHIEFModel / EAGLE lines (chief_pool.npz)."""
+    from oracle import chief_oracle as co
+    from stamp_b200.encoder import EagleB200, GatedAttentionPool, topk
+    from test_oracle_cpu import load_chief_golden
+
+    seed, cases = load_chief_golden()
+    sd = co.init_state_dict(seed=seed)
+    pool = GatedAttentionPool(sd).to(cuda_device)
+    for name, c in cases.items():
+        out = pool(c["x"].to(cuda_device))
+        a, a_ref = out["attention_raw"].cpu(), c["attention_raw"]
+        assert (a - a_ref).abs().max().item() < 2e-5 * max(1.0, a_ref.abs().max().item()), name
+        p, p_ref = out["WSI_feature"].cpu().double().flatten(), c["wsi"].double().flatten()
+        assert ((p - p_ref).norm() / p_ref.norm()).item() < 1e-4, name
+        k = min(25, c["x"].shape[0])
+        _, idx = topk(out["attention_raw"].squeeze(0).contiguous(), k)
+        assert torch.equal(idx.cpu(), c["topk"].long()), name            # margins checked when the fixture was written
+        emb = EagleB200(sd)._generate_slide_embedding(c["x"], cuda_device, agg_feats=c["agg"])
+        assert np.allclose(emb, c["eagle"].numpy(), rtol=1e-5, atol=1e-6), name
