@@ -206,3 +206,43 @@ def test_tile_cache_reader_matches_pillow(tmp_path):
                 assert np.array_equal(got[i].numpy(), ref)
         if fmt == "PNG":
             assert np.array_equal(got.numpy(), tiles)
+
+
+def _reference_functions(path: Path, names: list[str]) -> dict:
+    """Executes individual pure-torch functions of a reference file (the file itself needs h5py / lightning):
+    their source segments are taken with ``ast`` and run in a namespace that only has torch."""
+    import ast
+
+    src = path.read_text()
+    tree = ast.parse(src)
+    ns: dict = {"torch": torch}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec("from __future__ import annotations\n" + ast.get_source_segment(src, node), ns)
+    return ns
+
+
+def test_bag_plumbing_matches_the_reference_functions():
+    """bags.to_fixed_size_bag / collate_bags against the reference's own _to_fixed_size_bag / _collate_to_tuple
+    (src/stamp/modeling/data.py:811-862, :255-277), executed from the reference file where it is present."""
+    ref_file = Path("/root/reference/src/stamp/modeling/data.py")
+    if not ref_file.exists():
+        pytest.skip("reference checkout not present on this machine")
+    from stamp_b200.bags import collate_bags, to_fixed_size_bag
+
+    ref = _reference_functions(ref_file, ["_to_fixed_size_bag", "_collate_to_tuple"])
+    g = torch.Generator().manual_seed(5)
+    items_ref, items_ours = [], []
+    for n, bag_size, det in [(10, 16, False), (100, 16, False), (100, 16, True), (16, 16, False), (1, 4, True), (37, 8, True)]:
+        bag, coords = torch.randn(n, 6, generator=g), torch.rand(n, 2, generator=g) * 1000
+        torch.manual_seed(n * 31 + bag_size)
+        rb, rc, rn = ref["_to_fixed_size_bag"](bag, coords, bag_size, deterministic=det)
+        torch.manual_seed(n * 31 + bag_size)                     # the same randperm draw
+        ob, oc, on = to_fixed_size_bag(bag, coords, bag_size, deterministic=det)
+        assert torch.equal(rb, ob) and torch.equal(rc, oc) and rn == on, (n, bag_size, det)
+        if bag_size == 16:
+            tgt = torch.tensor([[0.0, 1.0]]) if n == 10 else torch.tensor([1.0, 0.0])
+            items_ref.append((rb, rc, rn, tgt))
+            items_ours.append((ob, oc, on, tgt))
+    for a, b in zip(ref["_collate_to_tuple"](items_ref), collate_bags(items_ours)):
+        assert torch.equal(a, b)

@@ -350,3 +350,30 @@ def test_stale_checkpoint_is_refused(cuda_device):
     model(bags, coords=coords, mask=None)
     with pytest.raises(RuntimeError):
         a.backward()
+
+
+def test_gradcam_matches_reference_heatmap_code_golden(cuda_device):
+    """mil_gradcam_trained_scale.npz was written by the reference's own _gradcam_per_category (jacrev over the
+    reference module, oracle/make_golden_gradcam.py) for the state dict / bag of mil_alibi_trained_scale.npz."""
+    import numpy as np
+
+    from stamp_b200 import train as T
+    from test_oracle_cpu import ROOT, load_golden
+
+    sd, bags, coords, _mask, _logits, n_heads = load_golden(ROOT / "tests" / "golden" / "mil_alibi_trained_scale.npz")
+    z = np.load(ROOT / "tests" / "golden" / "mil_gradcam_trained_scale.npz")
+    cam_ref, scores_ref = torch.from_numpy(z["cam"]), torch.from_numpy(z["scores"])
+    model = _model(sd, n_heads, cuda_device).eval()
+    feats, c = bags[0].to(cuda_device), coords[0].to(cuda_device)
+    cam = T.gradcam_per_category(model, feats, c).cpu()
+    assert cam.shape == cam_ref.shape
+    assert torch.allclose(cam, cam_ref, rtol=1e-3, atol=1e-7)
+    # the pre-softmax scores are what carries the information (bf16 backward: 5e-2 of the row norm)
+    x = feats.clone().requires_grad_(True)
+    logits = model(x[None], coords=c[None], mask=None)[0]
+    for k in range(3):
+        (j,) = torch.autograd.grad(logits[k], x, retain_graph=True)
+        s = (x.detach() * j).mean(-1).abs().cpu()
+        rel = float((s - scores_ref[k]).norm() / scores_ref[k].norm())
+        print(f"class {k}: heatmap score rel err {rel:.3e}")
+        assert rel < GRAD_TOL
