@@ -145,3 +145,11 @@ class EagleB200(ChiefB200):
         code = _bind().stamp_gather_mean_f32(agg.data_ptr(), idx.data_ptr(), k, agg.shape[1], out.data_ptr(), _stream())
         _lib.check(code, "stamp_gather_mean_f32")
         return out.cpu().numpy()
+
+    def _generate_patient_embedding(self, feats_list: list[Tensor], device, agg_feats_list: list[Tensor] | None = None,
+                                    **kwargs) -> np.ndarray:
+        """eagle.py:122-134: all slides of the patient concatenated, then the slide-level selection."""
+        if agg_feats_list is None:
+            raise ValueError("agg_feats_list is required for patient embedding")
+        return self._generate_slide_embedding(torch.cat(feats_list, dim=0), device,
+                                              agg_feats=torch.cat(agg_feats_list, dim=0))

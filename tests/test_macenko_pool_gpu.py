@@ -154,5 +154,13 @@ def test_chief_and_eagle_match_reference_model_golden(cuda_device):
         k = min(25, c["x"].shape[0])
         _, idx = topk(out["attention_raw"].squeeze(0).contiguous(), k)
         assert torch.equal(idx.cpu(), c["topk"].long()), name            # margins checked when the fixture was written
-        emb = EagleB200(sd)._generate_slide_embedding(c["x"], cuda_device, agg_feats=c["agg"])
+        eagle = EagleB200(sd)
+        emb = eagle._generate_slide_embedding(c["x"], cuda_device, agg_feats=c["agg"])
         assert np.allclose(emb, c["eagle"].numpy(), rtol=1e-5, atol=1e-6), name
+        # patient level (eagle.py:122-134): the slides' features concatenated -> the same embedding for a split bag
+        h = c["x"].shape[0] // 2
+        pat = eagle._generate_patient_embedding([c["x"][:h], c["x"][h:]], cuda_device,
+                                                agg_feats_list=[c["agg"][:h], c["agg"][h:]])
+        assert np.allclose(pat, emb, rtol=1e-6, atol=1e-7), name
+        with pytest.raises(ValueError):
+            eagle._generate_patient_embedding([c["x"]], cuda_device)
