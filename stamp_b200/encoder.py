@@ -153,3 +153,55 @@ class EagleB200(ChiefB200):
             raise ValueError("agg_feats_list is required for patient embedding")
         return self._generate_slide_embedding(torch.cat(feats_list, dim=0), device,
                                               agg_feats=torch.cat(agg_feats_list, dim=0))
+
+
+# ---- TITAN: wrapper behaviour only (the slide transformer itself is un-vendored HF remote code) ----------------
+def titan_coords_px(coords_um, mpp: float, device=None) -> Tensor:
+    """titan.py:47-53: micron coordinates -> level-0 pixel coordinates, truncated to int64."""
+    c = torch.as_tensor(coords_um, dtype=torch.float32)
+    c = (c / mpp).to(torch.int64)
+    return c if device is None else c.to(device)
+
+
+def titan_virtual_slide(feats_list: list[Tensor], coords_um_list: list, tile_size_um: float):
+    """titan.py:131-168 + :64-83: all slides of a patient laid side by side along x (each slide shifted by the
+    right edge of the previous one), features concatenated -> (feats [1, N, D], coords_um [N, 2])."""
+    import numpy as np
+
+    shifted, offset = [], 0.0
+    for c in coords_um_list:
+        c = np.array(c, dtype=np.float64, copy=True)
+        c[:, 0] += offset
+        offset = float(c[:, 0].max()) + float(tile_size_um)
+        shifted.append(c)
+    return torch.cat(feats_list, dim=0).unsqueeze(0), np.concatenate(shifted, axis=0)
+
+
+class TitanB200:
+    """``Encoder``-shaped TITAN wrapper (identifier "titan", needs conch1_5 features): input preparation as in
+    the reference (src/stamp/encoding/encoder/titan.py:38-83); ``model`` is whatever provides
+    ``encode_slide_from_patch_features(feats, coords_px, patch_size_lvl0)`` -- the reference's is an un-vendored
+    Hugging Face remote-code model, which this repository neither restates nor accelerates."""
+
+    identifier = "titan"
+    precision = torch.float32
+
+    def __init__(self, model) -> None:
+        self.model = model
+
+    def _generate_slide_embedding(self, feats: Tensor, device, coords_um=None, mpp: float | None = None,
+                                  tile_size_px: int | None = None, **kwargs) -> np.ndarray:
+        if coords_um is None or mpp is None or tile_size_px is None:
+            raise ValueError("Coords must be provided.")
+        coords_px = titan_coords_px(coords_um, mpp, device)
+        with torch.inference_mode():
+            emb = self.model.encode_slide_from_patch_features(feats.to(device), coords_px, int(tile_size_px))
+        return emb.detach().squeeze().cpu().numpy()
+
+    def _generate_patient_embedding(self, feats_list: list[Tensor], device, coords_um_list=None, tile_size_um=None,
+                                    tile_size_px=None, **kwargs) -> np.ndarray:
+        if coords_um_list is None or tile_size_um is None or tile_size_px is None:
+            raise ValueError("coords_list must be provided.")
+        feats, coords_um = titan_virtual_slide(feats_list, coords_um_list, tile_size_um)
+        return self._generate_slide_embedding(feats, device, coords_um=coords_um, mpp=tile_size_um / tile_size_px,
+                                              tile_size_px=tile_size_px)
