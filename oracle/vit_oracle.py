@@ -26,8 +26,10 @@ The transform is ``ToTensor`` + ``Normalize(IMAGENET_DEFAULT_MEAN, IMAGENET_DEFA
 
 PARITY UNPINNED: timm, the pretrained weights and the reference's only golden test at this boundary
 (tests/test_feature_extractors.py:83-169, ctranspath only, needs network) are unavailable offline.
-The restatement is cross-checked against torchvision's independent ViT implementation
-(``tests/test_oracle_cpu.py::test_vit_oracle_matches_torchvision``).  State-dict keys are timm's.
+The restatement is cross-checked by weight mapping against two independent implementations:
+torchvision's ViT (``tests/test_oracle_cpu.py::test_vit_oracle_matches_torchvision``) and Hugging Face's
+``Dinov2WithRegistersModel`` for LayerScale / packed SwiGLU / register tokens
+(``::test_vit_oracle_matches_hf_dinov2_with_registers``).  State-dict keys are timm's.
 """
 
 from __future__ import annotations
