@@ -123,3 +123,26 @@ def sync_alibi_running_mean(model: nn.Module) -> None:
     flat.div_(ws)
     for i, b in enumerate(bufs):
         b.copy_(flat[i:i + 1].to(b.dtype))
+
+
+def crossval_splits(patients: Sequence[str], labels: Sequence | None, n_splits: int) -> list[tuple[list[str], list[str]]]:
+    """The reference's fold assignment (``_get_splits``, src/stamp/modeling/crossval.py:373-423):
+    ``StratifiedKFold(n_splits, shuffle=True, random_state=0)`` over the patients with their class labels
+    (plain ``KFold`` when ``labels`` is None: regression), so a fold trained here sees exactly the patients the
+    reference's fold would.  Returns ``[(train_patients, test_patients)]`` in fold order."""
+    import numpy as np
+    from sklearn.model_selection import KFold, StratifiedKFold
+
+    pts = np.array(list(patients))
+    if labels is None:
+        it = KFold(n_splits=n_splits, shuffle=True, random_state=0).split(pts)
+    else:
+        it = StratifiedKFold(n_splits=n_splits, shuffle=True, random_state=0).split(pts, np.array(list(labels)))
+    return [(pts[tr].tolist(), pts[te].tolist()) for tr, te in it]
+
+
+def folds_for_rank(n_folds: int, rank: int, world_size: int) -> list[int]:
+    """Fold-per-GPU cross-validation (SURVEY.md 8e): folds are independent trainings, so ``folds[rank::world]``
+    needs no collective at all and reproduces the sequential reference fold by fold; with more GPUs than folds
+    the surplus ranks get nothing (use data parallelism inside a fold instead)."""
+    return list(range(n_folds))[rank::world_size]

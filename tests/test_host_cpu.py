@@ -273,3 +273,24 @@ def test_titan_wrapper_input_preparation():
     assert out.tolist() == [32.0, 2048.0, 512.0]
     with pytest.raises(ValueError):
         enc._generate_slide_embedding(f1, "cpu")
+
+
+def test_crossval_splits_follow_the_reference_splitter():
+    """crossval.py:373-423: StratifiedKFold(shuffle=True, random_state=0) over the patient ids."""
+    import numpy as np
+    from sklearn.model_selection import StratifiedKFold
+
+    from stamp_b200.sharding import crossval_splits, folds_for_rank
+
+    patients = [f"pat{i:03d}" for i in range(64)]
+    labels = ["MSI" if i % 4 == 0 else "MSS" for i in range(64)]
+    splits = crossval_splits(patients, labels, 5)
+    ref = StratifiedKFold(n_splits=5, shuffle=True, random_state=0).split(np.array(patients), np.array(labels))
+    for (tr, te), (rtr, rte) in zip(splits, ref):
+        assert tr == np.array(patients)[rtr].tolist() and te == np.array(patients)[rte].tolist()
+    tests = [set(te) for _, te in splits]
+    assert set().union(*tests) == set(patients) and sum(len(t) for t in tests) == 64      # a partition
+    assert all(abs(sum(labels[patients.index(p)] == "MSI" for p in te) - 16 / 5) < 1.01 for _, te in splits)
+    assert len(crossval_splits(patients, None, 4)) == 4
+    assert [folds_for_rank(5, r, 8) for r in range(8)] == [[0], [1], [2], [3], [4], [], [], []]
+    assert [folds_for_rank(5, r, 2) for r in range(2)] == [[0, 2, 4], [1, 3]]
