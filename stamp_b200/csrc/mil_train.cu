@@ -579,14 +579,12 @@ wgrad_kernel(const uint16_t* __restrict__ dY, long long ldy, const uint16_t* __r
 
 inline int last_status() { return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA; }
 
-float* g_wgrad_scratch = nullptr;      // set by stamp_mil_train_backward for the duration of the call (one stream)
-size_t g_wgrad_scratch_bytes = 0;
-
+// scratch: per-split partial tiles for the tcgen05 kernel (part of the caller's ctx buffer), may be null
 int wgrad(const uint16_t* dY, long long ldy, const uint16_t* X, long long ldx, float* dW, long long ldw, int M,
-          int Nout, int Kin, cudaStream_t stream) {
+          int Nout, int Kin, float* scratch, size_t scratch_bytes, cudaStream_t stream) {
     if (M <= 0 || (Nout % 8) != 0 || (Kin % 8) != 0 || (ldy % 8) != 0 || (ldx % 8) != 0) return SB_ERR_BAD_ARG;
     {
-        const int rc = wgrad_tc(dY, ldy, X, ldx, dW, ldw, M, Nout, Kin, g_wgrad_scratch, g_wgrad_scratch_bytes,
+        const int rc = wgrad_tc(dY, ldy, X, ldx, dW, ldw, M, Nout, Kin, scratch, scratch_bytes,
                                 stream);   // long token dimension: tcgen05
         if (rc != SB_ERR_UNSUPPORTED) return rc;
     }
@@ -921,8 +919,8 @@ int stamp_mil_train_backward(const StampMilConfig* cfg, const StampMilTrainTop* 
     float* delta = reinterpret_cast<float*>(ws + L.off_delta);
     auto xbuf = [&](int i) { return reinterpret_cast<float*>(ws + L.off_x + L.x_stride * i); };
     const long long Md = static_cast<long long>(M) * d;
-    g_wgrad_scratch = reinterpret_cast<float*>(ws + L.off_wscratch);
-    g_wgrad_scratch_bytes = L.wscratch_bytes;
+    float* wsc = reinterpret_cast<float*>(ws + L.off_wscratch);
+    const size_t wsb = L.wscratch_bytes;
     const uint32_t th_ff = drop_thresh(step->p_drop_ff);
     const float ik_ff = inv_keep(step->p_drop_ff);
 
@@ -949,7 +947,7 @@ int stamp_mil_train_backward(const StampMilConfig* cfg, const StampMilTrainTop* 
 
         // ---- feed-forward block: x_out = x_mid + drop(ff2(drop(gelu(ff1(LN2(x_mid)))))) ----
         SB_TRY(mask_cast(dx, g16b, Md, th_ff, ik_ff, site_seed(step->seed, 2 + 2 * l), stream));   // dy [M,d]
-        SB_TRY(wgrad(g16b, d, h, ff, gy.ff2_w, ff, M, d, ff, stream));
+        SB_TRY(wgrad(g16b, d, h, ff, gy.ff2_w, ff, M, d, ff, wsc, wsb, stream));
         SB_TRY(colsum_bf16(g16b, d, M, d, gy.ff2_b, stream));
         {
             GemmParams p = gp_bf16(M, ff, d, ST_32, g32, ff, nullptr);                              // dh [M,ff]
@@ -961,7 +959,7 @@ int stamp_mil_train_backward(const StampMilConfig* cfg, const StampMilTrainTop* 
                 g32, z1, M, ff, g16a, 0, 0, 0, th_ff, ik_ff, site_seed(step->seed, 1 + 2 * l));    // dz1 [M,ff]
             count_launch();
         }
-        SB_TRY(wgrad(g16a, ff, xn2, d, gy.ff1_w, d, M, ff, d, stream));
+        SB_TRY(wgrad(g16a, ff, xn2, d, gy.ff1_w, d, M, ff, d, wsc, wsb, stream));
         SB_TRY(colsum_bf16(g16a, ff, M, ff, gy.ff1_b, stream));
         {
             GemmParams p = gp_bf16(M, d, ff, ST_32, g32, d, nullptr);                               // d xn2 [M,d]
@@ -971,7 +969,7 @@ int stamp_mil_train_backward(const StampMilConfig* cfg, const StampMilTrainTop* 
 
         // ---- attention block: x_mid = x_in + fc(attn(qkv(LN1(x_in)))) ----
         SB_TRY(mask_cast(dx, g16b, Md, 0u, 1.f, 0, stream));
-        SB_TRY(wgrad(g16b, d, att, d, gy.fc_w, d, M, d, d, stream));
+        SB_TRY(wgrad(g16b, d, att, d, gy.fc_w, d, M, d, d, wsc, wsb, stream));
         SB_TRY(colsum_bf16(g16b, d, M, d, gy.fc_b, stream));
         {
             GemmParams p = gp_bf16(M, d, d, ST_32, g32, d, nullptr);                                // d att [M,d] fp32
@@ -990,7 +988,7 @@ int stamp_mil_train_backward(const StampMilConfig* cfg, const StampMilTrainTop* 
         a.dout32 = g32; a.dout = g16a; a.delta = delta;
         a.dq = g16c; a.dk = g16c + d; a.dv = g16c + 2 * d;
         SB_TRY(attention_train_bwd(a, hd, stream));
-        SB_TRY(wgrad(g16c, 3LL * d, xn1, d, gy.qkv_w, d, M, 3 * d, d, stream));
+        SB_TRY(wgrad(g16c, 3LL * d, xn1, d, gy.qkv_w, d, M, 3 * d, d, wsc, wsb, stream));
         SB_TRY(colsum_bf16(g16c, 3LL * d, M, 3 * d, gy.qkv_b, stream));
         {
             GemmParams p = gp_bf16(M, d, 3 * d, ST_32, g32, d, nullptr);                            // d xn1 [M,d]
@@ -1008,7 +1006,7 @@ int stamp_mil_train_backward(const StampMilConfig* cfg, const StampMilTrainTop* 
             site_seed(step->seed, 0));                                                              // dz0 [BN,d]
         count_launch();
     }
-    SB_TRY(wgrad(g16a, d, bags16, F, gtop->proj_w, F, BN, d, F, stream));
+    SB_TRY(wgrad(g16a, d, bags16, F, gtop->proj_w, F, BN, d, F, wsc, wsb, stream));
     SB_TRY(colsum_bf16(g16a, d, BN, d, gtop->proj_b, stream));
     if (dbags != nullptr) {
         GemmParams p = gp_bf16(BN, F, d, ST_32, dbags, F, nullptr);
