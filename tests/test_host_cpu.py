@@ -294,3 +294,25 @@ def test_crossval_splits_follow_the_reference_splitter():
     assert len(crossval_splits(patients, None, 4)) == 4
     assert [folds_for_rank(5, r, 8) for r in range(8)] == [[0], [1], [2], [3], [4], [], [], []]
     assert [folds_for_rank(5, r, 2) for r in range(2)] == [[0, 2, 4], [1, 3]]
+
+
+def test_vals_to_im_matches_the_reference_function():
+    """heatmaps/__init__.py:142-156, executed from the reference file where it is present."""
+    ref_file = Path("/root/reference/src/stamp/heatmaps/__init__.py")
+    if not ref_file.exists():
+        pytest.skip("reference checkout not present on this machine")
+    from torch import Tensor
+
+    from stamp_b200.heatmaps import vals_to_im
+
+    ns = _reference_functions(ref_file, ["_vals_to_im"])
+    ns["Tensor"] = Tensor
+    g = torch.Generator().manual_seed(3)
+    cells = torch.randperm(7 * 5, generator=g)[:20]
+    coords = torch.stack([cells % 7, cells // 7], dim=-1)
+    for scores in (torch.rand(20, 3, generator=g), torch.rand(20, generator=g)):
+        assert torch.equal(vals_to_im(scores, coords), ns["_vals_to_im"](scores, coords))
+    with pytest.raises(RuntimeError):
+        from stamp_b200.heatmaps import ranked_tiles
+
+        ranked_tiles(torch.rand(5), 2, 2)
