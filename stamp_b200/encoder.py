@@ -9,13 +9,69 @@ src/stamp/encoding/encoder/chief.py:27-89,255-275 and eagle.py:92-120.
 from __future__ import annotations
 
 import ctypes as C
+from abc import ABC, abstractmethod
 from collections.abc import Mapping
+from enum import StrEnum
 
 import numpy as np
 import torch
 from torch import Tensor
 
 from . import _lib
+
+try:
+    # The reference's own base class and enums whenever STAMP is importable: ``init_slide_encoder_`` /
+    # ``init_patient_encoder_`` dispatch on ``case Encoder():`` (src/stamp/encoding/__init__.py:72-73,158-159),
+    # which only a subclass of *that* class satisfies, and the subclass inherits ``encode_slides_`` /
+    # ``encode_patients_`` (the h5 walk + atomic save, encoder/__init__.py:42-171,203-229) unchanged.
+    from stamp.encoding.config import EncoderName  # type: ignore[import-not-found]
+    from stamp.encoding.encoder import Encoder  # type: ignore[import-not-found]
+    from stamp.preprocessing.config import ExtractorName  # type: ignore[import-not-found]
+
+    BOUND_TO_REFERENCE = True
+except ImportError:
+    BOUND_TO_REFERENCE = False
+
+    class EncoderName(StrEnum):  # type: ignore[no-redef]
+        """The values of stamp.encoding.config.EncoderName this package provides."""
+
+        EAGLE = "eagle"
+        CHIEF_CTRANSPATH = "chief"
+
+    class ExtractorName(StrEnum):  # type: ignore[no-redef]
+        """The values of stamp.preprocessing.config.ExtractorName the encoders below name."""
+
+        CTRANSPATH = "ctranspath"
+        CHIEF_CTRANSPATH = "chief-ctranspath"
+        VIRCHOW2 = "virchow2"
+
+    class Encoder(ABC):  # type: ignore[no-redef]
+        """Stand-alone stand-in for stamp.encoding.encoder.Encoder (same constructor and abstract methods,
+        encoder/__init__.py:29-41); only used when the ``stamp`` package is not installed.  The feature-file walk
+        (``encode_slides_`` / ``encode_patients_``) is the reference's own code and needs its package."""
+
+        def __init__(self, model, identifier, precision: torch.dtype, required_extractors: list) -> None:
+            self.model, self.identifier = model, identifier
+            self.precision, self.required_extractors = precision, required_extractors
+
+        @abstractmethod
+        def _generate_slide_embedding(self, feats: Tensor, device, **kwargs) -> np.ndarray: ...
+
+        @abstractmethod
+        def _generate_patient_embedding(self, feats_list: list[Tensor], device, **kwargs) -> np.ndarray: ...
+
+        def encode_slides_(self, *args, **kwargs) -> None:
+            raise ImportError("encode_slides_ is STAMP's own h5 walk (src/stamp/encoding/encoder/__init__.py:42-93): "
+                              "install the stamp package; stamp_b200 then subclasses its Encoder")
+
+        encode_patients_ = encode_slides_
+
+_EagleBase = Encoder
+if BOUND_TO_REFERENCE:
+    try:  # EAGLE's feature-file pairing (ctranspath + virchow2 h5 per slide, eagle.py:40-89,136-300) is host I/O
+        from stamp.encoding.encoder.eagle import Eagle as _EagleBase  # type: ignore[import-not-found,no-redef]
+    except ImportError:  # its module imports gdown etc. at the top
+        pass
 
 
 class StampGatedAttnWeights(C.Structure):
@@ -109,14 +165,13 @@ class GatedAttentionPool(torch.nn.Module):
         return {"attention_raw": attn[None], "WSI_feature": pooled[None]}
 
 
-class ChiefB200:
-    """``Encoder``-shaped CHIEF slide encoder (identifier "chief", needs ctranspath features)."""
-
-    identifier = "chief"
-    precision = torch.float32
+class ChiefB200(Encoder):
+    """CHIEF slide encoder (``EncoderName.CHIEF_CTRANSPATH``; needs chief-ctranspath features): the constructor
+    arguments of the reference's ``CHIEF`` (chief.py:114-121) with the model replaced by the B200 pooling module."""
 
     def __init__(self, state_dict: Mapping[str, Tensor]) -> None:
-        self.model = GatedAttentionPool(state_dict)
+        super().__init__(model=GatedAttentionPool(state_dict), identifier=EncoderName.CHIEF_CTRANSPATH,
+                         precision=torch.float32, required_extractors=[ExtractorName.CHIEF_CTRANSPATH])
 
     def _generate_slide_embedding(self, feats: Tensor, device, **kwargs) -> np.ndarray:
         self.model.to(device)
@@ -127,11 +182,16 @@ class ChiefB200:
         return self._generate_slide_embedding(torch.cat(feats_list, 0), device)
 
 
-class EagleB200(ChiefB200):
-    """EAGLE: CHIEF attention over ctranspath features -> top-25 tiles -> mean of the matching
-    Virchow2 features (eagle.py:92-120)."""
+class EagleB200(_EagleBase):
+    """EAGLE (``EncoderName.EAGLE``): CHIEF attention over ctranspath features -> top-25 tiles -> mean of the
+    matching Virchow2 features (eagle.py:28-39,92-134).  With STAMP installed this subclasses the reference's
+    ``Eagle`` and inherits its feature-file pairing; only the arithmetic is replaced."""
 
-    identifier = "eagle"
+    def __init__(self, state_dict: Mapping[str, Tensor]) -> None:
+        self.required_agg_extractor = ExtractorName.VIRCHOW2
+        Encoder.__init__(self, model=GatedAttentionPool(state_dict), identifier=EncoderName.EAGLE,
+                         precision=torch.float32,
+                         required_extractors=[ExtractorName.CTRANSPATH, ExtractorName.CHIEF_CTRANSPATH])
 
     def _generate_slide_embedding(self, feats: Tensor, device, agg_feats: Tensor | None = None, **kwargs) -> np.ndarray:
         if agg_feats is None:
@@ -155,7 +215,9 @@ class EagleB200(ChiefB200):
                                               agg_feats=torch.cat(agg_feats_list, dim=0))
 
 
-# ---- TITAN: wrapper behaviour only (the slide transformer itself is un-vendored HF remote code) ----------------
+# ---- TITAN: NOT built.  The slide transformer is un-vendored Hugging Face remote code with
+# gated weights; nothing here restates or accelerates it.  What remains are the two pieces of input preparation of the
+# reference's wrapper that are in-tree arithmetic, for callers that feed their own TITAN model. -----------------------
 def titan_coords_px(coords_um, mpp: float, device=None) -> Tensor:
     """titan.py:47-53: micron coordinates -> level-0 pixel coordinates, truncated to int64."""
     c = torch.as_tensor(coords_um, dtype=torch.float32)
@@ -166,8 +228,6 @@ def titan_coords_px(coords_um, mpp: float, device=None) -> Tensor:
 def titan_virtual_slide(feats_list: list[Tensor], coords_um_list: list, tile_size_um: float):
     """titan.py:131-168 + :64-83: all slides of a patient laid side by side along x (each slide shifted by the
     right edge of the previous one), features concatenated -> (feats [1, N, D], coords_um [N, 2])."""
-    import numpy as np
-
     shifted, offset = [], 0.0
     for c in coords_um_list:
         c = np.array(c, dtype=np.float64, copy=True)
@@ -175,33 +235,3 @@ def titan_virtual_slide(feats_list: list[Tensor], coords_um_list: list, tile_siz
         offset = float(c[:, 0].max()) + float(tile_size_um)
         shifted.append(c)
     return torch.cat(feats_list, dim=0).unsqueeze(0), np.concatenate(shifted, axis=0)
-
-
-class TitanB200:
-    """``Encoder``-shaped TITAN wrapper (identifier "titan", needs conch1_5 features): input preparation as in
-    the reference (src/stamp/encoding/encoder/titan.py:38-83); ``model`` is whatever provides
-    ``encode_slide_from_patch_features(feats, coords_px, patch_size_lvl0)`` -- the reference's is an un-vendored
-    Hugging Face remote-code model, which this repository neither restates nor accelerates."""
-
-    identifier = "titan"
-    precision = torch.float32
-
-    def __init__(self, model) -> None:
-        self.model = model
-
-    def _generate_slide_embedding(self, feats: Tensor, device, coords_um=None, mpp: float | None = None,
-                                  tile_size_px: int | None = None, **kwargs) -> np.ndarray:
-        if coords_um is None or mpp is None or tile_size_px is None:
-            raise ValueError("Coords must be provided.")
-        coords_px = titan_coords_px(coords_um, mpp, device)
-        with torch.inference_mode():
-            emb = self.model.encode_slide_from_patch_features(feats.to(device), coords_px, int(tile_size_px))
-        return emb.detach().squeeze().cpu().numpy()
-
-    def _generate_patient_embedding(self, feats_list: list[Tensor], device, coords_um_list=None, tile_size_um=None,
-                                    tile_size_px=None, **kwargs) -> np.ndarray:
-        if coords_um_list is None or tile_size_um is None or tile_size_px is None:
-            raise ValueError("coords_list must be provided.")
-        feats, coords_um = titan_virtual_slide(feats_list, coords_um_list, tile_size_um)
-        return self._generate_slide_embedding(feats, device, coords_um=coords_um, mpp=tile_size_um / tile_size_px,
-                                              tile_size_px=tile_size_px)

@@ -5,7 +5,9 @@ Mirrors the reference's plugin interface (src/stamp/preprocessing/extractor/__in
 accepts an instance directly (src/stamp/preprocessing/__init__.py:117,237-238), moves ``model`` to
 the device, calls ``model(batch)`` under ``inference_mode`` and stores ``.half().cpu()``
 (:243,322-327).  ``identifier`` is what lands in the output folder name and the ``extractor`` h5
-attribute, so the factories below keep the reference's identifiers ("uni", "virchow2").
+attribute, so the factories below keep the reference's identifiers (the ``ExtractorName`` values
+"uni", "virchow2", "uni2", "h-optimus-0", "h-optimus-1"; src/stamp/preprocessing/config.py:13-33).
+When ``stamp`` is importable the factories return instances of the reference's own ``Extractor``.
 
 The transform returns the tile as a uint8 HWC tensor (legal: the reference's ``empty`` extractor
 does the same, src/stamp/preprocessing/extractor/empty.py:31-36); ToTensor + Normalize run on the
@@ -28,15 +30,25 @@ from .vit import (H_OPTIMUS_ARCH, UNI2_ARCH, UNI_ARCH, VIRCHOW2_ARCH, TileEncode
 
 ExtractorModel = TypeVar("ExtractorModel", bound=nn.Module)
 
+try:
+    # The reference's own class whenever STAMP is importable: ``extract_`` dispatches on
+    # ``case Extractor():`` (src/stamp/preprocessing/__init__.py:237-238), which only an instance of
+    # *that* class satisfies -- a look-alike dataclass would fall through to ``assert_never``.
+    from stamp.preprocessing.extractor import Extractor  # type: ignore[import-not-found]
 
-@dataclass(frozen=True)
-class Extractor(Generic[ExtractorModel]):
-    """Same fields as stamp.preprocessing.extractor.Extractor."""
+    BOUND_TO_REFERENCE = True
+except ImportError:
+    BOUND_TO_REFERENCE = False
 
-    _: KW_ONLY
-    model: ExtractorModel
-    transform: Callable[..., Tensor]
-    identifier: str
+    @dataclass(frozen=True)
+    class Extractor(Generic[ExtractorModel]):  # type: ignore[no-redef]
+        """Stand-alone stand-in with the fields of stamp.preprocessing.extractor.Extractor (:18-28);
+        only used when the ``stamp`` package is not installed."""
+
+        _: KW_ONLY
+        model: ExtractorModel
+        transform: Callable[..., Tensor]
+        identifier: str
 
 
 def pil_to_u8_hwc(img) -> Tensor:
@@ -106,13 +118,13 @@ def uni2(weights=None, max_batch: int = 96) -> Extractor[TileEncoder]:
 def h_optimus_0(weights=None, max_batch: int = 64) -> Extractor[TileEncoder]:
     """H-optimus-0 ViT-g/14 (reference: .../extractor/h_optimus_0.py:14-34; its Resize(224) is the identity
     on STAMP's 224 px tiles, mean / std are the model card's)."""
-    return _make(H_OPTIMUS_ARCH, "h_optimus_0", weights, "hf-hub:bioptimus/H-optimus-0",
+    return _make(H_OPTIMUS_ARCH, "h-optimus-0", weights, "hf-hub:bioptimus/H-optimus-0",
                  dict(init_values=1e-5, dynamic_img_size=False), max_batch)
 
 
 def h_optimus_1(weights=None, max_batch: int = 64) -> Extractor[TileEncoder]:
     """H-optimus-1, same architecture and preprocessing (reference: .../extractor/h_optimus_1.py)."""
-    return _make(H_OPTIMUS_ARCH, "h_optimus_1", weights, "hf-hub:bioptimus/H-optimus-1",
+    return _make(H_OPTIMUS_ARCH, "h-optimus-1", weights, "hf-hub:bioptimus/H-optimus-1",
                  dict(init_values=1e-5, dynamic_img_size=False), max_batch)
 
 

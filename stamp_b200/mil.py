@@ -57,6 +57,16 @@ def _bind() -> C.CDLL:
     return lib
 
 
+# Bumped by anything that rewrites parameters through raw device pointers (FusedAdamW.step): the parameters'
+# own version counters do not see such writes, so the packed-weight cache is keyed on this as well.
+_weights_epoch = 0
+
+
+def bump_weights_epoch() -> None:
+    global _weights_epoch
+    _weights_epoch += 1
+
+
 def round_to_tf32(t: Tensor) -> Tensor:
     """Round-to-nearest onto TF32's 10 explicit mantissa bits (the tensor core would truncate)."""
     i = t.detach().float().contiguous().view(torch.int32)
@@ -137,7 +147,22 @@ class VisionTransformer(nn.Module):
     # ---- weight packing: reference layout -> GEMM operands (cached until a parameter changes) ----
     def _pack_key(self):
         ps = list(self.parameters()) + list(self.buffers())
-        return (str(ps[0].device), tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
+        return (_weights_epoch, str(ps[0].device), tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
+
+    # ctypes structures with raw device pointers, workspaces and the checkpoint buffer are per-process caches:
+    # copy.deepcopy / torch.save(model) / spawn pickling carry the parameters only
+    _TRANSIENT = {"_packed": None, "_workspace": None, "_train_ctx": None, "_train_state": None}
+
+    def __getstate__(self):
+        state = dict(super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__)
+        state.update(self._TRANSIENT)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        for k, v in self._TRANSIENT.items():
+            self.__dict__.setdefault(k, v)
+        self.__dict__.setdefault("_train_gen", 0)
 
     def _pack(self):
         key = self._pack_key()
@@ -198,12 +223,16 @@ class VisionTransformer(nn.Module):
             raise ValueError(f"bags have {bags.shape[2]} features, model expects {self._cfg['dim_input']}")
         if not bags.is_cuda or not self.class_token.is_cuda:
             raise RuntimeError("stamp_b200 VisionTransformer runs on a CUDA device only (no CPU fallback)")
-        if torch.is_grad_enabled() and (bags.requires_grad or any(p.requires_grad for p in self.parameters())):
-            # training_step / heatmap gradients: checkpointing forward + backward kernels (train.py)
-            if mask is not None:
-                raise NotImplementedError(
-                    "gradients are implemented for the mask=None branch (the one every Lightning step and "
-                    "the heatmap Jacobian take); call masked forwards under torch.no_grad()")
+        wants_grad = torch.is_grad_enabled() and (bags.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if wants_grad and mask is not None:
+            raise NotImplementedError(
+                "stamp_b200 VisionTransformer: a masked forward cannot record an autograd graph (gradients exist "
+                "for the mask=None branch, the one every Lightning step and the heatmap Jacobian take). Wrap "
+                "masked evaluation in torch.no_grad() / inference_mode(), or freeze the model's parameters.")
+        if mask is None and (wants_grad or self.training):
+            # training_step / heatmap gradients: checkpointing forward + backward kernels (train.py).  A
+            # train-mode forward under no_grad takes the same path, so that dropout and the running-mean update
+            # of training mode happen exactly when the reference's module would apply them.
             from .train import mil_forward_with_grad
             return mil_forward_with_grad(self, bags, coords)
         lib = _bind()

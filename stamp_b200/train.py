@@ -26,7 +26,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from .mil import StampMilConfig, VisionTransformer
+from .mil import StampMilConfig, VisionTransformer, bump_weights_epoch
 
 _TOP_FIELDS = ("proj_w", "proj_b", "class_token", "norm_w", "norm_b", "head_w", "head_b")
 _LAYER_FIELDS = ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "bias_scale", "fc_w", "fc_b", "ln2_w", "ln2_b",
@@ -244,6 +244,7 @@ class _MilTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits: Tensor):
         want = bool(ctx.needs_input_grad[1])
+        ctx.st.model._train_state = None    # the hand-over slot only; ctx keeps the state (no model<->state cycle)
         dbags, *grads = _MilBwdFn.apply(dlogits, ctx.st, want)
         return (None, dbags if want else None, None, None, None, None, None, *grads)
 
@@ -328,10 +329,14 @@ class FusedAdamW(torch.optim.Optimizer):
 
     The parameters are re-pointed into one contiguous buffer (``p.data`` become views) and so are their
     ``.grad``; ``flat_grad`` is also what :class:`stamp_b200.sharding.FlatGradAllReducer` all-reduces.
-    Being a ``torch.optim.Optimizer`` it works with ``OneCycleLR`` (which cycles ``lr`` and ``betas[0]``)."""
+    Being a ``torch.optim.Optimizer`` it works with ``OneCycleLR`` (which cycles ``lr`` and ``betas[0]``).
+    One parameter group only; the moments and the step count travel in ``state_dict()`` (key ``"fused"``)."""
 
     def __init__(self, params: Iterable[Tensor], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2) -> None:
+        params = list(params)
+        if any(isinstance(p, dict) for p in params):
+            raise ValueError("FusedAdamW keeps ONE flat buffer: parameter groups are not supported")
         params = [p for p in params if p.requires_grad]
         if not params:
             raise ValueError("FusedAdamW got no trainable parameters")
@@ -339,6 +344,7 @@ class FusedAdamW(torch.optim.Optimizer):
             _need_cuda(p, "parameters")
             if p.dtype != torch.float32:
                 raise TypeError("FusedAdamW keeps fp32 master parameters")
+        self._built = False
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         dev = params[0].device
         # every parameter starts on a 256-byte boundary: the GEMM / vector kernels need 16-byte aligned bases
@@ -351,6 +357,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self.flat_grad = torch.zeros_like(self.flat_param)
         self.exp_avg = torch.zeros_like(self.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        self._params, self._offs, self._sizes = params, offs, sizes
         with torch.no_grad():
             for p, o, n in zip(params, offs, sizes):
                 view = self.flat_param[o:o + n]
@@ -358,9 +365,57 @@ class FusedAdamW(torch.optim.Optimizer):
                 p.data = view.view_as(p)
                 p.grad = self.flat_grad[o:o + n].view_as(p)
         self._step = 0
+        self._built = True
+        bump_weights_epoch()
+
+    def add_param_group(self, param_group) -> None:
+        if getattr(self, "_built", False):
+            raise ValueError("FusedAdamW keeps ONE flat buffer: parameter groups cannot be added after construction")
+        super().add_param_group(param_group)
+
+    # ---- checkpointing: the moments live outside Optimizer.state ---------------------------------------
+    def state_dict(self) -> dict:
+        sd = super().state_dict()
+        sd["fused"] = {"step": self._step, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                       "sizes": list(self._sizes)}
+        return sd
+
+    def load_state_dict(self, state_dict: dict) -> None:
+        fused = state_dict.get("fused")
+        if fused is None:
+            raise KeyError("not a FusedAdamW state dict (no 'fused' entry): the Adam moments would silently restart")
+        if list(fused["sizes"]) != list(self._sizes):
+            raise ValueError("FusedAdamW state dict was saved for a different parameter list")
+        super().load_state_dict({k: v for k, v in state_dict.items() if k != "fused"})
+        with torch.no_grad():
+            self.exp_avg.copy_(fused["exp_avg"])
+            self.exp_avg_sq.copy_(fused["exp_avg_sq"])
+        self._step = int(fused["step"])
+
+    # ---- the parameters and their gradients must still be views of the flat buffers ---------------------
+    @torch.no_grad()
+    def relink(self) -> None:
+        """``model.zero_grad()`` (``set_to_none=True``), ``p.grad = None`` or a stray ``.grad`` assignment detach a
+        gradient from ``flat_grad``: fold whatever autograd accumulated elsewhere back in and re-link the view.
+        A parameter that no longer lives in ``flat_param`` (``model.half()`` / ``.to()`` after construction) is an
+        error: the kernel would update memory the model does not read."""
+        pbase, gbase = self.flat_param.data_ptr(), self.flat_grad.data_ptr()
+        for p, o, n in zip(self._params, self._offs, self._sizes):
+            if p.data_ptr() != pbase + 4 * o or p.dtype != torch.float32:
+                raise RuntimeError("a parameter was moved or cast after FusedAdamW was built (its storage is no longer "
+                                   "the optimiser's flat buffer); build the optimiser after model.to(...)")
+            g = p.grad
+            if g is None or g.data_ptr() != gbase + 4 * o:
+                view = self.flat_grad[o:o + n].view_as(p)
+                if g is None:
+                    view.zero_()
+                else:
+                    view.copy_(g)
+                p.grad = view
 
     def zero_grad(self, set_to_none: bool = False) -> None:  # grads stay views of flat_grad
         self.flat_grad.zero_()
+        self.relink()
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
@@ -368,6 +423,7 @@ class FusedAdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        self.relink()
         lib = _bind()
         g = self.param_groups[0]
         self._step += 1
@@ -376,9 +432,9 @@ class FusedAdamW(torch.optim.Optimizer):
                                         float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
                                         float(g["weight_decay"]), self._step, float(grad_scale), _stream()),
                    "stamp_adamw_step")
-        # the kernel wrote through raw pointers: bump the version counter the parameter views share, so
-        # caches keyed on it (VisionTransformer._pack) see the update
-        self.flat_param[:0].zero_()
+        # the kernel wrote through raw pointers, which no version counter sees: invalidate the packed-weight
+        # caches (VisionTransformer._pack) explicitly
+        bump_weights_epoch()
         return loss
 
 
@@ -402,6 +458,7 @@ def data_parallel_step(model: VisionTransformer, opt: FusedAdamW, batch, class_w
     opt.zero_grad()
     loss = training_step(model, batch, class_weights)
     loss.backward()
+    opt.relink()                 # gradients that autograd put elsewhere are folded into flat_grad first
     scale = all_reduce_flat_sum(opt.flat_grad)
     sync_alibi_running_mean(model)
     opt.step(grad_scale=scale)

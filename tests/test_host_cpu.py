@@ -252,7 +252,7 @@ def test_titan_wrapper_input_preparation():
     """titan.py:47-53 (um -> int64 px) and :131-168 (virtual slide: slides side by side along x)."""
     import numpy as np
 
-    from stamp_b200.encoder import TitanB200, titan_coords_px, titan_virtual_slide
+    from stamp_b200.encoder import titan_coords_px, titan_virtual_slide
 
     px = titan_coords_px(np.array([[0.0, 256.0], [511.9, 1024.2]]), mpp=0.5)
     assert px.dtype == torch.int64 and px.tolist() == [[0, 512], [1023, 2048]]
@@ -263,16 +263,6 @@ def test_titan_wrapper_input_preparation():
     assert feats.shape == (1, 5, 4) and coords[:2].tolist() == c1.tolist()
     assert coords[2:, 0].tolist() == [512.0, 1024.0, 768.0] and coords[2:, 1].tolist() == [0.0, 0.0, 256.0]
     assert c2[0, 0] == 0.0                                    # inputs are not modified in place
-
-    class Fake:
-        def encode_slide_from_patch_features(self, feats, coords_px, patch):
-            return torch.tensor([[float(feats.sum()), float(coords_px.max()), float(patch)]])
-
-    enc = TitanB200(Fake())
-    out = enc._generate_patient_embedding([f1, f2], "cpu", coords_um_list=[c1, c2], tile_size_um=256.0, tile_size_px=512)
-    assert out.tolist() == [32.0, 2048.0, 512.0]
-    with pytest.raises(ValueError):
-        enc._generate_slide_embedding(f1, "cpu")
 
 
 def test_crossval_splits_follow_the_reference_splitter():

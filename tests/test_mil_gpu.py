@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from test_oracle_cpu import GOLDEN, load_golden
+from test_oracle_cpu import GOLDEN, GOLDEN_LONG, load_golden, load_golden_long
 
 pytestmark = pytest.mark.gpu
 
@@ -43,6 +43,20 @@ def test_mil_matches_reference_golden(cuda_device, path):
     assert out.shape == ref_logits.shape and torch.isfinite(out).all()
     err = _rel_per_bag(out, ref_logits)
     print(path.stem, "max per-bag relative error", err)
+    assert err < 1e-3, err
+
+
+@pytest.mark.parametrize("path", GOLDEN_LONG, ids=[p.stem for p in GOLDEN_LONG])
+def test_mil_long_bag_matches_reference_golden(cuda_device, path):
+    """The benched shape (one bag of 4096 x 1024, default-size model, trained running mean) against the logits
+    of the reference module itself: pins the tcgen05 long-bag attention kernel to vision_tranformer.py:42-74
+    (ALiBi) and :218-228 (nn.MultiheadAttention) directly, not through the oracle."""
+    sd, bags, coords, ref_logits = load_golden_long(path)
+    model = _model_from_sd(sd, 8, cuda_device)
+    with torch.inference_mode():
+        out = model(bags.to(cuda_device), coords=coords.to(cuda_device), mask=None)
+    err = _rel_per_bag(out, ref_logits)
+    print(path.stem, "max per-bag relative error vs the reference module", err)
     assert err < 1e-3, err
 
 
@@ -123,10 +137,13 @@ def test_mil_heatmap_style_per_tile_batch(cuda_device):
     assert fro < 1e-3, fro
     # top-k tile indices identical (north_star: bit-exact top-k) on the class-1 probability
     pr, po = torch.softmax(ref, 1)[:, 1], torch.softmax(out.cpu().float(), 1)[:, 1]
-    k = 10
+    # margin-checked fixture: the largest k <= 10 whose ranks 1..k+1 are separated by more than the numerical
+    # noise of the scores; the margin itself is asserted (a fixture without one would not test the contract)
     gap = pr.sort(descending=True).values
-    if (gap[:k] - gap[1:k + 1]).min() > 1e-4:  # margin-checked fixture
-        assert torch.equal(pr.topk(k).indices, po.topk(k).indices)
+    margins = gap[:11] - gap[1:12]
+    k = max(kk for kk in range(1, 11) if margins[:kk].min() > 1e-4)
+    assert k >= 5, f"fixture has no score margin among its top tiles: {margins.tolist()}"
+    assert torch.equal(pr.topk(k).indices, po.topk(k).indices)
 
 
 def test_mil_empty_and_tiny_bags(cuda_device):

@@ -162,6 +162,41 @@ def test_default_size_gradients_match_oracle(cuda_device, n_tiles, batch):
     _check_grads(model, ref_grads, f"default N={n_tiles}")
 
 
+def test_benched_shape_gradients_match_oracle(cuda_device):
+    """The shape bench.py and BASELINE configs[3] run: 8 bags of 4096 x 1024 per GPU, default model.  All eight bags
+    go through the kernels; two of them (first and sixth) carry the loss (the other targets are all-zero rows, whose
+    cross-entropy term and gradient vanish), so the fp32 CPU oracle only has to differentiate two 4097-token bags.
+    The running mean is updated from the distances of all eight bags, as the reference does."""
+    from stamp_b200 import train as T
+
+    B, N, live = 8, 4096, (0, 5)
+    sd = mil_oracle.init_state_dict(dim_input=1024, dim_output=2, seed=5)
+    bags, coords = mil_oracle.synthetic_bag(N, 1024, seed=4242, batch=B, signal=True)
+    targets = torch.zeros(B, 2)
+    for i, b in enumerate(live):
+        targets[b, i % 2] = 1.0
+    model = _model(sd, 8, cuda_device)
+    loss = T.training_step(model, (bags.to(cuda_device), coords.to(cuda_device), None, targets.to(cuda_device)), None)
+    loss.backward()
+    torch.cuda.synchronize()
+
+    sd2 = mil_oracle.running_mean_update(sd, coords)
+    for k, v in model.state_dict().items():
+        if "scale_distance" in k:
+            assert torch.allclose(v.cpu(), sd2[k], rtol=1e-4), k
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd2.items() if "scale_distance" not in k}
+    full = {**sd2, **params}
+    ref_loss = 0.0
+    for b in live:   # one bag at a time: the S x S intermediates of one bag are ~5 GB in fp32
+        logits = mil_oracle.forward(full, bags[b:b + 1], coords[b:b + 1], None, exact_dist=True)
+        term = mil_oracle.cross_entropy(logits, targets[b:b + 1], None) / B
+        term.backward()
+        ref_loss += float(term.detach())
+    ref_grads = {k: v.grad.detach() for k, v in params.items()}
+    assert abs(float(loss.detach()) - ref_loss) < LOGIT_TOL * max(1.0, ref_loss), (float(loss.detach()), ref_loss)
+    _check_grads(model, ref_grads, "benched shape 8 x 4096")
+
+
 def test_default_size_mha_variant_matches_oracle(cuda_device):
     """use_alibi=False (the reference's default backbone): long bag -> tcgen05 forward / backward, plain softmax."""
     from stamp_b200 import train as T
@@ -311,6 +346,104 @@ def test_golden_adamw_step(cuda_device):
     sd_after = {k: v for k, v in g["after"].items()}
     ref = mil_oracle.forward(sd_after, g["bags"], g["coords"], None)
     assert ((a.cpu() - ref).norm(dim=1) / ref.norm(dim=1)).max() < 2e-2
+
+
+@pytest.mark.parametrize("use_alibi", [False, True])
+def test_eval_forward_after_optimizer_step_uses_new_weights(cuda_device, use_alibi):
+    """validate -> train -> validate: the packed-weight cache of the inference path must be rebuilt after
+    FusedAdamW.step (it writes the parameters through raw pointers, which no version counter sees).  With
+    use_alibi=False -- the reference's default -- no running-mean buffer changes between the two evaluations, so
+    nothing else invalidates the cache."""
+    from stamp_b200 import train as T
+
+    sd = mil_oracle.init_state_dict(dim_input=64, dim_output=2, dim_model=128, n_heads=2, dim_feedforward=128,
+                                    seed=17, use_alibi=use_alibi)
+    bags, coords = mil_oracle.synthetic_bag(90, 64, seed=3, batch=2, signal=True)
+    targets = torch.nn.functional.one_hot(torch.arange(2) % 2, 2).float()
+    model = _model(sd, 2, cuda_device)
+    opt = T.FusedAdamW(model.parameters(), lr=5e-2)
+    dev = lambda t: t.to(cuda_device)
+    model.eval()
+    with torch.no_grad():
+        before = model(dev(bags), coords=dev(coords), mask=None).cpu()      # packs (and caches) the weights
+    model.train()
+    T.training_step(model, (dev(bags), dev(coords), None, dev(targets)), None).backward()
+    opt.step()
+    model.eval()
+    with torch.no_grad():
+        after = model(dev(bags), coords=dev(coords), mask=None).cpu()
+    sd_now = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref = mil_oracle.forward(sd_now, bags, coords, None, n_heads=2)
+    assert (after - before).abs().max() > 1e-3, "the step at lr 5e-2 must move the logits"
+    rel = ((after - ref).norm(dim=1) / ref.norm(dim=1)).max()
+    assert rel < 1e-3, float(rel)
+
+
+def test_fused_adamw_state_dict_relink_and_groups(cuda_device):
+    """Checkpoint / resume keeps the Adam moments and the bias-correction step; gradients detached from the flat
+    buffer (model.zero_grad(set_to_none=True), stray .grad tensors) are folded back in; one group only."""
+    from stamp_b200 import train as T
+
+    g = torch.Generator().manual_seed(2)
+    shapes = [(64, 32), (64,), (1,)]
+    mk = lambda: [torch.nn.Parameter(torch.randn(s, generator=torch.Generator().manual_seed(7 + i)).to(cuda_device))
+                  for i, s in enumerate(shapes)]
+    a, b, r = mk(), mk(), [torch.nn.Parameter(p.detach().clone()) for p in mk()]
+    oa, ob, ref = T.FusedAdamW(a, lr=1e-2), T.FusedAdamW(b, lr=1e-2), torch.optim.AdamW(r, lr=1e-2)
+    grads = [[torch.randn(s, generator=g).to(cuda_device) for s in shapes] for _ in range(4)]
+
+    def feed(params, gs, detach):
+        for p, x in zip(params, gs):
+            if detach:
+                p.grad = None               # what model.zero_grad() does by default
+                p.grad = x.clone()          # autograd then allocates a fresh tensor
+            else:
+                p.grad.copy_(x)
+
+    for i in range(2):
+        feed(a, grads[i], detach=False); oa.step(); oa.zero_grad()
+        feed(r, grads[i], detach=True); ref.step()
+    state = oa.state_dict()
+    assert "fused" in state and state["fused"]["step"] == 2
+    with torch.no_grad():
+        for p, q in zip(b, a):
+            p.copy_(q)
+    ob.load_state_dict(state)               # resume in a fresh optimiser
+    for i in range(2, 4):
+        feed(b, grads[i], detach=True); ob.step()          # detached gradients: relink folds them in
+        feed(r, grads[i], detach=True); ref.step()
+    for p, q in zip(b, r):
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-6)
+        assert p.grad.data_ptr() >= ob.flat_grad.data_ptr()          # re-linked into the flat buffer
+    with pytest.raises(ValueError):
+        ob.add_param_group({"params": [torch.nn.Parameter(torch.zeros(4, device=cuda_device))]})
+    with pytest.raises(KeyError):
+        ob.load_state_dict(ref.state_dict())
+    b[0].data = b[0].data.clone()           # parameter moved out of the flat buffer: refuse to step
+    with pytest.raises(RuntimeError):
+        ob.step()
+
+
+def test_model_deepcopy_and_train_mode_forward_without_grad(cuda_device):
+    import copy
+
+    sd = mil_oracle.init_state_dict(dim_input=64, dim_output=2, dim_model=128, n_heads=2, dim_feedforward=128, seed=19)
+    bags, coords = mil_oracle.synthetic_bag(40, 64, seed=4, batch=1)
+    model = _model(sd, 2, cuda_device).eval()
+    with torch.no_grad():
+        a = model(bags.to(cuda_device), coords=coords.to(cuda_device), mask=None)
+    twin = copy.deepcopy(model)             # the ctypes caches are dropped, not pickled
+    assert twin._packed is None and twin._workspace is None
+    with torch.no_grad():
+        assert torch.equal(a, twin(bags.to(cuda_device), coords=coords.to(cuda_device), mask=None))
+    # train mode under no_grad behaves like the reference module: the running mean moves
+    twin.train()
+    rm0 = twin.transformer.layers[0][0].mhsa.attentions[0].scale_distance.running_mean.clone()
+    with torch.no_grad():
+        twin(bags.to(cuda_device), coords=coords.to(cuda_device), mask=None)
+    assert not torch.equal(rm0, twin.transformer.layers[0][0].mhsa.attentions[0].scale_distance.running_mean)
+    with pytest.raises(NotImplementedError):
+        twin(bags.to(cuda_device), coords=coords.to(cuda_device), mask=torch.zeros(1, 40, dtype=torch.bool, device=cuda_device))
 
 
 def test_loss_decreases_on_planted_signal(cuda_device):

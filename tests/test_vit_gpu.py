@@ -87,6 +87,45 @@ def test_virchow2_vit_h14_matches_oracle(cuda_device):
     assert err < 1e-3, err
 
 
+def _run_in_full_batch(cfg_o, n_oracle, batch, device):
+    """The benched batch: `n_oracle` oracle-checked tiles spread over a batch of `batch` different tiles (the GEMM
+    wave shape, CTA-pair tiles and attention grid of the bench), same < 1e-3 per-tile bound."""
+    from oracle import vit_oracle as vo
+    from stamp_b200.vit import TileEncoder, VitArch
+
+    w = vo.make_weights(cfg_o, seed=1234)
+    tiles = vo.synthetic_tiles(batch, seed=17, img=cfg_o.img)
+    pos = torch.linspace(0, batch - 1, n_oracle).round().long()
+    with torch.no_grad():
+        ref = vo.forward(w, cfg_o, tiles[pos])
+    arch = VitArch(cfg_o.name, img=cfg_o.img, patch=cfg_o.patch, dim=cfg_o.dim, depth=cfg_o.depth,
+                   heads=cfg_o.heads, mlp_hidden=cfg_o.mlp_hidden, mlp=cfg_o.mlp,
+                   reg_tokens=cfg_o.reg_tokens, ln_eps=cfg_o.ln_eps, no_embed_class=cfg_o.no_embed_class,
+                   mean=cfg_o.mean, std=cfg_o.std)
+    enc = TileEncoder(arch, w, max_batch=batch).to(device).eval()
+    out = enc(tiles.to(device))
+    assert out.shape == (batch, cfg_o.dim) and torch.isfinite(out).all()
+    # every tile of the batch is a different image: no two feature rows may coincide (a mis-indexed batch would)
+    assert torch.unique(out.float().cpu(), dim=0).shape[0] == batch
+    return _per_tile_rel(out[pos.to(device)].float(), ref)
+
+
+def test_uni_vit_l16_at_benched_batch_192(cuda_device):
+    from oracle import vit_oracle as vo
+
+    err = _run_in_full_batch(vo.UNI, 4, 192, cuda_device)
+    print("ViT-L/16 @ batch 192, max per-tile relative error:", err)
+    assert err < 1e-3, err
+
+
+def test_virchow2_vit_h14_at_benched_batch_96(cuda_device):
+    from oracle import vit_oracle as vo
+
+    err = _run_in_full_batch(vo.VIRCHOW2, 2, 96, cuda_device)
+    print("ViT-H/14 @ batch 96, max per-tile relative error:", err)
+    assert err < 1e-3, err
+
+
 def test_tile_encoder_refuses_cpu():
     from oracle import vit_oracle as vo
     from stamp_b200.vit import TileEncoder, VitArch
