@@ -386,7 +386,8 @@ int launch_attn(const AttnParams& p, cudaStream_t stream) {
             return SB_ERR_CUDA;
         configured = true;
     }
-    dim3 grid(p.B * p.H, (p.S + BQ - 1) / BQ);  // (bag, head) on x: heatmaps call with B = n_tiles
+    const int nq = (p.q_rows > 0 && p.q_rows < p.S) ? p.q_rows : p.S;
+    dim3 grid(p.B * p.H, (nq + BQ - 1) / BQ);  // (bag, head) on x: heatmaps call with B = n_tiles
     // algorithmic FLOPs of the reference math: QK^T and one [S,S]x[S,hd] product per head
     ProfScope prof(PROF_ATTN, 4.0 * p.B * p.H * static_cast<double>(p.S) * p.S * HD, stream);
     flash_attn_kernel<HD, ALIBI><<<grid, ATT_THREADS, bytes, stream>>>(p);
@@ -403,9 +404,7 @@ int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream) {
         return SB_ERR_BAD_ARG;
     // short unmasked sequences (ViT tiles): tcgen05 kernel; anything else: the general kernel below
     {
-        int rc = attention_vit_persist_fwd(p, head_dim, stream);   // persistent, single TMEM pass
-        if (rc != SB_ERR_UNSUPPORTED) return rc;
-        rc = attention_tc_fwd(p, head_dim, stream);
+        const int rc = attention_tc_fwd(p, head_dim, stream);
         if (rc != SB_ERR_UNSUPPORTED) return rc;
     }
     // long unmasked bags (MIL aggregator, plain or ALiBi): tcgen05 two-pass kernel

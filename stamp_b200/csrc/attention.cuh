@@ -26,6 +26,8 @@ struct AttnParams {
     const float* dscale;     // [B, 2] {2^-e, 2^e} from alibi_dist_scale
     const uint8_t* mask;     // [B, S] 1 = masked token, or null
     int mask_mode;           // 1: reference ALiBi masked branch (post-softmax), 2: -inf before softmax
+    int q_rows;              // 0: every token is a query; n > 0: only the first n tokens' outputs are needed (rows up
+                             // to the end of their query tile may still be written)
 };
 
 int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
@@ -34,10 +36,6 @@ int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 int attention_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 void attention_tc_enable(int on);
 void attention_tc_set_trace(long long* device_buf);  // debug: 5 x int64 per CTA (phase cycle counts)
-// persistent single-TMEM-pass kernel for ViT tiles (attention_vit_persist.cu), tried before attention_tc_fwd
-int attention_vit_persist_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
-void attention_vit_persist_enable(int on);
-void attention_vit_persist_set_trace(long long* device_buf);  // debug: 6 x int64 per CTA
 // tcgen05 two-pass kernel for long unmasked bags, plain or ALiBi (attention_mil_tc.cu)
 int attention_mil_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 void attention_mil_tc_enable(int on);

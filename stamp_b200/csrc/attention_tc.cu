@@ -278,7 +278,8 @@ int attention_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream) {
         configured_bytes = L.total;
     }
     if (static_cast<long long>(p.B) * p.H > 65535) return SB_ERR_UNSUPPORTED;
-    dim3 grid((p.S + 127) / 128, p.B * p.H);
+    const int nq = (p.q_rows > 0 && p.q_rows < p.S) ? p.q_rows : p.S;
+    dim3 grid((nq + 127) / 128, p.B * p.H);
     ProfScope prof(PROF_ATTN, 4.0 * p.B * p.H * static_cast<double>(p.S) * p.S * 64, stream);
     vit_attn_tc_kernel<<<grid, TC_THREADS, L.total, stream>>>(
         tm_q, tm_kv, static_cast<__half*>(p.out), p.out_row_stride, p.out_batch_stride, p.S, p.H, D, nk,

@@ -39,7 +39,6 @@ void stamp_b200_gemm_force_mode(int mode) { sb::gemm_force_mode(mode); }
 // development aid (not part of the public header): per-CTA phase cycle counts of the ViT attention
 void stamp_b200_debug_attention_trace(long long* device_buf) {
     sb::attention_tc_set_trace(device_buf);
-    sb::attention_vit_persist_set_trace(device_buf);
 }
 
 void stamp_b200_attention_tc_enable(int on) {
@@ -47,9 +46,6 @@ void stamp_b200_attention_tc_enable(int on) {
     sb::attention_mil_tc_enable(on);        // bit 0 on/off, bit 2 two-pass kernel, bit 3 eager rescale (tests)
     sb::attention_train_tc_enable(on & 1);
     sb::wgrad_tc_enable(on & 1);
-    // bit 1: prefer the persistent single-TMEM-pass ViT kernel (measured equal to the default
-    // two-CTA-per-SM kernel on B200, kept as an opt-in alternative)
-    sb::attention_vit_persist_enable((on & 2) != 0);
 }
 
 int stamp_gemm_tn(const void* A, long long lda, const void* W, long long ldw, void* out,

@@ -116,6 +116,25 @@ __device__ __forceinline__ void umma_commit_cta2(uint64_t* bar) {
         : "memory");
 }
 
+// ---- TMA stores of the epilogue (bulk async-group completion) -----------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// global[tile] += smem[tile], element type of the tensor map (fp32); performed by the L2 atomics units
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+// the staging tile may be overwritten once the previous bulk operations have READ it
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+
 // ---- epilogue for 4 consecutive columns [n, n+4) of output row `orow` (input row m) ------------
 // (slow path: only the ragged right edge of a matrix with N % 4 != 0 comes through here)
 // (inlined exactly once, in a non-unrolled loop: a real call would force the kernel parameter
@@ -241,11 +260,11 @@ __device__ __forceinline__ void epilogue4(const GemmParams& p, float4 acc, int m
     }
 }
 
-template <int BN, bool TF32, int CTAS>
+template <int BN, bool TF32, int CTAS, int EPI>
 // 10 warps: one SM sub-partition (16K registers) hosts 3 of them -> at most 168 registers per thread
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     using C = Cfg<BN, CTAS>;
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle needs 1024-byte aligned tiles (identical offset in both CTAs of a pair)
@@ -268,6 +287,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if constexpr (EPI != 0) tma_prefetch_desc(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < C::STAGES; ++i) {
@@ -390,6 +410,110 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 orow[k] = (p.gin > 0) ? (m / p.gin) * p.gout + p.goff + (m % p.gin) : m;
             }
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+            if constexpr (EPI != 0) {
+                // ---- one thread per accumulator row; the output leaves through a TMA store / reduce-add ----
+                const uint32_t srow = stg + lane * 128;    // this lane's 128-byte row of the staging tile
+                const int sw = lane & 7;                   // 128B swizzle: 16-byte chunk index ^ (row & 7)
+                const bool swiglu = (EPI == 1) && p.store == ST_SWIGLU16;
+#pragma unroll 1
+                for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+                    const int col = chalf * COLS_PER_WARP + c * 32;
+                    const int n0 = n_blk * BN + col;
+                    if (n0 >= p.N) break;  // warp-uniform
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_row + col, r);
+                    // the bias of the 32 columns is the same for every lane: uniform (broadcast) loads
+                    float4 b4[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        b4[j] = (p.bias != nullptr && n0 + 4 * j < p.N) ? ldg4(p.bias + n0 + 4 * j)
+                                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[4 * j] = __uint_as_float(r[4 * j]) + b4[j].x;
+                        v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4[j].y;
+                        v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4[j].z;
+                        v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4[j].w;
+                    }
+                    if (p.act == ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    } else if (p.act == ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                    }
+                    if constexpr (EPI == 1) {
+                        const bool bf = p.bf16 != 0;
+                        if (swiglu) {
+                            // column pairs (x1, x2) -> one output: 16 outputs = 32 bytes of the row per chunk;
+                            // the four chunks of this warp fill one 64-output (128-byte) row
+                            if (c == 0) {
+                                if (lane == 0) bulk_wait_read0();
+                                __syncwarp();
+                            }
+                            uint32_t w[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                w[j] = pack_16(silu(v[4 * j]) * v[4 * j + 1], silu(v[4 * j + 2]) * v[4 * j + 3], bf);
+                            sts_v4(srow + (((2 * c) ^ sw) * 16), make_uint4(w[0], w[1], w[2], w[3]));
+                            sts_v4(srow + (((2 * c + 1) ^ sw) * 16), make_uint4(w[4], w[5], w[6], w[7]));
+                            const bool last = (c == COLS_PER_WARP / 32 - 1) || (n0 + 32 >= p.N);
+                            if (last) {
+                                fence_proxy_async();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    tma_store_2d(&tmC, stg, (n_blk * BN + chalf * COLS_PER_WARP) >> 1, m_base);
+                                    bulk_commit();
+                                }
+                            }
+                        } else {
+                            // 32 outputs = 64 bytes: two chunks fill one 64-column (128-byte) staging row
+                            if ((c & 1) == 0) {
+                                if (lane == 0) bulk_wait_read0();
+                                __syncwarp();
+                            }
+                            uint32_t w[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) w[j] = pack_16(v[2 * j], v[2 * j + 1], bf);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                sts_v4(srow + ((((c & 1) * 4 + j) ^ sw) * 16),
+                                       make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
+                            if ((c & 1) == 1 || n0 + 32 >= p.N) {
+                                fence_proxy_async();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    tma_store_2d(&tmC, stg, n0 - (c & 1) * 32, m_base);
+                                    bulk_commit();
+                                }
+                            }
+                        }
+                    } else {
+                        // x += gamma * (acc + bias): 32 fp32 columns = one 128-byte staging row per chunk
+                        if (p.gamma != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 g4 = (n0 + 4 * j < p.N) ? ldg4(p.gamma + n0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                v[4 * j] *= g4.x; v[4 * j + 1] *= g4.y; v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
+                            }
+                        }
+                        if (lane == 0) bulk_wait_read0();
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            sts_v4(srow + ((j ^ sw) * 16), make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                                      __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_reduce_add_2d(&tmC, stg, n0, m_base);
+                            bulk_commit();
+                        }
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
                 const int col = chalf * COLS_PER_WARP + c * 32;
@@ -525,6 +649,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 __syncwarp();
             }
+            }  // EPI == 0
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -532,6 +657,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 else mbar_arrive(&tempty_bar[acc]);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if constexpr (EPI != 0) {
+            if (lane == 0) bulk_wait0();   // every store / reduce of this warp has completed before the CTA exits
         }
     }
 
@@ -604,15 +732,15 @@ int make_tmap_3d_f16(CUtensorMap* tm, const void* ptr, int inner, int rows, int 
 namespace {
 
 int g_num_sms = 0;
-int g_force_mode = 0;  // 0 auto, 1 never use the 2-CTA kernel, 2 always (when legal): tests / tuning
+int g_force_mode = 0;  // bits 0-1: 0 auto, 1 never use the 2-CTA kernel, 2 always (when legal); bit 2: legacy epilogue
 
-template <int BN, bool TF32, int CTAS>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int tiles,
+template <int BN, bool TF32, int CTAS, int EPI>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int tiles,
            cudaStream_t stream) {
     using C = Cfg<BN, CTAS>;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tn_kernel<BN, TF32, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(gemm_tn_kernel<BN, TF32, CTAS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  C::SMEM_BYTES) != cudaSuccess)
             return SB_ERR_CUDA;
         configured = true;
@@ -632,11 +760,11 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, TF32, CTAS>, tmA, tmB, p);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, TF32, CTAS, EPI>, tmA, tmB, tmC, p);
     count_launch();
     if (e != cudaSuccess) {
-        fprintf(stderr, "stamp_b200: gemm_tn_kernel<%d,%d,%d> launch failed: %s (grid %d, smem %d)\n", BN,
-                static_cast<int>(TF32), CTAS, cudaGetErrorString(e), grid, C::SMEM_BYTES);
+        fprintf(stderr, "stamp_b200: gemm_tn_kernel<%d,%d,%d,%d> launch failed: %s (grid %d, smem %d)\n", BN,
+                static_cast<int>(TF32), CTAS, EPI, cudaGetErrorString(e), grid, C::SMEM_BYTES);
         cudaGetLastError();
     }
     return e == cudaSuccess ? SB_OK : SB_ERR_CUDA;
@@ -679,22 +807,41 @@ int gemm_tn(const void* A, long long lda, const void* B, long long ldb, const Ge
     // 128 x 256 unless that leaves most SMs without a tile
     const int tiles_pair = ((p.M + 255) / 256) * ((p.N + 255) / 256);
     bool use_pair = !p.tf32 && p.N >= 256 && tiles_pair >= 2 * (g_num_sms / 2);
-    if (g_force_mode == 1) use_pair = false;
-    if (g_force_mode == 2 && !p.tf32) use_pair = true;
+    if ((g_force_mode & 3) == 1) use_pair = false;
+    if ((g_force_mode & 3) == 2 && !p.tf32) use_pair = true;
     const bool use256 = (p.N >= 256) && (tiles256 >= g_num_sms);
     const int bn = (use_pair || use256) ? 256 : 128;
 
     const int kind = p.tf32 ? 2 : (p.bf16 ? 1 : 0);
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
     if (p.a_kwrap < 0 || (p.a_kwrap % 64) != 0) return SB_ERR_BAD_ARG;
     int rc = make_tmap(&tmA, A, p.M, p.a_kwrap > 0 ? p.a_kwrap : p.K, lda, BM, kind);
     if (rc != SB_OK) return rc;
     rc = make_tmap(&tmB, B, p.N, p.K, ldb, use_pair ? 128 : bn, kind);
     if (rc != SB_OK) return rc;
 
-    if (use_pair) return launch<256, false, 2>(tmA, tmB, p, tiles_pair, stream);
-    if (p.tf32) return use256 ? launch<256, true, 1>(tmA, tmB, p, tiles256, stream) : launch<128, true, 1>(tmA, tmB, p, tiles128, stream);
-    return use256 ? launch<256, false, 1>(tmA, tmB, p, tiles256, stream) : launch<128, false, 1>(tmA, tmB, p, tiles128, stream);
+    // epilogue variant: TMA store (16-bit outputs) / TMA reduce-add (fp32 residual) when the output is a plain
+    // matrix; the generic register path otherwise
+    int epi = 0;
+    const bool plain = p.gin == 0 && p.table == nullptr && p.out_lo == nullptr && (g_force_mode & 4) == 0;
+    if (plain && !p.tf32 && p.store == ST_16 && (p.ldo % 8) == 0) epi = 1;
+    if (plain && !p.tf32 && p.store == ST_SWIGLU16 && bn == 256 && (p.ldo % 8) == 0 && p.act == ACT_NONE) epi = 1;
+    if (plain && p.store == ST_RESID32 && p.act == ACT_NONE) epi = 2;
+    tmC = tmA;
+    if (epi == 1)
+        rc = make_tmap(&tmC, p.out, p.M, p.store == ST_SWIGLU16 ? p.N / 2 : p.N, p.ldo, 32, p.bf16 ? 1 : 0);
+    else if (epi == 2)
+        rc = make_tmap(&tmC, p.out, p.M, p.N, p.ldo, 32, 2);
+    if (rc != SB_OK) return rc;
+
+#define SB_GEMM_LAUNCH(BN_, TF_, CT_, TILES_)                                                             \
+    (epi == 1 ? launch<BN_, TF_, CT_, (TF_) ? 0 : 1>(tmA, tmB, tmC, p, TILES_, stream)                     \
+     : epi == 2 ? launch<BN_, TF_, CT_, 2>(tmA, tmB, tmC, p, TILES_, stream)                               \
+                : launch<BN_, TF_, CT_, 0>(tmA, tmB, tmC, p, TILES_, stream))
+    if (use_pair) return SB_GEMM_LAUNCH(256, false, 2, tiles_pair);
+    if (p.tf32) return use256 ? SB_GEMM_LAUNCH(256, true, 1, tiles256) : SB_GEMM_LAUNCH(128, true, 1, tiles128);
+    return use256 ? SB_GEMM_LAUNCH(256, false, 1, tiles256) : SB_GEMM_LAUNCH(128, false, 1, tiles128);
+#undef SB_GEMM_LAUNCH
 }
 
 }  // namespace sb

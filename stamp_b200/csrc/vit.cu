@@ -99,6 +99,12 @@ int stamp_vit_forward(const StampVitConfig* cfg, const StampVitWeights* w,
 
     for (int l = 0; l < cfg->depth; ++l) {
         const StampVitBlock& b = blocks[l];
+        // global_pool = 'token' (uni.py:26-31, virchow2.py:24-30 take x[:, 0]): the last block's outputs are only
+        // read at the class-token rows, so after its K / V projections everything runs on those B rows alone
+        // (row b*T of x and xn addressed with a row pitch of T*D; same arithmetic for the rows that are kept)
+        const bool cls_only = (l == cfg->depth - 1);
+        const int Mr = cls_only ? B : M;                                  // rows from the attention output on
+        const long long ldr = cls_only ? static_cast<long long>(T) * D : D;  // their pitch in x / xn
         rc = layernorm(x, D, b.ln1_w, b.ln1_b, xn, nullptr, D, M, D, cfg->ln_eps, 0, stream);
         if (rc != SB_OK) return rc;
         {
@@ -114,22 +120,25 @@ int stamp_vit_forward(const StampVitConfig* cfg, const StampVitWeights* w,
             a.row_stride = 3LL * D; a.batch_stride = 3LL * D * T;
             a.out = xn; a.out_f32 = 0; a.out_row_stride = D; a.out_batch_stride = static_cast<long long>(D) * T;
             a.B = B; a.S = T; a.H = cfg->heads;
+            a.q_rows = cls_only ? 1 : 0;
             a.scale_log2 = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
             rc = attention_fwd(a, hd, stream);
             if (rc != SB_OK) return rc;
         }
         {
             GemmParams p{};
-            p.M = M; p.N = D; p.K = D;
-            p.store = ST_RESID32; p.out = x; p.ldo = D; p.bias = b.proj_b; p.gamma = b.ls1;
-            rc = gemm_tn(xn, D, b.proj_w, D, p, stream);
+            p.M = Mr; p.N = D; p.K = D;
+            p.store = ST_RESID32; p.out = x; p.ldo = ldr; p.bias = b.proj_b; p.gamma = b.ls1;
+            rc = gemm_tn(xn, ldr, b.proj_w, D, p, stream);
             if (rc != SB_OK) return rc;
         }
-        rc = layernorm(x, D, b.ln2_w, b.ln2_b, xn, nullptr, D, M, D, cfg->ln_eps, 0, stream);
+        // (cls_only: the normalised class-token rows are written compactly, [B, D], over the head of xn -- the
+        //  attention output there has been consumed by the projection above)
+        rc = layernorm(x, ldr, b.ln2_w, b.ln2_b, xn, nullptr, D, Mr, D, cfg->ln_eps, 0, stream);
         if (rc != SB_OK) return rc;
         {
             GemmParams p{};
-            p.M = M; p.N = cfg->mlp_hidden; p.K = D;
+            p.M = Mr; p.N = cfg->mlp_hidden; p.K = D;
             p.act = (cfg->mlp_kind == 1) ? ACT_NONE : ACT_GELU;
             p.store = (cfg->mlp_kind == 1) ? ST_SWIGLU16 : ST_16;
             p.out = big; p.ldo = L.hid_out; p.bias = b.fc1_b;
@@ -138,8 +147,8 @@ int stamp_vit_forward(const StampVitConfig* cfg, const StampVitWeights* w,
         }
         {
             GemmParams p{};
-            p.M = M; p.N = D; p.K = static_cast<int>(L.hid_out);
-            p.store = ST_RESID32; p.out = x; p.ldo = D; p.bias = b.fc2_b; p.gamma = b.ls2;
+            p.M = Mr; p.N = D; p.K = static_cast<int>(L.hid_out);
+            p.store = ST_RESID32; p.out = x; p.ldo = ldr; p.bias = b.fc2_b; p.gamma = b.ls2;
             rc = gemm_tn(big, L.hid_out, b.fc2_w, L.hid_out, p, stream);
             if (rc != SB_OK) return rc;
         }
