@@ -116,20 +116,43 @@ def cpu_vit_tiles_per_s(sample_tiles: int, reps: int, warm: int) -> tuple[float,
     return sample_tiles * reps / dt, torch.get_num_threads(), dt
 
 
-def cpu_mil_slides_per_s(n_tiles: int, reps: int) -> float:
+REF_VIT_FILE = Path("/root/reference/src/stamp/modeling/models/vision_tranformer.py")
+
+
+def cpu_mil_slides_per_s(n_tiles: int, reps: int) -> tuple[float, str]:
+    """Whole-bag eval forward on the host cores: the reference's own module when its source is present (BASELINE.md
+    5.1; it is imported by file path, needs only torch / einops / beartype / jaxtyping), the oracle port otherwise
+    (the GPU box has no /root/reference)."""
     import torch
 
     from oracle import mil_oracle
 
     sd = mil_oracle.init_state_dict(dim_input=1024, dim_output=2, seed=0)
     bags, coords = mil_oracle.synthetic_bag(n_tiles, 1024, seed=0)
+    kind = "port"
+    fwd = lambda b, c: mil_oracle.forward(sd, b, c, None)
+    if REF_VIT_FILE.exists():
+        try:
+            import importlib.util
+
+            spec = importlib.util.spec_from_file_location("ref_vision_tranformer", REF_VIT_FILE)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules["ref_vision_tranformer"] = mod
+            spec.loader.exec_module(mod)
+            m = mod.VisionTransformer(dim_output=2, dim_input=1024, dim_model=512, n_layers=2, n_heads=8,
+                                      dim_feedforward=512, dropout=0.25, use_alibi=True).eval()
+            m.load_state_dict(sd)
+            fwd = lambda b, c: m(b, coords=c, mask=None)
+            kind = "reference"
+        except Exception:  # noqa: BLE001 - missing optional dependency of the reference file: fall back to the port
+            kind = "port"
     with torch.inference_mode():
-        mil_oracle.forward(sd, bags[:, :256], coords[:, :256], None)
+        fwd(bags[:, :256], coords[:, :256])
         t0 = time.perf_counter()
         for _ in range(reps):
-            mil_oracle.forward(sd, bags, coords, None)
+            fwd(bags, coords)
         dt = time.perf_counter() - t0
-    return reps / dt
+    return reps / dt, kind
 
 
 def run_reference(args) -> None:
@@ -285,10 +308,10 @@ def run_b200(args) -> None:
         bags_host, coords_host = bags.half().cpu().pin_memory(), coords.cpu().pin_memory()
         from stamp_b200.deploy import predict_bags
 
+        bags16 = bags.half()          # features as the .h5 feature files hold them
+
         def mil_step_device():
-            with torch.inference_mode():
-                for i in range(n_bags):
-                    mil(bags[i:i + 1], coords=coords[i:i + 1], mask=None)
+            return predict_bags(mil, ((bags16[i], coords[i]) for i in range(n_bags)), dev)
 
         def mil_step_e2e():
             return predict_bags(mil, ((bags_host[i], coords_host[i]) for i in range(n_bags)), dev)
@@ -310,8 +333,9 @@ def run_b200(args) -> None:
                    "value": res["value"], "e2e": res["e2e"], "unit": "slides/s",
                    "roofline_frac": (res["value"] / world) * MIL_FLOPS_PER_BAG / 1e12 / peak_tf,
                    "h2d_bytes_per_slide": n_tiles * (1024 * 2 + 2 * 4), "d2h_bytes_per_slide": 8,
-                   "e2e_note": "stamp_b200.deploy.predict_bags: fp16 features (as stored in the feature files) from pinned "
-                               "host memory, copies double-buffered on a side stream, probabilities read back"}
+                   "e2e_note": "stamp_b200.deploy.predict_bags (batch-1 whole-bag forwards issued round-robin on 3 CUDA "
+                               "streams): value = fp16 bags resident in HBM, e2e = fp16 bags (as stored in the feature "
+                               "files) from pinned host memory; probabilities read back in both"}
 
     # ---- MIL training step (BASELINE configs[3]: ALiBi Transformer-MIL, bf16, 4096 x 1024 bags, global
     #      batch 8 bags per GPU = 64 on the 8-GPU box): forward + backward + ONE all-reduce of the flat
@@ -375,37 +399,11 @@ def run_b200(args) -> None:
         del tb, tc, tb_host, tc_host, tmodel, opt
         torch.cuda.empty_cache()
 
-    # ---- BASELINE configs[2] per-GPU rate: Macenko stain normalisation + Virchow2 ViT-H/14 (slides shard one
-    #      per GPU exactly like configs[1], so the per-GPU rate is what scales) and configs[4]: one 50k-tile
-    #      slide through the MIL aggregator + its class-activation map (C backward passes), rank 0 only
-    extra_out = None
+    # ---- BASELINE configs[4]: one 50k-tile slide through the MIL aggregator + its class-activation map
+    #      (C backward passes), rank 0 only
+    extra_out = {}
     if rank == 0 and not args.skip_mil:
         from stamp_b200 import train as T
-        from stamp_b200.extractor import virchow2
-        from stamp_b200.macenko import macenko_normalize
-        from stamp_b200.vit import VIRCHOW2_ARCH
-
-        ext_h = virchow2(weights="random", max_batch=96)
-        model_h = ext_h.model.to(dev).eval()
-        n_h = 96 * 21
-        tiles_h = torch.randint(20, 235, (n_h, 224, 224, 3), dtype=torch.uint8, device=dev)
-        norm_h = torch.empty_like(tiles_h)
-
-        def virchow_step():
-            macenko_normalize(tiles_h, out=norm_h)      # one stain fit over the batch of tiles
-            return model_h(norm_h)
-
-        for _ in range(2):
-            virchow_step()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(2):
-            virchow_step()
-        e1.record()
-        torch.cuda.synchronize()
-        v_tps = 2 * n_h / (e0.elapsed_time(e1) * 1e-3)
-        del tiles_h, norm_h, model_h, ext_h
-        torch.cuda.empty_cache()
 
         n50 = 50_000
         hm = VisionTransformer(dim_output=2, dim_input=768, dim_model=512, n_layers=2, n_heads=8, dim_feedforward=512,
@@ -434,9 +432,6 @@ def run_b200(args) -> None:
         # reference math for S = 50 001: forward 2 layers x 8 heads x 4 S^2 hd, each Jacobian row a backward (2x)
         hm_flops = 2 * 8 * 4.0 * (n50 + 1) ** 2 * 64 * (1 + 1 + 2 * 2)
         extra_out = {
-            "virchow2_macenko": {"metric": "tiles/sec, Macenko + Virchow2 ViT-H/14 (BASELINE configs[2], per GPU)",
-                                 "value": v_tps, "unit": "tiles/s", "batch": 96,
-                                 "roofline_frac": v_tps * VIRCHOW2_ARCH.flops_per_tile() / 1e12 / peak_tf},
             "heatmap_50k": {"metric": "50k-tile slide: whole-bag MIL forward + grad-CAM over 2 classes (BASELINE configs[4])",
                             "ms_per_slide": hm_ms, "unit": "ms", "attention_roofline_frac": hm_flops / (hm_ms * 1e-3) / 1e12 / peak_tf},
         }
@@ -462,7 +457,9 @@ def run_b200(args) -> None:
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / n
 
-        mt = torch.randint(20, 235, (768, 224, 224, 3), dtype=torch.uint8, device=dev)
+        from bench_extra import synthetic_he_tiles
+
+        mt = synthetic_he_tiles(768, seed=3, device=dev)      # H&E-like tiles, not uniform noise
         mo_ = torch.empty_like(mt)
         ms = timed(lambda: macenko_normalize(mt, out=mo_))
         mac_gbs = 2 * mt.numel() / ms / 1e6
@@ -501,6 +498,25 @@ def run_b200(args) -> None:
         }
         del mt, mo_, px
 
+    # ---- BASELINE configs[2] and configs[3] as specified, every rank takes part (bench_extra.py)
+    cohort_out = crossval_out = None
+    if not args.skip_mil and not args.skip_configs:
+        from bench_extra import cohort_block, crossval_block
+
+        torch.cuda.empty_cache()
+        cohort_out = cohort_block(dev, rank, world, peak_tf, slides_per_gpu=args.cohort_slides_per_gpu)
+        torch.cuda.empty_cache()
+        crossval_out = crossval_block(dev, rank, world)
+        torch.cuda.empty_cache()
+
+    # ---- the reference's own GPU path (eager torch on this GPU) for the same three stages (rank 0, N = 1)
+    torch_gpu = None
+    if rank == 0 and world == 1 and not args.skip_mil and not args.skip_torch_baseline:
+        from bench_extra import torch_gpu_block
+
+        torch_gpu = torch_gpu_block(dev, {"vit_tiles_per_s": value, "mil_slides_per_s": mil_out["value"] if mil_out else None,
+                                          "mil_train_bags_per_s": train_out["value"] if train_out else None})
+
     # ---- CPU baseline (rank 0, single GPU runs only): oracle port on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
@@ -508,7 +524,7 @@ def run_b200(args) -> None:
         cpu = {"value": tps, "unit": "tiles/s", "cores": cores, "kind": "port",
                "sample": f"8 x 16 synthetic tiles ({dt:.1f} s), ViT-L/16 fp32 oracle port of the timm path"}
         if mil_out is not None:
-            cpu["mil_slides_per_s"] = cpu_mil_slides_per_s(4096, reps=3)
+            cpu["mil_slides_per_s"], cpu["mil_kind"] = cpu_mil_slides_per_s(4096, reps=3)
 
     if rank == 0:
         line = {
@@ -520,8 +536,9 @@ def run_b200(args) -> None:
                        "batch": args.batch, "l2": "inputs (1.5 GB/slide) larger than L2, no flush",
                        "sharding": f"slides[rank::{world}], no data-path collective"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "mil": mil_out, "mil_train": train_out, "other_configs": extra_out,
-            "hbm_kernels": hbm_out,
+            "cpu_baseline": cpu, "mil": mil_out, "mil_train": train_out,
+            "other_configs": {"virchow2_cohort": cohort_out, "crossval": crossval_out, **(extra_out or {})},
+            "torch_gpu_baseline": torch_gpu, "hbm_kernels": hbm_out,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -538,6 +555,9 @@ def main() -> None:
     ap.add_argument("--slide-tiles", type=int, default=SLIDE_TILES)
     ap.add_argument("--skip-mil", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="skip the configs[2] cohort and configs[3] crossval blocks")
+    ap.add_argument("--skip-torch-baseline", action="store_true")
+    ap.add_argument("--cohort-slides-per-gpu", type=int, default=32)   # 32 x 8 GPUs = the 256-slide cohort
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

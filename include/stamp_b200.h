@@ -177,7 +177,8 @@ int stamp_vit_forward(const StampVitConfig* cfg, const StampVitWeights* w,
  *   everything it calls (:15-295), as used by LitTileClassifier.predict_step/validation_step
  *   (src/stamp/modeling/models/__init__.py:288-313), deploy._predict (src/stamp/modeling/deploy.py:390-456)
  *   and heatmaps_ (src/stamp/heatmaps/__init__.py:392,419).
- * bags fp32 [B,N,F], coords fp32 [B,N,2], mask uint8 [B,N] (1 = masked tile) or NULL,
+ * bags [B,N,F] fp32 (bags_f16 = 0) or fp16 as the feature files store them (bags_f16 = 1, 16-byte aligned: no
+ * up-cast round trip), coords fp32 [B,N,2], mask uint8 [B,N] (1 = masked tile) or NULL,
  * logits fp32 [B,C].  mask == NULL takes the reference's mask=None branch (padding tiles attend and
  * are attended, ALiBi applies to the class token's (0,0) coordinate); a mask reproduces :359-379.
  * HOST structs holding DEVICE pointers.
@@ -215,7 +216,7 @@ typedef struct {
 size_t stamp_mil_workspace_bytes(const StampMilConfig* cfg, int B, int N);
 
 int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w,
-                      const StampMilLayer* layers /* [n_layers] */, const float* bags,
+                      const StampMilLayer* layers /* [n_layers] */, const void* bags, int bags_f16,
                       const float* coords, const uint8_t* mask, float* logits, int B, int N,
                       void* workspace, size_t workspace_bytes, void* stream);
 

@@ -126,11 +126,11 @@ def forward(sd: dict[str, Tensor], bags: Tensor, coords: Tensor, mask: Tensor | 
     x = _drop(x, dm.get(0), p_proj)
     d = x.shape[-1]
     x = torch.cat([sd["class_token"].expand(B, 1, d), x], dim=1)
-    coords = torch.cat([torch.zeros(B, 1, 2, dtype=coords.dtype), coords], dim=1)
+    coords = torch.cat([torch.zeros(B, 1, 2, dtype=coords.dtype, device=coords.device), coords], dim=1)
 
     attn_mask = alibi_mask = None
     if mask is not None:
-        m = torch.cat([torch.zeros(B, 1, dtype=torch.bool), mask], dim=1)
+        m = torch.cat([torch.zeros(B, 1, dtype=torch.bool, device=mask.device), mask], dim=1)
         attn_mask = m[:, :, None] & m[:, None, :]            # einsum("bq,bk->bqk") on bools
         attn_mask[:, 1:, 0] = True
         alibi_mask = torch.zeros_like(attn_mask)
@@ -165,7 +165,7 @@ def forward(sd: dict[str, Tensor], bags: Tensor, coords: Tensor, mask: Tensor | 
                 # Reference quirk kept on purpose (vision_tranformer.py:222-226): the [B,S,S] mask is
                 # expanded with .repeat(H,1,1) -> rows ordered (head, bag), but nn.MultiheadAttention
                 # reads its [B*H,S,S] mask as (bag, head): bag b / head h gets the mask of bag (b*H+h) % B.
-                idx = (torch.arange(B)[:, None] * n_heads + torch.arange(n_heads)[None, :]) % B
+                idx = (torch.arange(B, device=x.device)[:, None] * n_heads + torch.arange(n_heads, device=x.device)[None, :]) % B
                 logits = logits.masked_fill(attn_mask[idx], float("-inf"))
             o = (torch.softmax(logits, -1) @ v).permute(0, 2, 1, 3).reshape(B, S, d)
             att = F.linear(o, sd[p + "0.mhsa.out_proj.weight"], sd[p + "0.mhsa.out_proj.bias"])
@@ -182,7 +182,7 @@ def running_mean_update(sd: dict[str, Tensor], coords: Tensor) -> dict[str, Tens
     head of every layer: rm <- mean(rm + (dist - rm) / n); n += 1, dist = cdist over tokens incl. the
     class token at (0,0).  Returns an updated copy of the state dict."""
     B = coords.shape[0]
-    c = torch.cat([torch.zeros(B, 1, 2, dtype=coords.dtype), coords], dim=1)
+    c = torch.cat([torch.zeros(B, 1, 2, dtype=coords.dtype, device=coords.device), coords], dim=1)
     dist = torch.cdist(c, c)
     out = dict(sd)
     for k in sd:
@@ -197,7 +197,7 @@ def cross_entropy(logits: Tensor, targets: Tensor, class_weights: Tensor | None)
     """LitTileClassifier._step loss (src/stamp/modeling/models/__init__.py:254-258): soft one-hot
     targets, class weights, mean over the batch = mean_b(-sum_c w_c y_bc log p_bc)."""
     logp = torch.log_softmax(logits, dim=1)
-    w = class_weights if class_weights is not None else torch.ones(logits.shape[1], dtype=logits.dtype)
+    w = class_weights if class_weights is not None else torch.ones(logits.shape[1], dtype=logits.dtype, device=logits.device)
     return -(w[None, :] * targets * logp).sum(dim=1).mean()
 
 

@@ -145,8 +145,8 @@ def transform_u8(tiles_u8: Tensor, dtype=torch.float32, mean=IMAGENET_MEAN, std=
     """uint8 [B,H,W,3] -> normalised CHW float (ToTensor + Normalize; ImageNet constants for UNI / Virchow2,
     explicit ones for e.g. H-optimus, h_optimus_0.py:26-28)."""
     x = tiles_u8.permute(0, 3, 1, 2).to(dtype) / 255.0
-    mean = torch.tensor(mean, dtype=dtype).view(1, 3, 1, 1)
-    std = torch.tensor(std, dtype=dtype).view(1, 3, 1, 1)
+    mean = torch.tensor(mean, dtype=dtype, device=tiles_u8.device).view(1, 3, 1, 1)
+    std = torch.tensor(std, dtype=dtype, device=tiles_u8.device).view(1, 3, 1, 1)
     return (x - mean) / std
 
 
@@ -156,7 +156,10 @@ def block_forward(w: dict[str, Tensor], p: str, x: Tensor, cfg: VitConfig) -> Te
     h = F.layer_norm(x, (D,), w[p + "norm1.weight"], w[p + "norm1.bias"], cfg.ln_eps)
     qkv = F.linear(h, w[p + "attn.qkv.weight"], w[p + "attn.qkv.bias"])
     q, k, v = qkv.reshape(B, T, 3, H, hd).permute(2, 0, 3, 1, 4)
-    att = torch.softmax((q @ k.transpose(-2, -1)) * hd ** -0.5, dim=-1) @ v
+    if x.is_cuda:   # the GPU baseline of bench.py: timm's fused_attn path (F.scaled_dot_product_attention)
+        att = F.scaled_dot_product_attention(q, k, v)
+    else:
+        att = torch.softmax((q @ k.transpose(-2, -1)) * hd ** -0.5, dim=-1) @ v
     att = att.transpose(1, 2).reshape(B, T, D)
     att = F.linear(att, w[p + "attn.proj.weight"], w[p + "attn.proj.bias"])
     x = x + w[p + "ls1.gamma"] * att

@@ -407,9 +407,11 @@ int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream) {
         const int rc = attention_tc_fwd(p, head_dim, stream);
         if (rc != SB_ERR_UNSUPPORTED) return rc;
     }
-    // long unmasked bags (MIL aggregator, plain or ALiBi): tcgen05 two-pass kernel
+    // long unmasked bags (MIL aggregator, plain or ALiBi): tcgen05 kernels, newest generation first
     {
-        const int rc = attention_mil_tc_fwd(p, head_dim, stream);
+        int rc = attention_mil_v3_fwd(p, head_dim, stream);
+        if (rc != SB_ERR_UNSUPPORTED) return rc;
+        rc = attention_mil_tc_fwd(p, head_dim, stream);
         if (rc != SB_ERR_UNSUPPORTED) return rc;
     }
     const bool alibi = p.coords != nullptr;

@@ -26,6 +26,9 @@ struct AttnParams {
     const float* dscale;     // [B, 2] {2^-e, 2^e} from alibi_dist_scale
     const uint8_t* mask;     // [B, S] 1 = masked token, or null
     int mask_mode;           // 1: reference ALiBi masked branch (post-softmax), 2: -inf before softmax
+    // long-bag tcgen05 kernel, third generation (attention_mil_v3.cu): pre-computed 16-bit distance matrix
+    // [B, S, ld = S rounded up to 64] scaled by dscale[2b]; slope[h] is then applied in fp32 in the epilogue
+    const uint16_t* dist16;
     int q_rows;              // 0: every token is a query; n > 0: only the first n tokens' outputs are needed (rows up
                              // to the end of their query tile may still be written)
 };
@@ -39,6 +42,16 @@ void attention_tc_set_trace(long long* device_buf);  // debug: 5 x int64 per CTA
 // tcgen05 two-pass kernel for long unmasked bags, plain or ALiBi (attention_mil_tc.cu)
 int attention_mil_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 void attention_mil_tc_enable(int on);
+
+// third-generation long-bag kernel (attention_mil_v3.cu) and its distance-matrix producer
+int attention_mil_v3_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
+void attention_mil_v3_enable(int on);   // bit 0: use it, bit 1: rescale eagerly (tests)
+size_t mil_dist16_bytes(int B, int S);
+// coords_s [B, S, 2] -> scale [B][2] = {2^-e, 2^e} (largest distance of the bag in (8192, 16384]) and
+// dist16 [B, S, ld] = |x_q - x_k| * 2^-e as fp16 (bf16 != 0: bfloat16)
+size_t mil_dist16_scratch_bytes(int B);
+int mil_dist16(const float* coords_s, int B, int S, int bf16, float* scale, uint16_t* dist16, void* bbox_scratch,
+               cudaStream_t stream);
 
 int alibi_dist_scale(const float* coords, const float* slope, int B, int S, int H, float* dscale,
                      cudaStream_t stream);

@@ -1,20 +1,14 @@
-// tcgen05 attention for long feature bags (the MIL aggregator: S = 4097 ... 50001 tokens, head_dim 64).
+// tcgen05 attention for long feature bags, second generation: distances recomputed from the [S, 2] coordinates
+// inside the kernel.  The MIL aggregator itself runs the third generation (attention_mil_v3.cu, distance tiles
+// pre-computed and fed by TMA); this kernel remains (a) behind the stand-alone C-ABI primitive stamp_attention_fwd,
+// whose callers pass coordinates and no distance matrix, and (b) as an independent implementation the tests compare
+// the third generation against (stamp_b200_attention_tc_enable bit 5).
 //
 //   plain : O = softmax(Q K^T * scale) V
 //   ALiBi : O = softmax(Q K^T * scale) V  -  c_h * Dist V          (bias subtracted AFTER the softmax,
-//           src/stamp/modeling/models/vision_tranformer.py:58-72; Dist recomputed from the [S,2] coordinates)
+//           src/stamp/modeling/models/vision_tranformer.py:58-72)
 //
-// One CTA = 128 query rows of one (bag, head); key/value tiles of 128 rows stream through a 2-stage
-// TMA ring.  Two passes over the keys instead of an online softmax:
-//   pass 1 : S = Q K^T on tcgen05 (double-buffered in TMEM), each softmax thread (= query row = TMEM
-//            lane) takes the running max of its row straight from TMEM -- no exp, no shuffles;
-//   pass 2 : S again; P = exp2(s*scale - m) and D = c_h*|x_q - x_k| are written as fp16 in the
-//            K-major 128B-swizzled UMMA layout; O1 += P V and O2 += D V accumulate in TMEM for the
-//            whole pass (the max is final, so the accumulators never need rescaling); the row sum l
-//            accumulates in a register.  O = O1 / l - O2.
-//   warp 0 TMA, warp 1 MMA issue, warps 2-5 softmax.  TMEM: S0 | S1 | O1 | O2 = 384 of 512 columns.
-// Costs 4 tensor-core units (2 x QK^T, PV, DV) against the reference's 2, but only one exp and one
-// sqrt per (query, key) pair -- the MUFU pipe, not the tensor core, bounds this kernel.
+// One CTA = 128 query rows of one (bag, head), single pass over 64-key tiles (details above mil_attn_tc2_kernel).
 #include <math.h>
 
 #include "attention.cuh"
@@ -45,17 +39,6 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return r;
 }
 
-struct MtSmem {
-    static constexpr int off_q = 0;
-    static constexpr int off_k = TILE_BYTES;                 // 2 stages
-    static constexpr int off_v = off_k + 2 * TILE_BYTES;     // 2 stages
-    static constexpr int off_p = off_v + 2 * TILE_BYTES;     // 2 x 64-key blocks
-    static constexpr int off_d = off_p + 2 * TILE_BYTES;     // 2 x 64-key blocks
-    static constexpr int off_c = off_d + 2 * TILE_BYTES;     // key coordinates, 2 x 128 float2
-    static constexpr int off_x = off_c + 2 * 128 * 8;        // row-statistics exchange, 4 x 128 floats
-    static constexpr int off_bar = off_x + 4 * 128 * 4;
-    static constexpr int total = off_bar + 128 + 1024;
-};
 
 // Training variant (TRAIN): bf16 operands; Dhat = dist * inv_rm_h, O = O1 / l - beta_h * O2; besides O (bf16)
 // it stores what the backward needs -- Osm = O1 / l and Dhat V = O2 in fp32 and the row log-sum-exp (log2
@@ -74,649 +57,6 @@ __device__ __forceinline__ uint32_t pack_op(float a, float b) {
     if constexpr (TRAIN) return pack_bf16(a, b);
     else return pack_f16(a, b);
 }
-
-template <bool ALIBI, bool TRAIN>
-__global__ void __launch_bounds__(MT_THREADS, 1)
-mil_attn_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_v,
-                   const AttnParams p, int k_col0, const MilTrainOut t) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t* sQ = smem + MtSmem::off_q;
-    uint8_t* sK = smem + MtSmem::off_k;
-    uint8_t* sV = smem + MtSmem::off_v;
-    uint8_t* sP = smem + MtSmem::off_p;
-    uint8_t* sD = smem + MtSmem::off_d;
-    float2* sC = reinterpret_cast<float2*>(smem + MtSmem::off_c);
-    float* sX = reinterpret_cast<float*>(smem + MtSmem::off_x);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MtSmem::off_bar);
-    uint64_t* kfull = bars;        // [2] TMA -> MMA
-    uint64_t* kempty = bars + 2;   // [2] MMA -> TMA
-    uint64_t* sfull = bars + 4;    // [2] MMA -> softmax   (S tile in TMEM)
-    uint64_t* sempty = bars + 6;   // [2] softmax -> MMA
-    uint64_t* pfull = bars + 8;    // softmax -> MMA       (P/D tiles in smem)
-    uint64_t* pempty = bars + 9;   // MMA -> softmax
-    uint64_t* ofull = bars + 10;
-    uint64_t* qfull = bars + 11;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
-    const int q0 = blockIdx.y * 128;
-    const int S = p.S;
-    const int nkt = (S + 127) / 128;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tm_qk);
-        tma_prefetch_desc(&tm_v);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&kfull[i], 1);
-            mbar_init(&kempty[i], 1);
-            mbar_init(&sfull[i], 1);
-            mbar_init(&sempty[i], 8);
-        }
-        mbar_init(pfull, 8);
-        mbar_init(pempty, 1);
-        mbar_init(ofull, 1);
-        mbar_init(qfull, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t COL_O1 = 256, COL_O2 = 320;
-
-    if (warp == 0) {
-        // ------------------------------------ TMA producer ------------------------------------
-        if (lane == 0) {
-            mbar_expect_tx(qfull, TILE_BYTES);
-            tma_load_3d(sQ, &tm_qk, qfull, h * 64, q0, b);
-            int it = 0;
-            for (int pass = 0; pass < 2; ++pass)
-                for (int kt = 0; kt < nkt; ++kt, ++it) {
-                    const int s = it & 1;
-                    mbar_wait(&kempty[s], ((it >> 1) & 1) ^ 1);
-                    mbar_expect_tx(&kfull[s], pass == 0 ? TILE_BYTES : 2 * TILE_BYTES);
-                    tma_load_3d(sK + s * TILE_BYTES, &tm_qk, &kfull[s], k_col0 + h * 64, kt * 128, b);
-                    if (pass == 1) tma_load_3d(sV + s * TILE_BYTES, &tm_v, &kfull[s], h * 64, kt * 128, b);
-                }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------ MMA issuer --------------------------------------
-        if (lane == 0) {
-            const uint32_t idesc_s = umma_idesc_f16(128, 128, TRAIN, false, false);
-            const uint32_t idesc_o = umma_idesc_f16(128, 64, TRAIN, false, true);  // V: MN-major B
-            const uint64_t q_desc = umma_desc_k128(smem_u32(sQ));
-            mbar_wait(qfull, 0);
-            int is = 0;  // S tiles issued so far (both passes)
-            auto issue_s = [&]() {
-                const int s = is & 1;
-                const uint32_t ph = (is >> 1) & 1;
-                mbar_wait(&kfull[s], ph);
-                mbar_wait(&sempty[s], ph ^ 1);
-                tc_fence_after();
-                const uint64_t k_desc = umma_desc_k128(smem_u32(sK + s * TILE_BYTES));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16_ss(tmem + s * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
-                umma_commit(&sfull[s]);
-                ++is;
-            };
-            // pass 1: row maxima only -- the K stage is free as soon as S is computed
-            for (int kt = 0; kt < nkt; ++kt) {
-                const int s = is & 1;
-                issue_s();
-                umma_commit(&kempty[s]);
-            }
-            // pass 2: S(kt+1) is issued before waiting for the P/D tiles of kt
-            issue_s();
-            for (int kt = 0; kt < nkt; ++kt) {
-                if (kt + 1 < nkt) issue_s();
-                const int s = (nkt + kt) & 1;  // K/V stage of tile kt in pass 2
-                mbar_wait(pfull, kt & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint64_t v_desc = umma_desc_mn128(smem_u32(sV + s * TILE_BYTES + k * 2048), 0);
-                    const uint64_t p_desc = umma_desc_k128(smem_u32(sP + (k >> 2) * TILE_BYTES)) + 2 * (k & 3);
-                    umma_f16_ss(tmem + COL_O1, p_desc, v_desc, idesc_o, (kt | k) != 0);
-                    if constexpr (ALIBI) {
-                        const uint64_t d_desc = umma_desc_k128(smem_u32(sD + (k >> 2) * TILE_BYTES)) + 2 * (k & 3);
-                        umma_f16_ss(tmem + COL_O2, d_desc, v_desc, idesc_o, (kt | k) != 0);
-                    }
-                }
-                umma_commit(pempty);
-                umma_commit(&kempty[s]);
-            }
-            umma_commit(ofull);
-        }
-    } else {
-        // ---------- softmax: two threads per query row (= TMEM lane), one 64-key half each ----------
-        const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;          // keys [64*half, 64*half + 64) of every tile
-        const int r = quarter * 32 + lane;
-        const int st = threadIdx.x - 64;           // 0..255 among the softmax threads
-        const int row = q0 + r;
-        const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-        const float sl2 = p.scale_log2;
-        const uint32_t sC_addr = smem_u32(sC), sP_addr = smem_u32(sP), sD_addr = smem_u32(sD);
-        int ic = 0;  // S tiles consumed so far (both passes)
-
-        // ---- pass 1: exact row max (each thread over its half of the columns) ----
-        float mx = -INFINITY;
-        for (int kt = 0; kt < nkt; ++kt, ++ic) {
-            const int s = ic & 1;
-            mbar_wait(&sfull[s], (ic >> 1) & 1);
-            tc_fence_after();
-            const int kv_valid = min(128, S - kt * 128) - half * 64;   // valid keys in this thread's half
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32b_x32(t_lane + s * 128 + half * 64, v0);
-            tmem_ld_32x32b_x32(t_lane + s * 128 + half * 64 + 32, v1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (j < kv_valid) mx = fmaxf(mx, __uint_as_float(v0[j]));
-                if (32 + j < kv_valid) mx = fmaxf(mx, __uint_as_float(v1[j]));
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sempty[s]);
-        }
-        sX[half * 128 + r] = mx;
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");
-        mx = fmaxf(mx, sX[(half ^ 1) * 128 + r]);
-        const float ms = mx * sl2;
-
-        // ---- pass 2: P, D tiles -> smem, l in a register ----
-        float2 cq = make_float2(0.f, 0.f);
-        float slope = 0.f, descale = 1.f;
-        const float2* cb = nullptr;
-        if constexpr (ALIBI) {
-            cb = reinterpret_cast<const float2*>(p.coords) + static_cast<long long>(b) * S;
-            if (row < S) cq = __ldg(cb + row);
-            if constexpr (TRAIN) {
-                slope = __ldg(t.inv_rm + h);
-                descale = __ldg(t.beta + h);
-            } else {
-                slope = __ldg(p.slope + h) * __ldg(p.dscale + 2 * b);
-                descale = __ldg(p.dscale + 2 * b + 1);
-            }
-        }
-        float l = 0.f;
-        const uint32_t pb = sP_addr + half * TILE_BYTES + r * 128;
-        const uint32_t db = sD_addr + half * TILE_BYTES + r * 128;
-        for (int kt = 0; kt < nkt; ++kt, ++ic) {
-            const int s = ic & 1;
-            const int kv_valid = min(128, S - kt * 128) - half * 64;
-            if constexpr (ALIBI) {
-                if (st < 128) {
-                    const int key = kt * 128 + st;
-                    sts_f2(sC_addr + ((kt & 1) * 128 + st) * 8, (key < S) ? __ldg(cb + key) : make_float2(0.f, 0.f));
-                }
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");
-            }
-            mbar_wait(&sfull[s], (ic >> 1) & 1);
-            mbar_wait(pempty, (kt & 1) ^ 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(t_lane + s * 128 + half * 64 + c * 32, v);
-                tmem_ld_wait();
-                uint32_t pw[16], dw[16];
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float pv[2], dv[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int kl = c * 32 + j + e;              // key inside this thread's 64-key half
-                        const bool valid = kl < kv_valid;
-                        pv[e] = valid ? ex2_approx(fmaf(__uint_as_float(v[j + e]), sl2, -ms)) : 0.f;
-                        l += pv[e];
-                        if constexpr (ALIBI) {
-                            const float2 ck = lds_f2(sC_addr + ((kt & 1) * 128 + half * 64 + kl) * 8);
-                            const float dx = cq.x - ck.x, dy = cq.y - ck.y;
-                            dv[e] = valid ? sqrt_approx(fmaf(dx, dx, dy * dy)) * slope : 0.f;
-                        }
-                    }
-                    pw[j >> 1] = pack_op<TRAIN>(pv[0], pv[1]);
-                    if constexpr (ALIBI) dw[j >> 1] = pack_op<TRAIN>(dv[0], dv[1]);
-                }
-                // 32 keys = four 16-byte chunks of row r inside this thread's 64-key block
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int off = ((c * 4 + q) ^ (r & 7)) * 16;
-                    sts_u4(pb + off, make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]));
-                    if constexpr (ALIBI)
-                        sts_u4(db + off, make_uint4(dw[4 * q], dw[4 * q + 1], dw[4 * q + 2], dw[4 * q + 3]));
-                }
-            }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(pfull);
-                mbar_arrive(&sempty[s]);
-            }
-        }
-        sX[half * 128 + r] = l;
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");
-        l += sX[(half ^ 1) * 128 + r];
-
-        // ---- epilogue: O = O1 / l - descale * O2 ; this thread stores 32 of the row's 64 columns ----
-        mbar_wait(ofull, 0);
-        tc_fence_after();
-        const float inv = 1.0f / l;
-        const long long obase = b * p.out_batch_stride + static_cast<long long>(row) * p.out_row_stride + h * 64 + half * 32;
-        {
-            uint32_t o1[32], o2[32];
-            tmem_ld_32x32b_x32(t_lane + COL_O1 + half * 32, o1);
-            if constexpr (ALIBI) tmem_ld_32x32b_x32(t_lane + COL_O2 + half * 32, o2);
-            tmem_ld_wait();
-            if constexpr (TRAIN) {
-                if (row < S) {
-                    if (half == 0) t.lse2[(static_cast<long long>(b) * p.H + h) * S + row] = ms + log2f(l);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float sm[8], y[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            sm[e] = __uint_as_float(o1[j + e]) * inv;
-                            y[e] = sm[e];
-                            if constexpr (ALIBI) y[e] = fmaf(-descale, __uint_as_float(o2[j + e]), sm[e]);
-                        }
-                        *reinterpret_cast<uint4*>(t.out16 + obase + j) =
-                            make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
-                        *reinterpret_cast<float4*>(t.osm + obase + j) = make_float4(sm[0], sm[1], sm[2], sm[3]);
-                        *reinterpret_cast<float4*>(t.osm + obase + j + 4) = make_float4(sm[4], sm[5], sm[6], sm[7]);
-                        if constexpr (ALIBI) {
-                            *reinterpret_cast<float4*>(t.odv + obase + j) =
-                                make_float4(__uint_as_float(o2[j]), __uint_as_float(o2[j + 1]), __uint_as_float(o2[j + 2]), __uint_as_float(o2[j + 3]));
-                            *reinterpret_cast<float4*>(t.odv + obase + j + 4) =
-                                make_float4(__uint_as_float(o2[j + 4]), __uint_as_float(o2[j + 5]), __uint_as_float(o2[j + 6]), __uint_as_float(o2[j + 7]));
-                        }
-                    }
-                }
-            } else if (row < S) {
-                float y[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    y[j] = __uint_as_float(o1[j]) * inv;
-                    if constexpr (ALIBI) y[j] = fmaf(-descale, __uint_as_float(o2[j]), y[j]);
-                }
-                if (p.out_f32) {
-                    float* of = reinterpret_cast<float*>(p.out) + obase;
-                    float* ol = (p.out_lo != nullptr) ? p.out_lo + obase : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 hi = make_float4(round_tf32(y[j]), round_tf32(y[j + 1]), round_tf32(y[j + 2]), round_tf32(y[j + 3]));
-                        *reinterpret_cast<float4*>(of + j) = hi;
-                        if (ol != nullptr)
-                            *reinterpret_cast<float4*>(ol + j) = make_float4(round_tf32(y[j] - hi.x), round_tf32(y[j + 1] - hi.y),
-                                                                             round_tf32(y[j + 2] - hi.z), round_tf32(y[j + 3] - hi.w));
-                    }
-                } else {
-                    __half* oh = reinterpret_cast<__half*>(p.out) + obase;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8)
-                        *reinterpret_cast<uint4*>(oh + j) = make_uint4(pack_f16(y[j], y[j + 1]), pack_f16(y[j + 2], y[j + 3]),
-                                                                       pack_f16(y[j + 4], y[j + 5]), pack_f16(y[j + 6], y[j + 7]));
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem, 512);
-    }
-}
-
-
-int g_mil_tc_enabled = 1;
-int g_mil_two_pass = 0;        // 1: the two-pass kernel above (A/B timing, tests)
-int g_mil_eager_rescale = 0;   // 1: rescale whenever the maximum grows (tests of the rescale path)
-int g_mil_one_cta = 0;         // 1: single-pass kernel with 128-key tiles, one CTA per SM (A/B timing, tests)
-
-// ------------------------------------------------------------------------------------------------------
-// Single-pass variant (default).  TMEM is read at 64 B/clk per SM, so the two-pass kernel above spends
-// ~2 x 1000 cycles per 128 x 128 tile only on fetching S twice.  Here every S tile is read ONCE:
-//   * each softmax thread (query row r, 64-key half h of every tile) keeps its own reference maximum m_h and
-//     sum l_h, and its half of the keys accumulates into its own TMEM accumulator (O1a: keys 0-63 of every
-//     tile, O1b: keys 64-127), so the two threads of a row never have to agree on a maximum inside the loop;
-//   * the reference maximum is only raised when a tile's maximum exceeds it by more than 2^8 (lazy
-//     rescaling): P = exp2(s - m_ref) stays below 256 -- harmless for fp16 / bf16 operands with fp32
-//     accumulation -- and the rare rescale multiplies the thread's O1 row in TMEM (tcgen05.ld / tcgen05.st)
-//     after the previous tile's products have retired;
-//   * the epilogue merges the halves: O1 = (O1a w_a + O1b w_b) / (l_a w_a + l_b w_b), w = exp2(m_h - max m).
-// The ALiBi accumulator O2 += D V needs no scaling at all.  TMEM: S0 | S1 | O1a | O1b | O2 = 448 columns.
-__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
-
-template <bool ALIBI, bool TRAIN>
-__global__ void __launch_bounds__(MT_THREADS, 1)
-mil_attn_tc1_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_v,
-                    const AttnParams p, int k_col0, const MilTrainOut t, float rescale_margin) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t* sQ = smem + MtSmem::off_q;
-    uint8_t* sK = smem + MtSmem::off_k;
-    uint8_t* sV = smem + MtSmem::off_v;
-    uint8_t* sP = smem + MtSmem::off_p;
-    uint8_t* sD = smem + MtSmem::off_d;
-    float2* sC = reinterpret_cast<float2*>(smem + MtSmem::off_c);
-    float* sX = reinterpret_cast<float*>(smem + MtSmem::off_x);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MtSmem::off_bar);
-    uint64_t* kfull = bars;        // [2] TMA -> MMA
-    uint64_t* kempty = bars + 2;   // [2] MMA -> TMA
-    uint64_t* sfull = bars + 4;    // [2] MMA -> softmax   (S tile in TMEM)
-    uint64_t* sempty = bars + 6;   // [2] softmax -> MMA
-    uint64_t* pfull = bars + 8;    // softmax -> MMA       (P/D tiles in smem)
-    uint64_t* pempty = bars + 9;   // MMA -> softmax
-    uint64_t* ofull = bars + 10;
-    uint64_t* qfull = bars + 11;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
-    const int q0 = blockIdx.y * 128;
-    const int S = p.S;
-    const int nkt = (S + 127) / 128;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tm_qk);
-        tma_prefetch_desc(&tm_v);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&kfull[i], 1);
-            mbar_init(&kempty[i], 1);
-            mbar_init(&sfull[i], 1);
-            mbar_init(&sempty[i], 8);
-        }
-        mbar_init(pfull, 8);
-        mbar_init(pempty, 1);
-        mbar_init(ofull, 1);
-        mbar_init(qfull, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, 512);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t COL_O1A = 256, COL_O1B = 320, COL_O2 = 384;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(qfull, TILE_BYTES);
-            tma_load_3d(sQ, &tm_qk, qfull, h * 64, q0, b);
-            for (int kt = 0; kt < nkt; ++kt) {
-                const int s = kt & 1;
-                mbar_wait(&kempty[s], ((kt >> 1) & 1) ^ 1);
-                mbar_expect_tx(&kfull[s], 2 * TILE_BYTES);
-                tma_load_3d(sK + s * TILE_BYTES, &tm_qk, &kfull[s], k_col0 + h * 64, kt * 128, b);
-                tma_load_3d(sV + s * TILE_BYTES, &tm_v, &kfull[s], h * 64, kt * 128, b);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc_s = umma_idesc_f16(128, 128, TRAIN, false, false);
-            const uint32_t idesc_o = umma_idesc_f16(128, 64, TRAIN, false, true);  // V: MN-major B
-            const uint64_t q_desc = umma_desc_k128(smem_u32(sQ));
-            mbar_wait(qfull, 0);
-            auto issue_s = [&](int kt) {
-                const int s = kt & 1;
-                const uint32_t ph = (kt >> 1) & 1;
-                mbar_wait(&kfull[s], ph);
-                mbar_wait(&sempty[s], ph ^ 1);
-                tc_fence_after();
-                const uint64_t k_desc = umma_desc_k128(smem_u32(sK + s * TILE_BYTES));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16_ss(tmem + s * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
-                umma_commit(&sfull[s]);
-            };
-            issue_s(0);
-            for (int kt = 0; kt < nkt; ++kt) {
-                if (kt + 1 < nkt) issue_s(kt + 1);
-                const int s = kt & 1;
-                mbar_wait(pfull, kt & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint64_t v_desc = umma_desc_mn128(smem_u32(sV + s * TILE_BYTES + k * 2048), 0);
-                    const uint64_t p_desc = umma_desc_k128(smem_u32(sP + (k >> 2) * TILE_BYTES)) + 2 * (k & 3);
-                    // keys 0-63 of the tile accumulate into O1a, keys 64-127 into O1b (separate reference maxima)
-                    umma_f16_ss(tmem + (k < 4 ? COL_O1A : COL_O1B), p_desc, v_desc, idesc_o, (kt | (k & 3)) != 0);
-                    if constexpr (ALIBI) {
-                        const uint64_t d_desc = umma_desc_k128(smem_u32(sD + (k >> 2) * TILE_BYTES)) + 2 * (k & 3);
-                        umma_f16_ss(tmem + COL_O2, d_desc, v_desc, idesc_o, (kt | k) != 0);
-                    }
-                }
-                umma_commit(pempty);
-                umma_commit(&kempty[s]);
-            }
-            umma_commit(ofull);
-        }
-    } else {
-        const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;          // keys [64*half, 64*half + 64) of every tile
-        const int r = quarter * 32 + lane;
-        const int st = threadIdx.x - 64;
-        const int row = q0 + r;
-        const uint32_t t_lane = tmem + (static_cast<uint32_t>(quarter * 32) << 16);
-        const uint32_t t_o1 = t_lane + (half == 0 ? COL_O1A : COL_O1B);
-        const float sl2 = p.scale_log2;
-        const uint32_t sC_addr = smem_u32(sC), sP_addr = smem_u32(sP), sD_addr = smem_u32(sD);
-
-        float2 cq = make_float2(0.f, 0.f);
-        float slope = 0.f, descale = 1.f;
-        const float2* cb = nullptr;
-        if constexpr (ALIBI) {
-            cb = reinterpret_cast<const float2*>(p.coords) + static_cast<long long>(b) * S;
-            if (row < S) cq = __ldg(cb + row);
-            if constexpr (TRAIN) {
-                slope = __ldg(t.inv_rm + h);
-                descale = __ldg(t.beta + h);
-            } else {
-                slope = __ldg(p.slope + h) * __ldg(p.dscale + 2 * b);
-                descale = __ldg(p.dscale + 2 * b + 1);
-            }
-        }
-        float ms = -INFINITY;      // reference maximum of this thread's keys, already multiplied by scale*log2(e)
-        float l = 0.f;
-        const uint32_t pb = sP_addr + half * TILE_BYTES + r * 128;
-        const uint32_t db = sD_addr + half * TILE_BYTES + r * 128;
-        for (int kt = 0; kt < nkt; ++kt) {
-            const int s = kt & 1;
-            const int kv_valid = min(128, S - kt * 128) - half * 64;   // valid keys in this thread's half
-            if constexpr (ALIBI) {
-                if (st < 128) {
-                    const int key = kt * 128 + st;
-                    sts_f2(sC_addr + ((kt & 1) * 128 + st) * 8, (key < S) ? __ldg(cb + key) : make_float2(0.f, 0.f));
-                }
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");
-            }
-            mbar_wait(&sfull[s], (kt >> 1) & 1);
-            tc_fence_after();
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32b_x32(t_lane + s * 128 + half * 64, v0);
-            tmem_ld_32x32b_x32(t_lane + s * 128 + half * 64 + 32, v1);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sempty[s]);     // S is in registers: the stage is free for tile kt + 2
-            float mx = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (j < kv_valid) mx = fmaxf(mx, __uint_as_float(v0[j]));
-                if (32 + j < kv_valid) mx = fmaxf(mx, __uint_as_float(v1[j]));
-            }
-            mbar_wait(pempty, (kt & 1) ^ 1);            // previous tile's P V / D V retired: O1 and sP / sD are ours
-            tc_fence_after();
-            {
-                // raise the reference maximum (lazily: only past the margin) and rescale l and this thread's O1 row.
-                // tcgen05.ld / .st are warp-collective (.sync.aligned): the branch is taken by the whole warp as
-                // soon as one row needs it, rows that do not rescale by 1.
-                const bool need = mx * sl2 > ms + rescale_margin;
-                const float ms_new = need ? mx * sl2 : ms;
-                const bool resc = need && kt > 0 && ms != -INFINITY;
-                const float f = resc ? ex2_approx(ms - ms_new) : 1.0f;
-                if (__any_sync(0xffffffffu, resc)) {
-                    l *= f;
-#pragma unroll 1
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t o[32];
-                        tmem_ld_32x32b_x32(t_o1 + c * 32, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
-                        tmem_st_32x32b_x32(t_o1 + c * 32, o);
-                    }
-                    tmem_st_wait();
-                }
-                ms = ms_new;
-            }
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t pw[16], dw[16];
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float pv[2], dv[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int kl = c * 32 + j + e;
-                        const bool valid = kl < kv_valid;
-                        const float sv = __uint_as_float(c == 0 ? v0[j + e] : v1[j + e]);
-                        pv[e] = valid ? ex2_approx(fmaf(sv, sl2, -ms)) : 0.f;
-                        l += pv[e];
-                        if constexpr (ALIBI) {
-                            const float2 ck = lds_f2(sC_addr + ((kt & 1) * 128 + half * 64 + kl) * 8);
-                            const float dx = cq.x - ck.x, dy = cq.y - ck.y;
-                            dv[e] = valid ? sqrt_approx(fmaf(dx, dx, dy * dy)) * slope : 0.f;
-                        }
-                    }
-                    pw[j >> 1] = pack_op<TRAIN>(pv[0], pv[1]);
-                    if constexpr (ALIBI) dw[j >> 1] = pack_op<TRAIN>(dv[0], dv[1]);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int off = ((c * 4 + q) ^ (r & 7)) * 16;
-                    sts_u4(pb + off, make_uint4(pw[4 * q], pw[4 * q + 1], pw[4 * q + 2], pw[4 * q + 3]));
-                    if constexpr (ALIBI)
-                        sts_u4(db + off, make_uint4(dw[4 * q], dw[4 * q + 1], dw[4 * q + 2], dw[4 * q + 3]));
-                }
-            }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(pfull);
-        }
-        // ---- merge the two halves of every row: weights w_h = exp2(m_h - max(m_a, m_b)) ----
-        sX[half * 128 + r] = ms;
-        sX[256 + half * 128 + r] = l;
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");
-        const float ms_o = sX[(half ^ 1) * 128 + r], l_o = sX[256 + (half ^ 1) * 128 + r];
-        const float M = fmaxf(ms, ms_o);
-        const float w_me = (ms == -INFINITY) ? 0.f : ex2_approx(ms - M);
-        const float w_ot = (ms_o == -INFINITY) ? 0.f : ex2_approx(ms_o - M);
-        const float w_a = half == 0 ? w_me : w_ot, w_b = half == 0 ? w_ot : w_me;
-        const float lt = l * w_me + l_o * w_ot;
-        const bool has_b = S > 64;                 // the O1b accumulator is never written for bags of <= 64 keys
-
-        mbar_wait(ofull, 0);
-        tc_fence_after();
-        const float inv = 1.0f / lt;
-        const long long obase = b * p.out_batch_stride + static_cast<long long>(row) * p.out_row_stride + h * 64 + half * 32;
-        {
-            uint32_t oa[32], ob[32], o2[32];
-            tmem_ld_32x32b_x32(t_lane + COL_O1A + half * 32, oa);
-            tmem_ld_32x32b_x32(t_lane + COL_O1B + half * 32, ob);
-            if constexpr (ALIBI) tmem_ld_32x32b_x32(t_lane + COL_O2 + half * 32, o2);
-            tmem_ld_wait();
-            if (row < S) {
-                float sm[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float v = __uint_as_float(oa[j]) * w_a;
-                    if (has_b) v = fmaf(__uint_as_float(ob[j]), w_b, v);
-                    sm[j] = v * inv;
-                }
-                if constexpr (TRAIN) {
-                    if (half == 0) t.lse2[(static_cast<long long>(b) * p.H + h) * S + row] = M + log2f(lt);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float y[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            y[e] = sm[j + e];
-                            if constexpr (ALIBI) y[e] = fmaf(-descale, __uint_as_float(o2[j + e]), sm[j + e]);
-                        }
-                        *reinterpret_cast<uint4*>(t.out16 + obase + j) =
-                            make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
-                        *reinterpret_cast<float4*>(t.osm + obase + j) = make_float4(sm[j], sm[j + 1], sm[j + 2], sm[j + 3]);
-                        *reinterpret_cast<float4*>(t.osm + obase + j + 4) = make_float4(sm[j + 4], sm[j + 5], sm[j + 6], sm[j + 7]);
-                        if constexpr (ALIBI) {
-                            *reinterpret_cast<float4*>(t.odv + obase + j) =
-                                make_float4(__uint_as_float(o2[j]), __uint_as_float(o2[j + 1]), __uint_as_float(o2[j + 2]), __uint_as_float(o2[j + 3]));
-                            *reinterpret_cast<float4*>(t.odv + obase + j + 4) =
-                                make_float4(__uint_as_float(o2[j + 4]), __uint_as_float(o2[j + 5]), __uint_as_float(o2[j + 6]), __uint_as_float(o2[j + 7]));
-                        }
-                    }
-                } else {
-                    float y[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        y[j] = sm[j];
-                        if constexpr (ALIBI) y[j] = fmaf(-descale, __uint_as_float(o2[j]), y[j]);
-                    }
-                    if (p.out_f32) {
-                        float* of = reinterpret_cast<float*>(p.out) + obase;
-                        float* ol = (p.out_lo != nullptr) ? p.out_lo + obase : nullptr;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 hi = make_float4(round_tf32(y[j]), round_tf32(y[j + 1]), round_tf32(y[j + 2]), round_tf32(y[j + 3]));
-                            *reinterpret_cast<float4*>(of + j) = hi;
-                            if (ol != nullptr)
-                                *reinterpret_cast<float4*>(ol + j) = make_float4(round_tf32(y[j] - hi.x), round_tf32(y[j + 1] - hi.y),
-                                                                                 round_tf32(y[j + 2] - hi.z), round_tf32(y[j + 3] - hi.w));
-                        }
-                    } else {
-                        __half* oh = reinterpret_cast<__half*>(p.out) + obase;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            *reinterpret_cast<uint4*>(oh + j) = make_uint4(pack_f16(y[j], y[j + 1]), pack_f16(y[j + 2], y[j + 3]),
-                                                                           pack_f16(y[j + 4], y[j + 5]), pack_f16(y[j + 6], y[j + 7]));
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem, 512);
-    }
-}
-
 
 // ------------------------------------------------------------------------------------------------------
 // Two-CTAs-per-SM variant of the single-pass kernel (default).  One CTA alone leaves every pipe below 55 %:
@@ -1047,6 +387,9 @@ mil_attn_tc2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 }
 
 
+int g_mil_tc_enabled = 1;
+int g_mil_eager_rescale = 0;   // tests: rescale whenever a row maximum grows
+
 template <bool ALIBI, bool TRAIN>
 int launch_mil(const CUtensorMap& tm_qk, const CUtensorMap& tm_v, const CUtensorMap& tm_k64, const CUtensorMap& tm_v64,
                const AttnParams& p, int k_col0, const MilTrainOut& t, cudaStream_t stream) {
@@ -1054,20 +397,12 @@ int launch_mil(const CUtensorMap& tm_qk, const CUtensorMap& tm_v, const CUtensor
     if (!configured) {
         if (cudaFuncSetAttribute(mil_attn_tc2_kernel<ALIBI, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Mt2Smem::total) != cudaSuccess)
             return SB_ERR_CUDA;
-        if (cudaFuncSetAttribute(mil_attn_tc_kernel<ALIBI, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MtSmem::total) != cudaSuccess ||
-            cudaFuncSetAttribute(mil_attn_tc1_kernel<ALIBI, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, MtSmem::total) != cudaSuccess)
-            return SB_ERR_CUDA;
         configured = true;
     }
     dim3 grid(p.B * p.H, (p.S + 127) / 128);
     ProfScope prof(PROF_ATTN, 4.0 * p.B * p.H * static_cast<double>(p.S) * p.S * 64, stream);
     const float margin = g_mil_eager_rescale ? 0.f : 8.f;
-    if (g_mil_two_pass)
-        mil_attn_tc_kernel<ALIBI, TRAIN><<<grid, MT_THREADS, MtSmem::total, stream>>>(tm_qk, tm_v, p, k_col0, t);
-    else if (g_mil_one_cta)
-        mil_attn_tc1_kernel<ALIBI, TRAIN><<<grid, MT_THREADS, MtSmem::total, stream>>>(tm_qk, tm_v, p, k_col0, t, margin);
-    else
-        mil_attn_tc2_kernel<ALIBI, TRAIN><<<grid, MT_THREADS, Mt2Smem::total, stream>>>(tm_qk, tm_k64, tm_v64, p, k_col0, t, margin);
+    mil_attn_tc2_kernel<ALIBI, TRAIN><<<grid, MT_THREADS, Mt2Smem::total, stream>>>(tm_qk, tm_k64, tm_v64, p, k_col0, t, margin);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
@@ -1076,9 +411,7 @@ int launch_mil(const CUtensorMap& tm_qk, const CUtensorMap& tm_v, const CUtensor
 
 void attention_mil_tc_enable(int on) {
     g_mil_tc_enabled = on & 1;
-    g_mil_two_pass = (on >> 2) & 1;
     g_mil_eager_rescale = (on >> 3) & 1;
-    g_mil_one_cta = (on >> 4) & 1;
 }
 
 // SB_ERR_UNSUPPORTED: outside this kernel's envelope (masked calls, head_dim != 64, short

@@ -671,7 +671,9 @@ int attention_train_fwd(const AttnTrainParams& p, int head_dim, cudaStream_t str
         (p.coords != nullptr && p.odv == nullptr))
         return SB_ERR_BAD_ARG;
     {
-        const int rc = attention_mil_tc_train_fwd(p, head_dim, stream);
+        int rc = attention_mil_v3_train_fwd(p, head_dim, stream);
+        if (rc != SB_ERR_UNSUPPORTED) return rc;
+        rc = attention_mil_tc_train_fwd(p, head_dim, stream);
         if (rc != SB_ERR_UNSUPPORTED) return rc;
     }
     if (head_dim == 64) return fwd_hd<64>(p, stream);

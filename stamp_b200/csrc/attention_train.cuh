@@ -23,6 +23,10 @@ struct AttnTrainParams {
     const float2* coords;   // [B, S] token coordinates, or null: plain softmax attention
     const float* beta;      // [H] bias_scale_h
     const float* inv_rm;    // [H] 1 / running_mean_h
+    // optional (long bags, attention_mil_v3.cu): bf16 distance matrix [B, S, ld] scaled by dist_scale[2b] = 2^-e,
+    // dist_scale[2b+1] = 2^e; null -> distances are recomputed from coords inside the kernels
+    const uint16_t* dist16;
+    const float* dist_scale;
     // backward only
     const float* dout32;    // fp32 dO, strides as out (input)
     uint16_t* dout;         // bf16 copy of dO written by the backward's first pass (scratch, strides as out)
@@ -37,6 +41,8 @@ int attention_train_fwd(const AttnTrainParams& p, int head_dim, cudaStream_t str
 // tcgen05 two-pass forward for long bags (attention_mil_tc.cu, training variant of the inference kernel);
 // SB_ERR_UNSUPPORTED = outside its envelope (head_dim != 64, <= 256 tokens)
 int attention_mil_tc_train_fwd(const AttnTrainParams& p, int head_dim, cudaStream_t stream);
+// third-generation forward (TMA-fed distance tiles, P through tensor memory); needs p.dist16 for ALiBi
+int attention_mil_v3_train_fwd(const AttnTrainParams& p, int head_dim, cudaStream_t stream);
 // tcgen05 dK/dV + dQ kernels (attention_train_tc.cu); need p.dout / p.delta filled; SB_ERR_UNSUPPORTED = not applicable
 int attention_train_tc_bwd(const AttnTrainParams& p, int head_dim, cudaStream_t stream);
 void attention_train_tc_enable(int on);   // tests: 0 forces the mma.sync kernels

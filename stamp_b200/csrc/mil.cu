@@ -113,7 +113,8 @@ inline int grid_for(long long total, int block) {
 
 struct Layout {
     long long M, S;
-    size_t off_x, off_xn, off_qkv, off_att, off_h, off_bags, off_coords, off_mask, off_dscale, total;
+    size_t off_x, off_xn, off_qkv, off_att, off_h, off_bags, off_coords, off_mask, off_dscale, off_dist, off_bbox, total;
+    bool v3;   // long unmasked ALiBi bags: third-generation attention kernel fed by a pre-computed distance matrix
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -139,6 +140,10 @@ bool make_layout(const StampMilConfig* c, int B, int N, Layout* L) {
     L->off_coords = o; o = align_up(o + M * 8, 256);
     L->off_mask = o;   o = align_up(o + M, 256);
     L->off_dscale = o; o = align_up(o + static_cast<size_t>(B) * 8 * (c->n_layers > 0 ? c->n_layers : 1), 256);
+    // (sized for the unmasked call; a masked call of the same shape simply leaves it unused)
+    L->v3 = c->use_alibi && hd == 64 && L->S > 256 && L->S <= 65535 && B <= 65535;
+    L->off_dist = o;   if (L->v3) o = align_up(o + mil_dist16_bytes(B, static_cast<int>(L->S)), 1024);
+    L->off_bbox = o;   if (L->v3) o = align_up(o + mil_dist16_scratch_bytes(B), 256);
     L->total = o;
     return true;
 }
@@ -174,7 +179,7 @@ size_t stamp_mil_workspace_bytes(const StampMilConfig* cfg, int B, int N) {
 }
 
 int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w, const StampMilLayer* layers,
-                      const float* bags, const float* coords, const uint8_t* mask, float* logits,
+                      const void* bags, int bags_f16, const float* coords, const uint8_t* mask, float* logits,
                       int B, int N, void* workspace, size_t workspace_bytes, void* stream_) {
     using namespace sb;
     Layout L;
@@ -203,9 +208,13 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w, const
     // project_features: Linear + GELU into rows 1.. of every bag; class token into row 0
     if (N > 0) {
         const long long n = static_cast<long long>(B) * N * F;
-        {
+        if (bags_f16) {
+            // features as the .h5 files store them (fp16): they are the GEMM operand as they are
+            if ((reinterpret_cast<uintptr_t>(bags) & 15) != 0) return SB_ERR_BAD_ARG;
+            bags16 = const_cast<__half*>(static_cast<const __half*>(bags));
+        } else {
             ProfScope prof(PROF_ROWOP, n * 6.0, stream);
-            cast_f32_f16_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(bags, bags16, n / 8, n);
+            cast_f32_f16_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(static_cast<const float*>(bags), bags16, n / 8, n);
             count_launch();
         }
         GemmParams p{};
@@ -225,7 +234,14 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w, const
 
     const float scale_log2 = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
 
-    if (alibi)  // power-of-two range scale of the distance operand, per layer (slopes differ) and bag
+    const bool v3 = L.v3 && mask == nullptr;
+    uint16_t* dist16 = reinterpret_cast<uint16_t*>(ws + L.off_dist);
+    if (v3) {
+        // token distances once per call (they do not depend on the layer or the head): fp16 [B, S, S], scaled per
+        // bag by a power of two; read by the attention kernel of every layer through TMA
+        rc = mil_dist16(reinterpret_cast<const float*>(coords_s), B, S, 0, dscale, dist16, ws + L.off_bbox, stream);
+        if (rc != SB_OK) return rc;
+    } else if (alibi)  // power-of-two range scale of the distance operand, per layer (slopes differ) and bag
         for (int l = 0; l < cfg->n_layers; ++l) {
             rc = alibi_dist_scale(reinterpret_cast<const float*>(coords_s), layers[l].slope, B, S, H,
                                   dscale + static_cast<size_t>(l) * B * 2, stream);
@@ -262,7 +278,8 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w, const
             a.out_f32 = 1; a.out_lo = reinterpret_cast<float*>(att) + d;
             a.out_row_stride = 2LL * d; a.out_batch_stride = 2LL * d * S;
             a.coords = reinterpret_cast<const float*>(coords_s); a.slope = y.slope;
-            a.dscale = dscale + static_cast<size_t>(l) * B * 2;
+            a.dscale = v3 ? dscale : dscale + static_cast<size_t>(l) * B * 2;
+            if (v3) a.dist16 = dist16;
             if (mask != nullptr) { a.mask = mask_s; a.mask_mode = 1; }
             rc = attention_fwd(a, hd, stream);
             if (rc != SB_OK) return rc;

@@ -19,6 +19,7 @@
 // Dropout masks are never stored: keep(i) = hash(seed, site, i) >= p * 2^32, regenerated in backward.
 #include <math.h>
 
+#include "attention.cuh"
 #include "attention_train.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
@@ -662,7 +663,9 @@ struct TrainLayout {
     size_t l_w_qkv, l_w_qkvT, l_w_fc, l_w_fcT, l_w_ff1, l_w_ff1T, l_w_ff2, l_w_ff2T;
     size_t off_w_proj, off_w_projT;
     size_t off_y32 /* [M, max(d,ff)] f32 scratch */, off_dx /* [M,d] f32 */, off_g16a /* [M, max(d,ff)] bf16 */,
-        off_g16b /* [M,d] bf16 */, off_g16c /* [M,3d] bf16 */, off_delta, off_dsum, off_wscratch, wscratch_bytes, total;
+        off_g16b /* [M,d] bf16 */, off_g16c /* [M,3d] bf16 */, off_delta, off_dsum, off_wscratch, wscratch_bytes,
+        off_dist /* bf16 [B,S,ld] token distances (long ALiBi bags) */, off_dist_scale /* [B][2] */, total;
+    bool dist;
 };
 
 inline size_t au(size_t v) { return (v + 255) / 256 * 256; }
@@ -720,6 +723,11 @@ bool make_train_layout(const StampMilConfig* c, int B, int N, TrainLayout* L) {
         L->wscratch_bytes = w;
     }
     L->off_wscratch = o; o = au(o + L->wscratch_bytes);
+    // distance matrix of the third-generation attention forward (attention_mil_v3.cu), shared by all layers
+    L->dist = c->use_alibi && hd == 64 && L->S > 256 && L->S <= 65535 && B <= 65535;
+    L->off_dist_scale = o; o = au(o + static_cast<size_t>(B) * 8 + 16 + mil_dist16_scratch_bytes(B));
+    L->off_dist = (o + 1023) / 1024 * 1024; o = L->off_dist;
+    if (L->dist) o = au(o + mil_dist16_bytes(B, static_cast<int>(L->S)));
     L->total = o;
     return true;
 }
@@ -827,6 +835,9 @@ int stamp_mil_train_forward(const StampMilConfig* cfg, const StampMilTrainTop* t
     }
     SB_TRY(fill_rows(x, d, B, S, 0, top->class_token, d, nullptr, 0, 1, d, stream));
     SB_TRY(mil_prepare(coords, nullptr, coords_s, nullptr, B, N, stream));
+    uint16_t* dist16 = reinterpret_cast<uint16_t*>(ws + L.off_dist);
+    float* dist_scale = reinterpret_cast<float*>(ws + L.off_dist_scale);
+    if (L.dist) SB_TRY(mil_dist16(reinterpret_cast<const float*>(coords_s), B, S, 1, dist_scale, dist16, dist_scale + ((2 * static_cast<size_t>(B) + 3) & ~static_cast<size_t>(3)), stream));
 
     const float scale = 1.0f / sqrtf(static_cast<float>(hd));
     for (int l = 0; l < cfg->n_layers; ++l) {
@@ -855,6 +866,7 @@ int stamp_mil_train_forward(const StampMilConfig* cfg, const StampMilTrainTop* t
         a.B = B; a.S = S; a.H = H; a.scale = scale; a.scale_log2 = scale * 1.4426950408889634f;
         if (cfg->use_alibi) {   // else: plain softmax attention (nn.MultiheadAttention, vision_tranformer.py:191,218-228)
             a.coords = coords_s; a.beta = y.bias_scale; a.inv_rm = step->inv_rm + static_cast<size_t>(l) * H;
+            if (L.dist) { a.dist16 = dist16; a.dist_scale = dist_scale; }
         }
         SB_TRY(attention_train_fwd(a, hd, stream));
         // x_mid = x_in + fc(att)

@@ -51,7 +51,7 @@ def _bind() -> C.CDLL:
         lib.stamp_mil_workspace_bytes.argtypes = [C.POINTER(StampMilConfig), C.c_int, C.c_int]
         lib.stamp_mil_forward.restype = C.c_int
         lib.stamp_mil_forward.argtypes = [C.POINTER(StampMilConfig), C.POINTER(StampMilWeights),
-                                          C.POINTER(StampMilLayer), C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(StampMilLayer), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         lib._mil_bound = True
     return lib
@@ -139,19 +139,24 @@ class VisionTransformer(nn.Module):
         self._cfg = dict(dim_input=dim_input, dim_model=dim_model, n_layers=n_layers, n_heads=n_heads,
                          dim_ff=dim_feedforward, dim_output=dim_output, use_alibi=int(use_alibi))
         self._packed = None       # (key, tensors kept alive, cfg, weights, layers)
-        self._workspace: Tensor | None = None
+        self._key_tensors = None
+        self._workspace: dict[int, Tensor] | None = None   # per CUDA stream: concurrent bags do not share scratch
         self._train_ctx: Tensor | None = None   # checkpoints between a training forward and its backward
         self._train_gen = 0
         self._train_state = None
 
     # ---- weight packing: reference layout -> GEMM operands (cached until a parameter changes) ----
     def _pack_key(self):
-        ps = list(self.parameters()) + list(self.buffers())
-        return (_weights_epoch, str(ps[0].device), tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
+        # (this runs on every inference call: one attribute read per tensor; the storage pointers of the first and
+        #  the last one catch .to(device) / load_state_dict(assign=True), which replace all of them together)
+        ps = self._key_tensors
+        if ps is None:
+            ps = self._key_tensors = list(self.parameters()) + list(self.buffers())
+        return (_weights_epoch, ps[0].device, tuple(p._version for p in ps), ps[0].data_ptr(), ps[-1].data_ptr())
 
     # ctypes structures with raw device pointers, workspaces and the checkpoint buffer are per-process caches:
     # copy.deepcopy / torch.save(model) / spawn pickling carry the parameters only
-    _TRANSIENT = {"_packed": None, "_workspace": None, "_train_ctx": None, "_train_state": None}
+    _TRANSIENT = {"_packed": None, "_workspace": None, "_train_ctx": None, "_train_state": None, "_key_tensors": None}
 
     def __getstate__(self):
         state = dict(super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__)
@@ -239,7 +244,8 @@ class VisionTransformer(nn.Module):
         _, _, cfg, w, layers = self._pack()
         B, N, _ = bags.shape
         dev = bags.device
-        bags32 = bags.detach().float().contiguous()
+        # fp16 features (the dtype the .h5 feature files hold) are consumed as they are; anything else as fp32
+        bags_in = bags.detach().contiguous() if bags.dtype == torch.float16 else bags.detach().float().contiguous()
         coords32 = coords.detach().float().contiguous()
         mask8 = mask.to(torch.uint8).contiguous() if mask is not None else None
         logits = torch.empty((B, self._cfg["dim_output"]), dtype=torch.float32, device=dev)
@@ -247,11 +253,16 @@ class VisionTransformer(nn.Module):
         if need == 0:
             raise ValueError("unsupported MIL configuration for the sm_100a kernels "
                              "(dims must be multiples of 8, head dim 32 or 64)")
-        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
-        code = lib.stamp_mil_forward(C.byref(cfg), C.byref(w), layers, bags32.data_ptr(), coords32.data_ptr(),
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if self._workspace is None or len(self._workspace) > 8:   # (callers that keep creating streams: start over)
+            self._workspace = {}
+        ws = self._workspace.get(stream)
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = self._workspace[stream] = torch.empty(need, dtype=torch.uint8, device=dev)
+        code = lib.stamp_mil_forward(C.byref(cfg), C.byref(w), layers, bags_in.data_ptr(),
+                                     int(bags_in.dtype == torch.float16), coords32.data_ptr(),
                                      None if mask8 is None else mask8.data_ptr(), logits.data_ptr(), B, N,
-                                     self._workspace.data_ptr(), self._workspace.numel(),
-                                     torch.cuda.current_stream().cuda_stream)
+                                     ws.data_ptr(), ws.numel(), stream)
         _lib.check(code, "stamp_mil_forward")
-        return logits.to(bags.dtype)
+        # fp16 bags: logits stay in the model's fp32 (predict_step casts the bags to the parameter dtype instead)
+        return logits if bags.dtype == torch.float16 else logits.to(bags.dtype)

@@ -79,10 +79,11 @@ def test_mil_default_size_matches_oracle(cuda_device, n_tiles, batch, use_alibi)
 
 @pytest.mark.parametrize("use_alibi", [True, False])
 def test_long_bag_attention_kernel_variants_agree(cuda_device, use_alibi):
-    """Long bags run on the single-pass tcgen05 kernel with lazy accumulator rescaling, two CTAs per SM (mode 1).
-    Bit 3 (modes 9, 25) forces a rescale whenever a row maximum grows (exercises the TMEM read-modify-write
-    path), bit 4 (17, 25) selects the one-CTA-per-SM variant with 128-key tiles, mode 5 the older two-pass
-    kernel; all must match the oracle.  Logit scales are blown up so that maxima do grow along the bag."""
+    """Long bags run on the third-generation tcgen05 kernel (attention_mil_v3.cu: distance tiles by TMA, P through
+    tensor memory, lazy accumulator rescaling; mode 1).  Bit 3 (modes 9, 41) forces a rescale whenever a row
+    maximum grows (exercises the TMEM read-modify-write path), bit 5 (33, 41) selects the second generation, an
+    independent implementation that recomputes the distances in the kernel; all must match the oracle.  Logit scales
+    are blown up so that maxima do grow along the bag."""
     from oracle import mil_oracle
     from stamp_b200 import _lib
 
@@ -101,7 +102,7 @@ def test_long_bag_attention_kernel_variants_agree(cuda_device, use_alibi):
     lib = _lib.load()
     outs = {}
     try:
-        for mode in (1, 9, 17, 25, 5):
+        for mode in (1, 9, 33, 41):
             lib.stamp_b200_attention_tc_enable(mode)
             with torch.inference_mode():
                 outs[mode] = model(bags.to(cuda_device), coords=coords.to(cuda_device), mask=None).cpu()
@@ -112,7 +113,7 @@ def test_long_bag_attention_kernel_variants_agree(cuda_device, use_alibi):
         print(f"alibi={use_alibi} mode={mode}: max per-bag relative error {err:.2e}")
         # fp16 q / k with 6x larger logits: the softmax side is noisier than in the 1e-3 default-size tests
         assert err < (1e-3 if use_alibi else 4e-3), (mode, err)
-    for mode in (9, 17, 25, 5):       # the kernels agree with each other far below that
+    for mode in (9, 33, 41):       # the kernels agree with each other far below that
         assert _rel_per_bag(outs[mode], outs[1]) < 3e-4, mode
 
 
