@@ -39,6 +39,9 @@ int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 int attention_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 void attention_tc_enable(int on);
 void attention_tc_set_trace(long long* device_buf);  // debug: 5 x int64 per CTA (phase cycle counts)
+// persistent streaming kernel for ViT tiles (attention_vit_stream.cu), tried before attention_tc_fwd
+int attention_vit_stream_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
+void attention_vit_stream_enable(int on);   // bit 0: use it, bit 1: rescale eagerly (tests)
 // tcgen05 two-pass kernel for long unmasked bags, plain or ALiBi (attention_mil_tc.cu)
 int attention_mil_tc_fwd(const AttnParams& p, int head_dim, cudaStream_t stream);
 void attention_mil_tc_enable(int on);

@@ -44,6 +44,8 @@ void stamp_b200_debug_attention_trace(long long* device_buf) {
 void stamp_b200_attention_tc_enable(int on) {
     sb::attention_tc_enable(on);
     sb::attention_mil_tc_enable(on);        // bit 0 on/off, bit 2 two-pass kernel, bit 3 eager rescale (tests)
+    // bit 6: skip the persistent streaming ViT kernel (the one-shot kernel of attention_tc.cu runs instead)
+    sb::attention_vit_stream_enable(((on & 1) && !(on & 64) ? 1 : 0) | ((on & 8) ? 2 : 0));
     // bit 5: skip the third-generation long-bag kernel (tests compare the generations); bit 3 applies to it too
     sb::attention_mil_v3_enable(((on & 1) && !(on & 32) ? 1 : 0) | ((on & 8) ? 2 : 0));
     sb::attention_train_tc_enable(on & 1);

@@ -290,7 +290,8 @@ def test_attention_mask_mode2(cuda_device):
     assert _rel(out.float(), ref) < 2e-3
 
 
-@pytest.mark.parametrize("B,S,H", [(2, 16, 2), (3, 100, 3), (2, 128, 2), (2, 129, 2), (5, 197, 16), (2, 256, 4), (1, 7, 1)])
+@pytest.mark.parametrize("B,S,H", [(2, 16, 2), (3, 100, 3), (2, 128, 2), (2, 129, 2), (5, 197, 16), (2, 256, 4), (1, 7, 1),
+                                   (40, 197, 16), (3, 64, 2), (2, 65, 1), (300, 50, 4)])
 def test_attention_tcgen05_vs_general(cuda_device, B, S, H):
     """Short unmasked head_dim-64 sequences take the tcgen05 kernel; same result as the general one."""
     from stamp_b200 import _lib, ops
@@ -298,15 +299,19 @@ def test_attention_tcgen05_vs_general(cuda_device, B, S, H):
     g = torch.Generator(device="cpu").manual_seed(S * 3 + H)
     qkv = torch.randn(B, S, 3 * H * 64, generator=g).to(cuda_device, torch.float16)
     ref = _attn_ref(qkv, H)
-    out_tc = ops.attention(qkv, H)          # default: tcgen05 kernel, two CTAs per SM
+    out_tc = ops.attention(qkv, H)          # default: persistent streaming tcgen05 kernel
     try:
+        _lib.load().stamp_b200_attention_tc_enable(9)
+        out_eager = ops.attention(qkv, H)   # same, accumulator rescaled whenever a row maximum grows
+        _lib.load().stamp_b200_attention_tc_enable(65)
+        out_one = ops.attention(qkv, H)     # one-shot tcgen05 kernel (first round), all keys in one pass
         _lib.load().stamp_b200_attention_tc_enable(0)
         out_gen = ops.attention(qkv, H)     # general (legacy tensor path) kernel
     finally:
         _lib.load().stamp_b200_attention_tc_enable(1)
-    assert torch.isfinite(out_tc).all()
-    assert _rel(out_tc.float(), ref) < 2e-3
-    assert _rel(out_gen.float(), ref) < 2e-3
+    for o in (out_tc, out_eager, out_one, out_gen):
+        assert torch.isfinite(o).all()
+        assert _rel(o.float(), ref) < 2e-3
 
 
 @pytest.mark.parametrize("S", [257, 1000, 4097])
