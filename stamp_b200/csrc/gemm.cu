@@ -37,14 +37,17 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per epilogue warp: one 32 x 32 fp32 block
 
-template <int BN, int CTAS>
+template <int BN, int CTAS, int EPI = 0>
 struct Cfg {
     static constexpr int B_ROWS = BN / CTAS;  // rows of the B tile this CTA loads
     static constexpr int A_BYTES = BM * BK_BYTES;
     static constexpr int B_BYTES = B_ROWS * BK_BYTES;
-    static constexpr int STAGES = (A_BYTES + B_BYTES == 48 * 1024) ? 4 : 6;
+    // TMA epilogues double-buffer their staging tile (a store must have READ its tile before the tile is rewritten;
+    // with one buffer that wait sat on the critical path of every chunk pair), paid for with one pipeline stage
+    static constexpr int EPI_BUFS = (EPI != 0) ? 2 : 1;
+    static constexpr int STAGES = ((A_BYTES + B_BYTES == 48 * 1024) ? 4 : 6) - (EPI != 0 ? 1 : 0);
     static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES;
+    static constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES * EPI_BUFS;
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
     static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + EPI_BYTES + BAR_BYTES + 1024;
 };
@@ -133,6 +136,7 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 // the staging tile may be overwritten once the previous bulk operations have READ it
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 
 // ---- epilogue for 4 consecutive columns [n, n+4) of output row `orow` (input row m) ------------
@@ -265,7 +269,7 @@ template <int BN, bool TF32, int CTAS, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-    using C = Cfg<BN, CTAS>;
+    using C = Cfg<BN, CTAS, EPI>;
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle needs 1024-byte aligned tiles (identical offset in both CTAs of a pair)
     uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -390,12 +394,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int quarter = warp & 3;      // TMEM lane quarter this warp may access
         const int chalf = ew >> 2;         // which half of the BN columns
         constexpr int COLS_PER_WARP = BN / 2;
-        const uint32_t stg = smem_u32(sEpi) + ew * EPI_STAGE_BYTES;  // shared-space byte address
+        const uint32_t stg = smem_u32(sEpi) + ew * EPI_STAGE_BYTES * C::EPI_BUFS;  // shared-space byte address
         const int seg = lane & 7;          // 16-byte column segment this lane owns when reading back
         const int rsub = lane >> 3;        // row (mod 4) this lane owns when reading back
         const uint32_t tempty_leader = (CTAS == 2) ? map_to_cta(smem_u32(&tempty_bar[0]), 0) : 0u;
         int acc = 0;
         uint32_t acc_phase = 0;
+        [[maybe_unused]] uint32_t epi_seq = 0;   // bulk operations issued by this warp so far (staging-tile parity)
         for (int t = first_tile; t < num_tiles; t += tile_step) {
             const int m_blk = t / num_n, n_blk = t % num_n;
             mbar_wait(&tfull_bar[acc], acc_phase);
@@ -412,23 +417,37 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
             if constexpr (EPI != 0) {
                 // ---- one thread per accumulator row; the output leaves through a TMA store / reduce-add ----
-                const uint32_t srow = stg + lane * 128;    // this lane's 128-byte row of the staging tile
+                // Two staging tiles per warp, used alternately: before a tile is rewritten only the bulk operation
+                // issued BEFORE the most recent one has to have read its source (wait_group.read 1).
                 const int sw = lane & 7;                   // 128B swizzle: 16-byte chunk index ^ (row & 7)
                 const bool swiglu = (EPI == 1) && p.store == ST_SWIGLU16;
-#pragma unroll 1
-                for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+                // chunks of 32 columns this warp owns inside the matrix (warp-uniform)
+                const int n_first = n_blk * BN + chalf * COLS_PER_WARP;
+                const int nch = (p.N <= n_first) ? 0 : min(COLS_PER_WARP / 32, (p.N - n_first + 31) / 32);
+                // The accumulator chunk c+1 is fetched from tensor memory WHILE chunk c goes through the activation
+                // (tcgen05.ld is asynchronous until tcgen05.wait::ld; under a running mainloop a 4 KB load takes far
+                // longer than its 256 cycles of port time -- ncu: two thirds of the epilogue warps' samples sat in that
+                // scoreboard), and the TMEM stage is handed back as soon as the LAST chunk is in registers.
+                auto chunk = [&](int c, uint32_t (&r)[32], uint32_t (&rn)[32]) {
                     const int col = chalf * COLS_PER_WARP + c * 32;
                     const int n0 = n_blk * BN + col;
-                    if (n0 >= p.N) break;  // warp-uniform
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(t_row + col, r);
+                    tmem_ld_wait();
+                    if (c + 1 < nch) {
+                        tmem_ld_32x32b_x32(t_row + col + 32, rn);
+                    } else {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if constexpr (CTAS == 2) mbar_arrive_cluster(tempty_leader + acc * 8);
+                            else mbar_arrive(&tempty_bar[acc]);
+                        }
+                    }
                     // the bias of the 32 columns is the same for every lane: uniform (broadcast) loads
                     float4 b4[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         b4[j] = (p.bias != nullptr && n0 + 4 * j < p.N) ? ldg4(p.bias + n0 + 4 * j)
                                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-                    tmem_ld_wait();
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -449,8 +468,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (swiglu) {
                             // column pairs (x1, x2) -> one output: 16 outputs = 32 bytes of the row per chunk;
                             // the four chunks of this warp fill one 64-output (128-byte) row
+                            const uint32_t sbuf = stg + (epi_seq & 1) * EPI_STAGE_BYTES;
+                            const uint32_t srow = sbuf + lane * 128;
                             if (c == 0) {
-                                if (lane == 0) bulk_wait_read0();
+                                if (lane == 0) bulk_wait_read1();
                                 __syncwarp();
                             }
                             uint32_t w[8];
@@ -459,19 +480,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 w[j] = pack_16(silu(v[4 * j]) * v[4 * j + 1], silu(v[4 * j + 2]) * v[4 * j + 3], bf);
                             sts_v4(srow + (((2 * c) ^ sw) * 16), make_uint4(w[0], w[1], w[2], w[3]));
                             sts_v4(srow + (((2 * c + 1) ^ sw) * 16), make_uint4(w[4], w[5], w[6], w[7]));
-                            const bool last = (c == COLS_PER_WARP / 32 - 1) || (n0 + 32 >= p.N);
+                            const bool last = (c + 1 == nch);
                             if (last) {
                                 fence_proxy_async();
                                 __syncwarp();
                                 if (lane == 0) {
-                                    tma_store_2d(&tmC, stg, (n_blk * BN + chalf * COLS_PER_WARP) >> 1, m_base);
+                                    tma_store_2d(&tmC, sbuf, (n_blk * BN + chalf * COLS_PER_WARP) >> 1, m_base);
                                     bulk_commit();
                                 }
+                                ++epi_seq;
                             }
                         } else {
                             // 32 outputs = 64 bytes: two chunks fill one 64-column (128-byte) staging row
+                            const uint32_t sbuf = stg + (epi_seq & 1) * EPI_STAGE_BYTES;
+                            const uint32_t srow = sbuf + lane * 128;
                             if ((c & 1) == 0) {
-                                if (lane == 0) bulk_wait_read0();
+                                if (lane == 0) bulk_wait_read1();
                                 __syncwarp();
                             }
                             uint32_t w[16];
@@ -481,13 +505,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int j = 0; j < 4; ++j)
                                 sts_v4(srow + ((((c & 1) * 4 + j) ^ sw) * 16),
                                        make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
-                            if ((c & 1) == 1 || n0 + 32 >= p.N) {
+                            if ((c & 1) == 1 || c + 1 == nch) {
                                 fence_proxy_async();
                                 __syncwarp();
                                 if (lane == 0) {
-                                    tma_store_2d(&tmC, stg, n0 - (c & 1) * 32, m_base);
+                                    tma_store_2d(&tmC, sbuf, n0 - (c & 1) * 32, m_base);
                                     bulk_commit();
                                 }
+                                ++epi_seq;
                             }
                         }
                     } else {
@@ -499,7 +524,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 v[4 * j] *= g4.x; v[4 * j + 1] *= g4.y; v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
                             }
                         }
-                        if (lane == 0) bulk_wait_read0();
+                        const uint32_t sbuf = stg + (epi_seq & 1) * EPI_STAGE_BYTES;
+                        const uint32_t srow = sbuf + lane * 128;
+                        if (lane == 0) bulk_wait_read1();
                         __syncwarp();
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
@@ -508,9 +535,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_reduce_add_2d(&tmC, stg, n0, m_base);
+                            tma_reduce_add_2d(&tmC, sbuf, n0, m_base);
                             bulk_commit();
                         }
+                        ++epi_seq;
+                    }
+                };
+                uint32_t ra[32], rb[32];
+                if (nch > 0) {
+                    tmem_ld_32x32b_x32(t_row + chalf * COLS_PER_WARP, ra);
+#pragma unroll 1
+                    for (int c = 0; c < nch; c += 2) {
+                        chunk(c, ra, rb);
+                        if (c + 1 < nch) chunk(c + 1, rb, ra);
+                    }
+                } else {   // tile column range entirely outside the matrix: only hand the stage back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (CTAS == 2) mbar_arrive_cluster(tempty_leader + acc * 8);
+                        else mbar_arrive(&tempty_bar[acc]);
                     }
                 }
             } else {
@@ -650,11 +694,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
             }
             }  // EPI == 0
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if constexpr (CTAS == 2) mbar_arrive_cluster(tempty_leader + acc * 8);
-                else mbar_arrive(&tempty_bar[acc]);
+            if constexpr (EPI == 0) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CTAS == 2) mbar_arrive_cluster(tempty_leader + acc * 8);
+                    else mbar_arrive(&tempty_bar[acc]);
+                }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -737,7 +783,7 @@ int g_force_mode = 0;  // bits 0-1: 0 auto, 1 never use the 2-CTA kernel, 2 alwa
 template <int BN, bool TF32, int CTAS, int EPI>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int tiles,
            cudaStream_t stream) {
-    using C = Cfg<BN, CTAS>;
+    using C = Cfg<BN, CTAS, EPI>;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(gemm_tn_kernel<BN, TF32, CTAS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
