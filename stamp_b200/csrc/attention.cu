@@ -404,7 +404,9 @@ int attention_fwd(const AttnParams& p, int head_dim, cudaStream_t stream) {
         return SB_ERR_BAD_ARG;
     // short unmasked sequences (ViT tiles): tcgen05 kernel; anything else: the general kernel below
     {
-        int rc = (p.S <= 256) ? attention_vit_stream_fwd(p, head_dim, stream) : SB_ERR_UNSUPPORTED;
+        // (head dimension 64 beyond 256 tokens is a feature bag: the long-bag kernels below; head dimension 80 is a
+        //  ViT-H tile encoder with 261 ... 265 tokens)
+        int rc = (p.S <= 256 || head_dim == 80) ? attention_vit_stream_fwd(p, head_dim, stream) : SB_ERR_UNSUPPORTED;
         if (rc != SB_ERR_UNSUPPORTED) return rc;
         rc = attention_tc_fwd(p, head_dim, stream);
         if (rc != SB_ERR_UNSUPPORTED) return rc;

@@ -32,30 +32,49 @@ namespace sb {
 namespace {
 
 constexpr int VS_THREADS = 192;
-constexpr int QB_BYTES = 128 * 128;    // 128 query rows x 64 halfs
-constexpr int KT_BYTES = 64 * 128;     // 64 keys x 64 halfs
-constexpr int VS_STAGES = 4;
+constexpr int SUB_Q = 128 * 128;       // one 64-column sub-tile of a query block: 128 rows x 64 halfs
+constexpr int SUB_K = 64 * 128;        // one 64-column sub-tile of a key / value tile: 64 keys x 64 halfs
 // Fetching the next tile's scores during this tile's exponentials (two 64-register tiles in flight) was measured
 // SLOWER on B200 (6.76 k vs 7.35 k tiles/s end to end: 168 registers with spills); kept behind this switch.
 constexpr bool VS_PREFETCH = false;
 
-struct VsSmem {
-    static constexpr int off_q = 0;                               // 2 Q blocks
-    static constexpr int off_kv = 2 * QB_BYTES;                   // VS_STAGES x (K tile | V tile)
-    static constexpr int off_bar = off_kv + VS_STAGES * 2 * KT_BYTES;
+// Head dimension 64 (ViT-L/16, UNI2-h, H-optimus): everything double buffered.  Head dimension 80 (ViT-H/14: Virchow2)
+// is handled as TWO 64-column sub-tiles per operand, the second one loaded as a full 64-column TMA box of which only
+// the first 16 columns belong to the head (the rest is never multiplied for Q / K; for V it lands in accumulator
+// columns 80..127 that are never read): the contraction is 5 steps of 16 instead of 4, the P V product one N = 128
+// MMA over both sub-tiles (MN-major operand of two 64-column blocks).  Shared memory doubles, so Q and the output
+// accumulator are single-buffered there and the K / V ring has two stages -- still two CTAs per SM.
+template <int HD>
+struct VsCfg {
+    static constexpr int NSUB = (HD + 63) / 64;
+    static constexpr int KSTEPS = HD / 16;              // of the Q K^T contraction
+    static constexpr int OCOLS = NSUB * 64;             // TMEM columns of one output accumulator
+    static constexpr int QBUFS = (NSUB == 1) ? 2 : 1;
+    static constexpr int OBUFS = (NSUB == 1) ? 2 : 1;
+    static constexpr int STAGES = (NSUB == 1) ? 4 : 2;
+    static constexpr int QB_BYTES = NSUB * SUB_Q;
+    static constexpr int KT_BYTES = NSUB * SUB_K;       // K tile (and V tile)
+    static constexpr int off_q = 0;
+    static constexpr int off_kv = QBUFS * QB_BYTES;     // STAGES x (K tile | V tile)
+    static constexpr int off_bar = off_kv + STAGES * 2 * KT_BYTES;
     static constexpr int total = off_bar + 256 + 1024;
+    static_assert(HD % 16 == 0 && HD <= 128, "head dimension: multiple of 16, at most 128");
+    static_assert(128 + OBUFS * OCOLS <= 256, "TMEM: S0 | S1 | accumulators within 256 columns");
 };
 
+template <int HD>
 __global__ void __launch_bounds__(VS_THREADS, 2)
 vit_attn_stream_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
                        __half* __restrict__ out, long long out_row_stride, long long out_batch_stride,
                        int S, int H, int D, int n_units, int nqb, float scale_log2, float rescale_margin) {
+    using C = VsCfg<HD>;
+    constexpr int VS_STAGES = C::STAGES, QB_BYTES = C::QB_BYTES, KT_BYTES = C::KT_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t* sQ = smem + VsSmem::off_q;
-    uint8_t* sKV = smem + VsSmem::off_kv;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + VsSmem::off_bar);
+    uint8_t* sQ = smem + C::off_q;
+    uint8_t* sKV = smem + C::off_kv;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::off_bar);
     uint64_t* full = bars;                       // [VS_STAGES] TMA -> MMA   (K, V tile)
     uint64_t* empty = bars + VS_STAGES;          // [VS_STAGES] MMA -> TMA
     uint64_t* qfull = bars + 2 * VS_STAGES;      // [2] TMA -> MMA   (Q block of a unit)
@@ -101,7 +120,12 @@ vit_attn_stream_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    constexpr uint32_t COL_O = 128;    // S0 at column 0, S1 at 64, Oa at 128, Ob at 192
+    constexpr uint32_t COL_O = 128;    // S0 at column 0, S1 at 64, accumulator(s) from 128
+    auto qbuf = [&](int i) { return (C::QBUFS == 2) ? (i & 1) : 0; };
+    auto obuf = [&](int i) { return (C::OBUFS == 2) ? (i & 1) : 0; };
+    // completion count a waiter of unit i's buffer has to see: with one buffer every unit uses it
+    auto qpar = [&](int i) { return (C::QBUFS == 2) ? ((i >> 1) & 1) : (i & 1); };
+    auto opar = [&](int i) { return (C::OBUFS == 2) ? ((i >> 1) & 1) : (i & 1); };
 
     // unit index -> (image b, head h, query block): the query blocks of one (b, h) are adjacent units, so the second
     // read of its K / V tiles hits L2
@@ -118,38 +142,46 @@ vit_attn_stream_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             for (int i = 0; i < my_units; ++i) {
                 int b, h, q0;
                 unit_of(i, b, h, q0);
-                mbar_wait(&qempty[i & 1], ((i >> 1) & 1) ^ 1);
-                mbar_expect_tx(&qfull[i & 1], QB_BYTES);
-                tma_load_3d(sQ + (i & 1) * QB_BYTES, &tm_q, &qfull[i & 1], h * 64, q0, b);
+                mbar_wait(&qempty[qbuf(i)], qpar(i) ^ 1);
+                mbar_expect_tx(&qfull[qbuf(i)], QB_BYTES);
+#pragma unroll
+                for (int sub = 0; sub < C::NSUB; ++sub)
+                    tma_load_3d(sQ + qbuf(i) * QB_BYTES + sub * SUB_Q, &tm_q, &qfull[qbuf(i)], h * HD + sub * 64, q0, b);
                 for (int kt = 0; kt < nkt; ++kt, ++g) {
                     const int st = g % VS_STAGES;
                     uint8_t* dst = sKV + st * 2 * KT_BYTES;
                     mbar_wait(&empty[st], ((g / VS_STAGES) & 1) ^ 1);
                     mbar_expect_tx(&full[st], 2 * KT_BYTES);
-                    tma_load_3d(dst, &tm_kv, &full[st], D + h * 64, kt * 64, b);                 // K tile
-                    tma_load_3d(dst + KT_BYTES, &tm_kv, &full[st], 2 * D + h * 64, kt * 64, b);  // V tile
+#pragma unroll
+                    for (int sub = 0; sub < C::NSUB; ++sub) {
+                        tma_load_3d(dst + sub * SUB_K, &tm_kv, &full[st], D + h * HD + sub * 64, kt * 64, b);                 // K
+                        tma_load_3d(dst + KT_BYTES + sub * SUB_K, &tm_kv, &full[st], 2 * D + h * HD + sub * 64, kt * 64, b);  // V
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------ MMA issuer --------------------------------------
         if (lane == 0) {
-            const uint32_t idesc_o = umma_idesc_f16(128, 64, false, false, true);   // V: MN-major B operand
+            const uint32_t idesc_o = umma_idesc_f16(128, C::OCOLS, false, false, true);   // V: MN-major B operand
             const int total = my_units * nkt;
             auto issue_s = [&](int g) {
                 const int i = g / nkt, kt = g - i * nkt;
                 const int st = g % VS_STAGES;
-                if (kt == 0) mbar_wait(&qfull[i & 1], (i >> 1) & 1);
+                if (kt == 0) mbar_wait(&qfull[qbuf(i)], qpar(i));
                 mbar_wait(&full[st], (g / VS_STAGES) & 1);
                 tc_fence_after();
                 const int ncols = (kt == nkt - 1) ? last_cols : 64;
                 const uint32_t idesc_s = umma_idesc_f16(128, ncols, false, false, false);
-                const uint64_t q_desc = umma_desc_k128(smem_u32(sQ + (i & 1) * QB_BYTES));
-                const uint64_t k_desc = umma_desc_k128(smem_u32(sKV + st * 2 * KT_BYTES));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16_ss(tmem + (g & 1) * 64, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+                for (int k = 0; k < C::KSTEPS; ++k) {
+                    // 16 head dimensions per step; steps 4.. come from the second 64-column sub-tile
+                    const uint64_t q_desc = umma_desc_k128(smem_u32(sQ + qbuf(i) * QB_BYTES + (k >> 2) * SUB_Q)) + 2 * (k & 3);
+                    const uint64_t k_desc = umma_desc_k128(smem_u32(sKV + st * 2 * KT_BYTES + (k >> 2) * SUB_K)) + 2 * (k & 3);
+                    umma_f16_ss(tmem + (g & 1) * 64, q_desc, k_desc, idesc_s, k != 0);
+                }
                 umma_commit(&sfull[g & 1]);
-                if (kt == nkt - 1) umma_commit(&qempty[i & 1]);      // the unit's Q block is free once its S tiles exist
+                if (kt == nkt - 1) umma_commit(&qempty[qbuf(i)]);    // the unit's Q block is free once its S tiles exist
             };
             if (total > 0) issue_s(0);
             for (int g = 0; g < total; ++g) {
@@ -157,17 +189,18 @@ vit_attn_stream_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                 const int i = g / nkt, kt = g - i * nkt;
                 const int st = g % VS_STAGES;
                 mbar_wait(&pfull[g & 1], (g >> 1) & 1);
-                if (kt == 0) mbar_wait(&oempty[i & 1], ((i >> 1) & 1) ^ 1);   // accumulator of unit i-2 copied out
+                if (kt == 0) mbar_wait(&oempty[obuf(i)], opar(i) ^ 1);   // the accumulator's previous unit has been copied out
                 tc_fence_after();
                 const int ksteps = (kt == nkt - 1) ? last_cols / 16 : 4;
                 for (int k = 0; k < ksteps; ++k) {
                     // 16 keys per step: 16 rows x 128 B of the V tile as an MN-major operand; P: 8 TMEM columns
-                    const uint64_t v_desc = umma_desc_mn128(smem_u32(sKV + st * 2 * KT_BYTES + KT_BYTES + k * 2048), 0);
-                    umma_f16_ts(tmem + COL_O + (i & 1) * 64, tmem + (g & 1) * 64 + k * 8, v_desc, idesc_o, (kt | k) != 0);
+                    // (N spans the 64-column sub-tiles of the V tile: leading byte offset = one sub-tile)
+                    const uint64_t v_desc = umma_desc_mn128(smem_u32(sKV + st * 2 * KT_BYTES + KT_BYTES + k * 2048), SUB_K);
+                    umma_f16_ts(tmem + COL_O + obuf(i) * C::OCOLS, tmem + (g & 1) * 64 + k * 8, v_desc, idesc_o, (kt | k) != 0);
                 }
                 umma_commit(&empty[st]);
                 umma_commit(pvdone);
-                if (kt == nkt - 1) umma_commit(&ofull[i & 1]);
+                if (kt == nkt - 1) umma_commit(&ofull[obuf(i)]);
             }
         }
     } else {
@@ -211,13 +244,13 @@ vit_attn_stream_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                         mbar_wait(pvdone, (g & 1) ^ 1);       // P V of the previous tile has retired
                         tc_fence_after();
 #pragma unroll 1
-                        for (int c = 0; c < 2; ++c) {
+                        for (int c = 0; c < (HD + 31) / 32; ++c) {
                             uint32_t o[32];
-                            tmem_ld_32x32b_x32(t_lane + COL_O + (i & 1) * 64 + c * 32, o);
+                            tmem_ld_32x32b_x32(t_lane + COL_O + obuf(i) * C::OCOLS + c * 32, o);
                             tmem_ld_wait();
 #pragma unroll
                             for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
-                            tmem_st_32x32b_x32(t_lane + COL_O + (i & 1) * 64 + c * 32, o);
+                            tmem_st_32x32b_x32(t_lane + COL_O + obuf(i) * C::OCOLS + c * 32, o);
                         }
                         tmem_st_wait();
                     }
@@ -287,13 +320,13 @@ vit_attn_stream_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                             mbar_wait(pvdone, (g & 1) ^ 1);
                             tc_fence_after();
 #pragma unroll 1
-                            for (int c = 0; c < 2; ++c) {
+                            for (int c = 0; c < (HD + 31) / 32; ++c) {
                                 uint32_t o[32];
-                                tmem_ld_32x32b_x32(t_lane + COL_O + (i & 1) * 64 + c * 32, o);
+                                tmem_ld_32x32b_x32(t_lane + COL_O + obuf(i) * C::OCOLS + c * 32, o);
                                 tmem_ld_wait();
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * f);
-                                tmem_st_32x32b_x32(t_lane + COL_O + (i & 1) * 64 + c * 32, o);
+                                tmem_st_32x32b_x32(t_lane + COL_O + obuf(i) * C::OCOLS + c * 32, o);
                             }
                             tmem_st_wait();
                         }
@@ -326,19 +359,20 @@ vit_attn_stream_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                 ++g;
             }
             // ---- epilogue of the unit: O / l -> fp16, this thread's 64 output columns (128 contiguous bytes) ----
-            mbar_wait(&ofull[i & 1], (i >> 1) & 1);
+            mbar_wait(&ofull[obuf(i)], opar(i));
             tc_fence_after();
             if (warp_live) {
                 const float inv = 1.0f / ((l4[0] + l4[1]) + (l4[2] + l4[3]));
-                __half* o = out + b * out_batch_stride + static_cast<long long>(row) * out_row_stride + h * 64;
+                __half* o = out + b * out_batch_stride + static_cast<long long>(row) * out_row_stride + h * HD;
 #pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < (HD + 31) / 32; ++c) {
                     uint32_t v[32];
-                    tmem_ld_32x32b_x32(t_lane + COL_O + (i & 1) * 64 + c * 32, v);
+                    tmem_ld_32x32b_x32(t_lane + COL_O + obuf(i) * C::OCOLS + c * 32, v);
                     tmem_ld_wait();
                     if (row < S) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
+                            if (c * 32 + j >= HD) break;       // (head dimension 80: the third chunk holds 16 columns)
                             uint4 w;
                             w.x = pack_f16(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
                             w.y = pack_f16(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
@@ -351,7 +385,7 @@ vit_attn_stream_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&oempty[i & 1]);
+            if (lane == 0) mbar_arrive(&oempty[obuf(i)]);
         }
     }
     tc_fence_before();
@@ -374,14 +408,12 @@ void attention_vit_stream_enable(int on) {
 
 // returns SB_ERR_UNSUPPORTED when the shape is outside this kernel's envelope (the caller falls back to the
 // one-shot kernel in attention_tc.cu, then to the general kernel in attention.cu -- same arithmetic)
-int attention_vit_stream_fwd(const AttnParams& p, int head_dim, cudaStream_t stream) {
-    if (!g_vs_enabled || head_dim != 64 || p.coords != nullptr || p.mask != nullptr || p.out_f32 || p.S > 1024 || p.S < 1)
-        return SB_ERR_UNSUPPORTED;
-    if (p.q == nullptr || p.k != p.q + static_cast<long long>(p.H) * 64 || p.v != p.q + 2LL * p.H * 64 ||
-        p.v_row_stride != 0 || p.row_stride != 3LL * p.H * 64 || (p.out_row_stride % 8) != 0 ||
-        (reinterpret_cast<uintptr_t>(p.q) & 15) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15) != 0)
-        return SB_ERR_UNSUPPORTED;  // expects the packed [.., 3, H, 64] projection layout
-    const int D = p.H * 64;
+namespace {
+
+template <int HD>
+int launch_vs(const AttnParams& p, cudaStream_t stream) {
+    using C = VsCfg<HD>;
+    const int D = p.H * HD;
     CUtensorMap tm_q, tm_kv;
     int rc = make_tmap_3d_f16(&tm_q, p.q, 3 * D, p.S, p.B, p.row_stride, p.batch_stride, 64, 128);
     if (rc != SB_OK) return rc;
@@ -389,7 +421,7 @@ int attention_vit_stream_fwd(const AttnParams& p, int head_dim, cudaStream_t str
     if (rc != SB_OK) return rc;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(vit_attn_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VsSmem::total) != cudaSuccess)
+        if (cudaFuncSetAttribute(vit_attn_stream_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::total) != cudaSuccess)
             return SB_ERR_CUDA;
         configured = true;
     }
@@ -400,12 +432,28 @@ int attention_vit_stream_fwd(const AttnParams& p, int head_dim, cudaStream_t str
     const int n_units = static_cast<int>(units_ll);
     const int slots = 2 * gemm_num_sms();
     const int grid = n_units < slots ? n_units : slots;
-    ProfScope prof(PROF_ATTN, 4.0 * p.B * p.H * static_cast<double>(p.S) * p.S * 64, stream);
-    vit_attn_stream_kernel<<<grid, VS_THREADS, VsSmem::total, stream>>>(
+    ProfScope prof(PROF_ATTN, 4.0 * p.B * p.H * static_cast<double>(p.S) * p.S * HD, stream);
+    vit_attn_stream_kernel<HD><<<grid, VS_THREADS, C::total, stream>>>(
         tm_q, tm_kv, static_cast<__half*>(p.out), p.out_row_stride, p.out_batch_stride, p.S, p.H, D, n_units, nqb,
         p.scale_log2, g_vs_eager ? 0.f : 8.f);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+}  // namespace
+
+// returns SB_ERR_UNSUPPORTED when the shape is outside this kernel's envelope (the caller falls back to the
+// one-shot kernel in attention_tc.cu, then to the general kernel in attention.cu -- same arithmetic)
+int attention_vit_stream_fwd(const AttnParams& p, int head_dim, cudaStream_t stream) {
+    if (!g_vs_enabled || (head_dim != 64 && head_dim != 80) || p.coords != nullptr || p.mask != nullptr || p.out_f32 ||
+        p.S > 1024 || p.S < 1)
+        return SB_ERR_UNSUPPORTED;
+    const long long hw = static_cast<long long>(p.H) * head_dim;
+    if (p.q == nullptr || p.k != p.q + hw || p.v != p.q + 2 * hw || p.v_row_stride != 0 || p.row_stride != 3 * hw ||
+        (p.out_row_stride % 8) != 0 || (reinterpret_cast<uintptr_t>(p.q) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(p.out) & 15) != 0)
+        return SB_ERR_UNSUPPORTED;  // expects the packed [.., 3, H, head_dim] projection layout
+    return head_dim == 64 ? launch_vs<64>(p, stream) : launch_vs<80>(p, stream);
 }
 
 }  // namespace sb

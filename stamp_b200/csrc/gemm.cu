@@ -35,6 +35,10 @@ constexpr int BK_BYTES = 128;      // one 128-byte swizzle row of K per tile row
 constexpr int UMMA_K_BYTES = 32;   // K extent of one tcgen05.mma: 16 x 16-bit or 8 x tf32
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+// Warp roles.  The single-thread TMA and MMA warps take the HIGHEST warp ids: a sub-partition's issue arbiter favours
+// higher warp ids, and as warps 0 / 1 the two pipeline drivers were starved by an activation-heavy epilogue (fc1 + GELU:
+// the epilogue warps waited for accumulators a quarter of the time while the tensor pipe idled at 62 %).
+constexpr int WARP_TMA = NUM_EPI_WARPS, WARP_MMA = NUM_EPI_WARPS + 1;
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per epilogue warp: one 32 x 32 fp32 block
 
 template <int BN, int CTAS, int EPI = 0>
@@ -288,12 +292,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == WARP_TMA && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if constexpr (EPI != 0) tma_prefetch_desc(&tmC);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == WARP_MMA && lane == 0) {
         for (int i = 0; i < C::STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -304,7 +308,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         fence_barrier_init();
     }
-    if (warp == 1) {
+    if (warp == WARP_MMA) {
         __syncwarp();
         if constexpr (CTAS == 2) { tmem_alloc2(tmem_slot, C::TMEM_COLS); tmem_relinquish2(); }
         else { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
@@ -323,7 +327,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int first_tile = blockIdx.x / CTAS;
     const int tile_step = gridDim.x / CTAS;
 
-    if (warp == 0) {
+    if (warp == WARP_TMA) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             int stage = 0;
@@ -351,7 +355,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == WARP_MMA) {
         // ------------------------------ MMA issuer (leader CTA) --------------------
         if (lane == 0 && leader) {
             const uint32_t idesc = TF32 ? umma_idesc_tf32(TILE_M, BN)
@@ -390,7 +394,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ------------------------------ epilogue ----------------------------------
-        const int ew = warp - 2;
+        const int ew = warp;
         const int quarter = warp & 3;      // TMEM lane quarter this warp may access
         const int chalf = ew >> 2;         // which half of the BN columns
         constexpr int COLS_PER_WARP = BN / 2;
@@ -711,7 +715,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
-    if (warp == 1) {
+    if (warp == WARP_MMA) {
         tc_fence_after();
         if constexpr (CTAS == 2) tmem_dealloc2(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS);
     }

@@ -314,6 +314,29 @@ def test_attention_tcgen05_vs_general(cuda_device, B, S, H):
         assert _rel(o.float(), ref) < 2e-3
 
 
+@pytest.mark.parametrize("B,S,H", [(2, 261, 16), (3, 265, 2), (2, 64, 3), (40, 261, 16), (2, 130, 1), (5, 16, 2)])
+def test_attention_head_dim_80_tcgen05_vs_general(cuda_device, B, S, H):
+    """ViT-H/14 heads (Virchow2: 261 tokens, 16 heads of 80): the streaming tcgen05 kernel handles the head as two
+    64-column sub-tiles (5 contraction steps, one N = 128 product for P V); same result as the general kernel."""
+    from stamp_b200 import _lib, ops
+
+    g = torch.Generator(device="cpu").manual_seed(S * 5 + H)
+    qkv = torch.randn(B, S, 3 * H * 80, generator=g).to(cuda_device, torch.float16)
+    ref = _attn_ref(qkv, H)
+    out_tc = ops.attention(qkv, H)
+    try:
+        _lib.load().stamp_b200_attention_tc_enable(9)
+        out_eager = ops.attention(qkv, H)
+        _lib.load().stamp_b200_attention_tc_enable(0)
+        out_gen = ops.attention(qkv, H)
+    finally:
+        _lib.load().stamp_b200_attention_tc_enable(1)
+    for o in (out_tc, out_eager, out_gen):
+        assert torch.isfinite(o).all()
+        assert _rel(o.float(), ref) < 2e-3
+    assert _rel(out_tc.float(), out_gen.float()) < 1e-3
+
+
 @pytest.mark.parametrize("S", [257, 1000, 4097])
 @pytest.mark.parametrize("alibi", [False, True])
 def test_attention_long_bag_tcgen05_vs_general(cuda_device, S, alibi):
