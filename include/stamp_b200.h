@@ -186,6 +186,13 @@ int stamp_vit_forward(const StampVitConfig* cfg, const StampVitWeights* w,
 typedef struct {
     int dim_input, dim_model, n_layers, n_heads, dim_ff, dim_output;
     int use_alibi;   /* 1: MultiHeadALiBi, 0: nn.MultiheadAttention */
+    /* Zero-padded shapes (0 = not padded).  The kernels want dim_input / dim_model / dim_ff in multiples of 8 and
+     * heads of 32 or 64 (80) columns; a model outside that envelope (the reference's own unit tests use heads of 33
+     * and 34, src/../tests/test_model.py) is run with zero-padded weights: dim_model = n_heads * padded head width
+     * (residual stream = real channels followed by zeros), and these two fields carry what the padding must not
+     * change -- the LayerNorm statistics and the softmax scale. */
+    int dim_model_real;   /* LayerNorm normalises over the first dim_model_real channels */
+    int head_dim_real;    /* softmax scale = head_dim_real ^ -0.5 */
 } StampMilConfig;
 
 typedef struct {

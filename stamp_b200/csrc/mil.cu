@@ -70,7 +70,7 @@ mil_prepare_kernel(const float* __restrict__ coords, const uint8_t* __restrict__
 // logits[b, :] = head(LayerNorm(x[b * S, :]))  -- the score-producing tail stays in fp32
 // (transformer.norm + [:, 0] + mlp_head, vision_tranformer.py:293,382-384). One CTA per bag.
 __global__ void __launch_bounds__(256)
-cls_head_kernel(const float* __restrict__ x, long long row_stride, int d, const float* __restrict__ nw,
+cls_head_kernel(const float* __restrict__ x, long long row_stride, int d, int d_real, const float* __restrict__ nw,
                 const float* __restrict__ nb, const float* __restrict__ hw, const float* __restrict__ hb,
                 int C, float eps, float* __restrict__ logits) {
     extern __shared__ float sh[];  // d normalised values + 32 scratch
@@ -85,16 +85,16 @@ cls_head_kernel(const float* __restrict__ x, long long row_stride, int d, const 
     __syncthreads();
     float tot = 0.f;
     for (int i = 0; i < nw_; ++i) tot += red[i];
-    const float mean = tot / d;
+    const float mean = tot / d_real;      // (zero-padded width: the padding channels are zeros)
     __syncthreads();
     float q = 0.f;
-    for (int i = tid; i < d; i += blockDim.x) { const float t = xr[i] - mean; q += t * t; }
+    for (int i = tid; i < d_real; i += blockDim.x) { const float t = xr[i] - mean; q += t * t; }
     q = warp_sum(q);
     if (lane == 0) red[warp] = q;
     __syncthreads();
     tot = 0.f;
     for (int i = 0; i < nw_; ++i) tot += red[i];
-    const float rstd = rsqrtf(tot / d + eps);
+    const float rstd = rsqrtf(tot / d_real + eps);
     for (int i = tid; i < d; i += blockDim.x) y[i] = (xr[i] - mean) * rstd * nw[i] + nb[i];
     __syncthreads();
     for (int c = warp; c < C; c += nw_) {
@@ -162,7 +162,7 @@ int mil_prepare(const float* coords, const uint8_t* mask, float2* coords_s, uint
 int cls_head(const float* x, long long bag_stride, int d, const float* norm_w, const float* norm_b,
              const float* head_w, const float* head_b, int C, int B, float* logits, cudaStream_t stream) {
     if (x == nullptr || logits == nullptr || B <= 0 || d <= 0 || C <= 0) return SB_ERR_BAD_ARG;
-    cls_head_kernel<<<B, 256, (d + 32) * sizeof(float), stream>>>(x, bag_stride, d, norm_w, norm_b, head_w, head_b, C,
+    cls_head_kernel<<<B, 256, (d + 32) * sizeof(float), stream>>>(x, bag_stride, d, d, norm_w, norm_b, head_w, head_b, C,
                                                                  1e-5f, logits);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
@@ -232,7 +232,9 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w, const
         count_launch();
     }
 
-    const float scale_log2 = (1.0f / sqrtf(static_cast<float>(hd))) * 1.4426950408889634f;
+    const int d_real = (cfg->dim_model_real > 0 && cfg->dim_model_real <= d) ? cfg->dim_model_real : d;
+    const int hd_real = (cfg->head_dim_real > 0 && cfg->head_dim_real <= hd) ? cfg->head_dim_real : hd;
+    const float scale_log2 = (1.0f / sqrtf(static_cast<float>(hd_real))) * 1.4426950408889634f;
 
     const bool v3 = L.v3 && mask == nullptr;
     uint16_t* dist16 = reinterpret_cast<uint16_t*>(ws + L.off_dist);
@@ -258,7 +260,7 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w, const
             // fc -- run in split precision (operand = hi + lo, three tensor-core passes, fp32
             // accumulate); q/k and the softmax side are plain fp16.  Error budget: DESIGN.md.
             // LayerNorm -> xn = [hi | lo] (fp16, row pitch 2d)
-            rc = layernorm(x, d, y.ln1_w, y.ln1_b, xn, xn + d, 2LL * d, M, d, 1e-5f, 0, stream);
+            rc = layernorm_padded(x, d, y.ln1_w, y.ln1_b, xn, xn + d, 2LL * d, M, d, d_real, 1e-5f, 0, stream);
             if (rc != SB_OK) return rc;
             __half* qk = qkv;                                   // [M, 2d]
             __half* v16 = qkv + static_cast<size_t>(M) * 2 * d;  // [M, d]
@@ -291,7 +293,7 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w, const
             rc = gemm_tn(att, 2LL * d, y.fc_w, 3LL * d, f, stream);
             if (rc != SB_OK) return rc;
         } else {
-            rc = layernorm(x, d, y.ln1_w, y.ln1_b, xn, nullptr, d, M, d, 1e-5f, 0, stream);
+            rc = layernorm_padded(x, d, y.ln1_w, y.ln1_b, xn, nullptr, d, M, d, d_real, 1e-5f, 0, stream);
             if (rc != SB_OK) return rc;
             GemmParams p{};
             p.M = M; p.N = 3 * d; p.K = d;
@@ -309,7 +311,7 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w, const
             rc = gemm_tn(att, d, y.fc_w, d, f, stream);
             if (rc != SB_OK) return rc;
         }
-        rc = layernorm(x, d, y.ln2_w, y.ln2_b, xn, nullptr, d, M, d, 1e-5f, 0, stream);
+        rc = layernorm_padded(x, d, y.ln2_w, y.ln2_b, xn, nullptr, d, M, d, d_real, 1e-5f, 0, stream);
         if (rc != SB_OK) return rc;
         {
             GemmParams p{};
@@ -327,7 +329,7 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w, const
         }
     }
     cls_head_kernel<<<B, 256, (d + 32) * sizeof(float), stream>>>(
-        x, static_cast<long long>(S) * d, d, w->norm_w, w->norm_b, w->head_w, w->head_b,
+        x, static_cast<long long>(S) * d, d, d_real, w->norm_w, w->norm_b, w->head_w, w->head_b,
         cfg->dim_output, 1e-5f, logits);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;

@@ -19,7 +19,9 @@ template <int MAXV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w,
                  const float* __restrict__ b, void* __restrict__ out, uint16_t* __restrict__ out_lo,
-                 long long ldo, int rows, int cols, float eps, int out_kind /*0 fp16, 1 bf16, 2 fp32*/) {
+                 long long ldo, int rows, int cols, int cols_real, float eps, int out_kind /*0 fp16, 1 bf16, 2 fp32*/) {
+    // cols_real <= cols: statistics over the first cols_real columns only (zero-padded widths: the padding columns
+    // hold zeros and have zero weight / bias, so they come out as zeros)
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -36,18 +38,25 @@ layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __rest
         }
     }
     s = warp_sum(s);
-    const float mean = s / static_cast<float>(cols);
+    const float mean = s / static_cast<float>(cols_real);
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         const int idx = lane + i * 32;
         if (idx < nvec) {
             float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+            if (cols_real < cols) {      // (warp-uniform) padded width: only real columns count
+                const int c0 = idx * 4;
+                if (c0 >= cols_real) dx = 0.f;
+                if (c0 + 1 >= cols_real) dy = 0.f;
+                if (c0 + 2 >= cols_real) dz = 0.f;
+                if (c0 + 3 >= cols_real) dw = 0.f;
+            }
             q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
         }
     }
     q = warp_sum(q);
-    const float rstd = rsqrtf(q / static_cast<float>(cols) + eps);
+    const float rstd = rsqrtf(q / static_cast<float>(cols_real) + eps);
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         const int idx = lane + i * 32;
@@ -218,6 +227,12 @@ inline int grid_for(long long total, int block) {
 
 int layernorm(const float* x, long long ldx, const float* w, const float* b, void* out, void* out_lo,
               long long ldo, int rows, int cols, float eps, int out_kind, cudaStream_t stream) {
+    return layernorm_padded(x, ldx, w, b, out, out_lo, ldo, rows, cols, cols, eps, out_kind, stream);
+}
+
+int layernorm_padded(const float* x, long long ldx, const float* w, const float* b, void* out, void* out_lo,
+                     long long ldo, int rows, int cols, int cols_real, float eps, int out_kind, cudaStream_t stream) {
+    if (cols_real <= 0 || cols_real > cols) return SB_ERR_BAD_ARG;
     if (rows <= 0 || cols <= 0 || (cols % 4) != 0 || (ldx % 4) != 0 || (ldo % 4) != 0 ||
         out_kind < 0 || out_kind > 2 || (out_lo != nullptr && out_kind != 0))
         return SB_ERR_BAD_ARG;
@@ -226,11 +241,11 @@ int layernorm(const float* x, long long ldx, const float* w, const float* b, voi
     const int blocks = (rows * 32 + threads - 1) / threads;
     ProfScope prof(PROF_ROWOP, static_cast<double>(rows) * cols * (4.0 + (out_kind == 2 ? 4.0 : 2.0)), stream);
     if (cols <= 512)
-        layernorm_kernel<4><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, lo, ldo, rows, cols, eps, out_kind);
+        layernorm_kernel<4><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, lo, ldo, rows, cols, cols_real, eps, out_kind);
     else if (cols <= 1024)
-        layernorm_kernel<8><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, lo, ldo, rows, cols, eps, out_kind);
+        layernorm_kernel<8><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, lo, ldo, rows, cols, cols_real, eps, out_kind);
     else if (cols <= 2048)
-        layernorm_kernel<16><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, lo, ldo, rows, cols, eps, out_kind);
+        layernorm_kernel<16><<<blocks, threads, 0, stream>>>(x, ldx, w, b, out, lo, ldo, rows, cols, cols_real, eps, out_kind);
     else
         return SB_ERR_UNSUPPORTED;
     count_launch();

@@ -10,6 +10,10 @@ namespace sb {
 int layernorm(const float* x, long long ldx, const float* w, const float* b, void* out, void* out_lo,
               long long ldo, int rows, int cols, float eps, int out_kind, cudaStream_t stream);
 
+// zero-padded widths: statistics over the first cols_real of cols columns (padding columns: zeros in, zeros out)
+int layernorm_padded(const float* x, long long ldx, const float* w, const float* b, void* out, void* out_lo,
+                     long long ldo, int rows, int cols, int cols_real, float eps, int out_kind, cudaStream_t stream);
+
 // x[g * rows_per_group + row_off + r, :] = src[r, :] (+ add[r, :]) for g < groups, r < nrows
 int fill_rows(float* x, long long ldx, int groups, int rows_per_group, int row_off,
               const float* src, long long lds, const float* add, long long lda, int nrows, int cols,

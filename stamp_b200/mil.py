@@ -31,7 +31,7 @@ from . import _lib
 
 class StampMilConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("dim_input", "dim_model", "n_layers", "n_heads", "dim_ff",
-                                       "dim_output", "use_alibi")]
+                                       "dim_output", "use_alibi", "dim_model_real", "head_dim_real")]
 
 
 class StampMilWeights(C.Structure):
@@ -169,9 +169,35 @@ class VisionTransformer(nn.Module):
             self.__dict__.setdefault(k, v)
         self.__dict__.setdefault("_train_gen", 0)
 
+    # ---- shapes outside the kernels' envelope run zero-padded (include/stamp_b200.h, StampMilConfig) ----
+    def _shape_plan(self) -> dict:
+        """Kernel shapes: widths in multiples of 8, heads of 32 / 64 (/ 80 without ALiBi) columns.  Anything else --
+        the reference's unit tests use heads of 33 and 34, 457 input features, 135 hidden units
+        (tests/test_model.py) -- is zero-padded: ``dim_model`` becomes ``n_heads * padded head width``."""
+        c = self._cfg
+        d, H, F, ff = c["dim_model"], c["n_heads"], c["dim_input"], c["dim_ff"]
+        hd = d // H
+        if hd <= 32:
+            hp = 32
+        elif hd <= 64:
+            hp = 64
+        elif hd <= 80 and not c["use_alibi"]:
+            hp = 80
+        else:
+            raise ValueError(f"unsupported MIL configuration for the sm_100a kernels: head dimension {hd} "
+                             f"(at most 64 with ALiBi, 80 without)")
+        up8 = lambda n: (n + 7) // 8 * 8
+        plan = dict(d=d, hd=hd, hp=hp, dc=H * hp, F=F, Fp=up8(F), ff=ff, ffp=up8(ff))
+        plan["padded"] = plan["dc"] != d or plan["Fp"] != F or plan["ffp"] != ff
+        return plan
+
     def _pack(self):
         key = self._pack_key()
         if self._packed is not None and self._packed[0] == key:
+            return self._packed
+        plan = self._shape_plan()
+        if plan["padded"]:
+            self._packed = self._pack_padded(key, plan)
             return self._packed
         keep: list[Tensor] = []
 
@@ -217,6 +243,69 @@ class VisionTransformer(nn.Module):
         self._packed = (key, keep, cfg, w, layers)
         return self._packed
 
+    def _pack_padded(self, key, plan):
+        """Same operands as :meth:`_pack` for a model outside the envelope: every weight zero-padded to the kernel
+        shapes.  Residual-space vectors / matrix sides (LayerNorm, biases, class token, projection rows, fc rows,
+        feed-forward) are padded at the end; head-space sides (q | k | v rows, fc columns) head by head, so that head
+        ``h`` occupies columns ``[h * hp, h * hp + hd)``.  Zero rows / columns keep every padding channel exactly zero
+        through GELU(0) = 0, the attention and the residual adds; LayerNorm statistics and the softmax scale use the
+        real sizes (``dim_model_real``, ``head_dim_real``)."""
+        import torch.nn.functional as Fn
+
+        keep: list[Tensor] = []
+        d, hd, hp, dc, F, Fp, ff, ffp = (plan[k] for k in ("d", "hd", "hp", "dc", "F", "Fp", "ff", "ffp"))
+        H, use_alibi = self._cfg["n_heads"], bool(self._cfg["use_alibi"])
+
+        def f32(t: Tensor) -> int:
+            t = t.detach().float().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        def f16(t: Tensor) -> int:
+            t = t.detach().half().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        vec = lambda v, n: Fn.pad(v.detach().float(), (0, n - v.shape[0]))               # residual / hidden vectors
+        mat = lambda m, r, c: Fn.pad(m.detach().float(), (0, c - m.shape[1], 0, r - m.shape[0]))
+        head_rows = lambda m: Fn.pad(m.detach().float().reshape(H, hd, -1), (0, 0, 0, hp - hd)).reshape(H * hp, -1)
+        head_vec = lambda v: Fn.pad(v.detach().float().reshape(H, hd), (0, hp - hd)).reshape(H * hp)
+        head_cols = lambda m: Fn.pad(m.detach().float().reshape(m.shape[0], H, hd), (0, hp - hd)).reshape(m.shape[0], H * hp)
+
+        cfg = StampMilConfig(**{**self._cfg, "dim_input": Fp, "dim_model": dc, "dim_ff": ffp,
+                                "dim_model_real": d, "head_dim_real": hd})
+        w = StampMilWeights(f16(mat(self.project_features[0].weight, dc, Fp)), f32(vec(self.project_features[0].bias, dc)),
+                            f32(vec(self.class_token, dc)), f32(vec(self.transformer.norm.weight, dc)),
+                            f32(vec(self.transformer.norm.bias, dc)), f32(mat(self.mlp_head[0].weight, self._cfg["dim_output"], dc)),
+                            f32(self.mlp_head[0].bias))
+        layers = (StampMilLayer * max(1, self._cfg["n_layers"]))()
+        for i, (att, ffn) in enumerate(self.transformer.layers):
+            m = att.mhsa
+            if use_alibi:
+                groups = (m.query_encoders, m.key_encoders, m.value_encoders)
+                qkv_w = torch.cat([mat(head_rows(torch.cat([e.weight for e in grp])), H * hp, dc) for grp in groups])
+                qkv_b = torch.cat([head_vec(torch.cat([e.bias for e in grp])) for grp in groups])
+                slope = torch.cat([a.bias_scale / a.scale_distance.running_mean for a in m.attentions])
+                fc_full = mat(head_cols(m.fc.weight), dc, dc)
+                fc_hi = round_to_tf32(fc_full)
+                fc_lo = round_to_tf32(fc_full - fc_hi)
+                fc_w, fc_b, slope_p = f32(torch.cat([fc_hi, fc_hi, fc_lo], dim=1)), f32(vec(m.fc.bias, dc)), f32(slope)
+                wv = qkv_w[2 * dc:]
+                wv_hi = wv.half()
+                v_w3 = f16(torch.cat([wv_hi, wv_hi, (wv - wv_hi.float()).half()], dim=1))
+            else:
+                wq, wk, wv = m.in_proj_weight.detach().float().split(d)
+                bq, bk, bv = m.in_proj_bias.detach().float().split(d)
+                qkv_w = torch.cat([mat(head_rows(x), H * hp, dc) for x in (wq, wk, wv)])
+                qkv_b = torch.cat([head_vec(x) for x in (bq, bk, bv)])
+                fc_w, fc_b, slope_p = f16(mat(head_cols(m.out_proj.weight), dc, dc)), f32(vec(m.out_proj.bias, dc)), None
+                v_w3 = None
+            layers[i] = StampMilLayer(f32(vec(att.norm.weight, dc)), f32(vec(att.norm.bias, dc)), f16(qkv_w), f32(qkv_b),
+                                      v_w3, slope_p, fc_w, fc_b, f32(vec(ffn[0].weight, dc)), f32(vec(ffn[0].bias, dc)),
+                                      f16(mat(ffn[1].weight, ffp, dc)), f32(vec(ffn[1].bias, ffp)),
+                                      f16(mat(ffn[4].weight, dc, ffp)), f32(vec(ffn[4].bias, dc)))
+        return (key, keep, cfg, w, layers)
+
     def forward(self, bags: Tensor, *, coords: Tensor, mask: Tensor | None) -> Tensor:
         if bags.dim() != 3 or coords.dim() != 3 or coords.shape[:2] != bags.shape[:2] or coords.shape[2] != 2:
             raise TypeError(f"expected bags [B,N,F] and coords [B,N,2], got {tuple(bags.shape)} / {tuple(coords.shape)}")
@@ -249,10 +338,11 @@ class VisionTransformer(nn.Module):
         coords32 = coords.detach().float().contiguous()
         mask8 = mask.to(torch.uint8).contiguous() if mask is not None else None
         logits = torch.empty((B, self._cfg["dim_output"]), dtype=torch.float32, device=dev)
+        if cfg.dim_input != bags_in.shape[2]:       # zero-padded input width (see _shape_plan)
+            bags_in = torch.nn.functional.pad(bags_in, (0, cfg.dim_input - bags_in.shape[2]))
         need = lib.stamp_mil_workspace_bytes(C.byref(cfg), B, N)
         if need == 0:
-            raise ValueError("unsupported MIL configuration for the sm_100a kernels "
-                             "(dims must be multiples of 8, head dim 32 or 64)")
+            raise ValueError("unsupported MIL configuration for the sm_100a kernels")
         stream = torch.cuda.current_stream(dev).cuda_stream
         if self._workspace is None or len(self._workspace) > 8:   # (callers that keep creating streams: start over)
             self._workspace = {}

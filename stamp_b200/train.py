@@ -209,13 +209,14 @@ class _MilTrainFn(torch.autograd.Function):
     def forward(model: VisionTransformer, bags: Tensor, coords: Tensor, inv_rm: Tensor, p_proj: float,
                 p_ff: float, seed: int, *params: Tensor) -> Tensor:
         lib = _bind()
-        cfg = StampMilConfig(**model._cfg)
+        cfg = StampMilConfig(**{**model._cfg, "dim_input": bags.shape[2]})    # (possibly zero-padded, see below)
         B, N, _ = bags.shape
         dev = bags.device
         need = lib.stamp_mil_train_ctx_bytes(C.byref(cfg), B, N)
         if need == 0:
             raise ValueError("unsupported MIL configuration for the sm_100a training kernels (needs head dim "
-                             "32/64, dims % 8 == 0, dim_model <= 1024, at least one tile)")
+                             "32/64, dim_model and dim_feedforward % 8 == 0, dim_model <= 1024, at least one tile; "
+                             "inference zero-pads other shapes, training only the input width)")
         buf = model._train_ctx
         if buf is None or buf.numel() < need or buf.device != dev:
             buf = model._train_ctx = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -275,7 +276,16 @@ def mil_forward_with_grad(model: VisionTransformer, bags: Tensor, coords: Tensor
             inv_rm = (1.0 / torch.cat([s.running_mean for s in _scalers(model)]).float()).reshape(L, H).contiguous()
         else:
             inv_rm = torch.ones(L, H, device=bags.device)
-    return _MilTrainFn.apply(model, bags, coords, inv_rm, p_proj, p_ff, seed, *_packed_params(model)).to(bags.dtype)
+    params = _packed_params(model)
+    Fin = bags.shape[2]
+    if Fin % 8:
+        # input widths that are not a multiple of 8 (the reference's acceptance test trains on 25 features): zero
+        # columns on both sides of the projection; autograd slices the padded gradients back
+        pad = (Fin + 7) // 8 * 8 - Fin
+        bags_p = torch.nn.functional.pad(bags, (0, pad))
+        params[0] = torch.nn.functional.pad(params[0], (0, pad))
+        return _MilTrainFn.apply(model, bags_p, coords, inv_rm, p_proj, p_ff, seed, *params).to(bags.dtype)
+    return _MilTrainFn.apply(model, bags, coords, inv_rm, p_proj, p_ff, seed, *params).to(bags.dtype)
 
 
 def dropout_keep_mask(seed: int, site: int, n: int, p: float, device) -> Tensor:

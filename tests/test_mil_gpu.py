@@ -147,6 +147,43 @@ def test_mil_heatmap_style_per_tile_batch(cuda_device):
     assert torch.equal(pr.topk(k).indices, po.topk(k).indices)
 
 
+@pytest.mark.parametrize("use_alibi", [False, True])
+@pytest.mark.parametrize("dims", [dict(dim_input=456, n_heads=4, head=33, dim_ff=135, n_layers=3, batch=6, n=75, C=3),
+                                  dict(dim_input=457, n_heads=5, head=34, dim_ff=135, n_layers=3, batch=7, n=76, C=4),
+                                  dict(dim_input=25, n_heads=8, head=64, dim_ff=512, n_layers=2, batch=3, n=300, C=2),
+                                  dict(dim_input=64, n_heads=3, head=20, dim_ff=96, n_layers=1, batch=2, n=40, C=2)])
+def test_mil_shapes_outside_the_kernel_envelope_run_zero_padded(cuda_device, dims, use_alibi):
+    """The reference's own unit tests build models the kernels have no native shape for (tests/test_model.py: heads of
+    33 / 34 columns, 456 / 457 input features, 135 hidden units; tests/test_train_deploy.py: 25 input features).  They
+    run with zero-padded weights (LayerNorm statistics and softmax scale on the real sizes), masked and unmasked,
+    and match the oracle like any other shape."""
+    from oracle import mil_oracle
+
+    H, hd = dims["n_heads"], dims["head"]
+    # (ALiBi: two layers, like every other 1e-3 check of that variant -- its unscaled distance term costs accuracy per
+    #  layer; the reference's odd-shape tests are use_alibi=False, three layers)
+    sd = mil_oracle.init_state_dict(dim_input=dims["dim_input"], dim_output=dims["C"], dim_model=H * hd, n_heads=H,
+                                    n_layers=min(dims["n_layers"], 2) if use_alibi else dims["n_layers"],
+                                    dim_feedforward=dims["dim_ff"], use_alibi=use_alibi,
+                                    seed=31, running_mean=3000.0)
+    bags, coords = mil_oracle.synthetic_bag(dims["n"], dims["dim_input"], seed=7, batch=dims["batch"])
+    g = torch.Generator().manual_seed(3)
+    mask = torch.arange(dims["n"])[None, :] >= torch.randint(1, dims["n"], (dims["batch"], 1), generator=g)
+    model = _model_from_sd(sd, H, cuda_device)
+    for m in (None, mask):
+        with torch.no_grad():
+            ref = mil_oracle.forward(sd, bags, coords, m, n_heads=H)
+            out = model(bags.to(cuda_device), coords=coords.to(cuda_device), mask=None if m is None else m.to(cuda_device))
+        assert out.shape == (dims["batch"], dims["C"])
+        err = _rel_per_bag(out, ref)
+        print(f"alibi={use_alibi} {dims} masked={m is not None}: max per-bag relative error {err:.2e}")
+        assert err < 1e-3, err
+    with torch.inference_mode():      # determinism of two evaluations (the reference's test_inference_reproducibility)
+        a = model(bags.to(cuda_device), coords=coords.to(cuda_device), mask=mask.to(cuda_device))
+        b = model(bags.to(cuda_device), coords=coords.to(cuda_device), mask=mask.to(cuda_device))
+    assert torch.equal(a, b)
+
+
 def test_mil_empty_and_tiny_bags(cuda_device):
     from oracle import mil_oracle
 

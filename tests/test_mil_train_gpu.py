@@ -220,6 +220,25 @@ def test_benched_shape_gradients_match_oracle(cuda_device):
             print(f"[benched shape, two bags with opposite labels] worst error / summed scale {worst:.3e}")
 
 
+@pytest.mark.parametrize("use_alibi", [False, True])
+def test_input_width_outside_the_envelope_trains_zero_padded(cuda_device, use_alibi):
+    """tests/test_train_deploy.py of the reference trains on 25-dimensional features: the training path pads the
+    input width (bags and projection weight) with zeros; every gradient, including the projection's, matches."""
+    from stamp_b200 import train as T
+
+    sd = mil_oracle.init_state_dict(dim_input=25, dim_output=2, dim_model=128, n_heads=2, dim_feedforward=128, seed=6,
+                                    use_alibi=use_alibi)
+    bags, coords = mil_oracle.synthetic_bag(32, 25, seed=9, batch=8, signal=True)
+    targets = torch.nn.functional.one_hot(torch.arange(8) % 2, 2).float()
+    model = _model(sd, 2, cuda_device)
+    loss = T.training_step(model, (bags.to(cuda_device), coords.to(cuda_device), None, targets.to(cuda_device)), None)
+    loss.backward()
+    _, ref_loss, ref_grads, _ = mil_oracle.train_grads(sd, bags, coords, targets, None, n_heads=2)
+    assert abs(float(loss.detach()) - float(ref_loss)) < LOGIT_TOL * max(1.0, float(ref_loss))
+    assert model.project_features[0].weight.grad.shape == (128, 25)
+    _check_grads(model, ref_grads, f"dim_input 25, alibi={use_alibi}")
+
+
 def test_default_size_mha_variant_matches_oracle(cuda_device):
     """use_alibi=False (the reference's default backbone): long bag -> tcgen05 forward / backward, plain softmax."""
     from stamp_b200 import train as T
