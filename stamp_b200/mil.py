@@ -144,6 +144,8 @@ class VisionTransformer(nn.Module):
         self._train_ctx: Tensor | None = None   # checkpoints between a training forward and its backward
         self._train_gen = 0
         self._train_state = None
+        self._flat_opt = None            # weakref to a FusedAdamW(model=self): packed-order flat buffers (train.py)
+        self._grad_sink_views = None
 
     # ---- weight packing: reference layout -> GEMM operands (cached until a parameter changes) ----
     def _pack_key(self):
@@ -156,7 +158,8 @@ class VisionTransformer(nn.Module):
 
     # ctypes structures with raw device pointers, workspaces and the checkpoint buffer are per-process caches:
     # copy.deepcopy / torch.save(model) / spawn pickling carry the parameters only
-    _TRANSIENT = {"_packed": None, "_workspace": None, "_train_ctx": None, "_train_state": None, "_key_tensors": None}
+    _TRANSIENT = {"_packed": None, "_workspace": None, "_train_ctx": None, "_train_state": None, "_key_tensors": None,
+                  "_flat_opt": None, "_grad_sink_views": None}
 
     def __getstate__(self):
         state = dict(super().__getstate__() if hasattr(super(), "__getstate__") else self.__dict__)

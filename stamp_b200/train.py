@@ -142,6 +142,28 @@ def _packed_params(model: VisionTransformer) -> list[Tensor]:
     return out
 
 
+def _packed_groups(model: VisionTransformer) -> list[list[Tensor] | None]:
+    """The same 7 + 13 per layer slots as :func:`_packed_params`, as groups of parameters whose row-wise concatenation
+    IS the packed tensor (None: a slot without parameters -- the bias_scale placeholder of nn.MultiheadAttention).
+    An optimiser that lays its flat buffers out in this order (``FusedAdamW(..., model=model)``) makes every packed
+    tensor a contiguous view: no torch.cat in the forward, and the backward kernels accumulate straight into
+    ``flat_grad``."""
+    out: list[list[Tensor] | None] = [[model.project_features[0].weight], [model.project_features[0].bias],
+                                      [model.class_token], [model.transformer.norm.weight], [model.transformer.norm.bias],
+                                      [model.mlp_head[0].weight], [model.mlp_head[0].bias]]
+    for att, ff in model.transformer.layers:
+        m = att.mhsa
+        if model._cfg["use_alibi"]:
+            groups = (m.query_encoders, m.key_encoders, m.value_encoders)
+            attn = [[e.weight for grp in groups for e in grp], [e.bias for grp in groups for e in grp],
+                    [a.bias_scale for a in m.attentions], [m.fc.weight], [m.fc.bias]]
+        else:
+            attn = [[m.in_proj_weight], [m.in_proj_bias], None, [m.out_proj.weight], [m.out_proj.bias]]
+        out += [[att.norm.weight], [att.norm.bias], *attn, [ff[0].weight], [ff[0].bias], [ff[1].weight], [ff[1].bias],
+                [ff[4].weight], [ff[4].bias]]
+    return out
+
+
 def _structs(tensors: list[Tensor], n_layers: int):
     top = StampMilTrainTop(*[t.data_ptr() for t in tensors[:7]])
     layers = (StampMilTrainLayer * n_layers)()
@@ -153,7 +175,7 @@ def _structs(tensors: list[Tensor], n_layers: int):
 class _TrainState:
     """What one checkpointing forward leaves for its backward(s) (not a pytree: functorch passes it through)."""
 
-    __slots__ = ("model", "cfg", "gen", "buf", "tensors", "inv_rm", "step_args", "shape", "bags_dtype")
+    __slots__ = ("model", "cfg", "gen", "buf", "tensors", "inv_rm", "step_args", "shape", "bags_dtype", "sink")
 
 
 def _run_backward(st: _TrainState, dlogits: Tensor, want_dbags: bool) -> tuple[Tensor | None, list[Tensor]]:
@@ -163,9 +185,13 @@ def _run_backward(st: _TrainState, dlogits: Tensor, want_dbags: bool) -> tuple[T
         raise RuntimeError("the checkpoint buffer of this forward was overwritten by a later training-mode "
                            "forward of the same model; run backward before the next forward")
     B, N = st.shape
-    sizes = [t.numel() for t in st.tensors]
-    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dlogits.device)
-    grads = [g.view_as(t) for g, t in zip(flat.split(sizes), st.tensors)]
+    if st.sink is not None and not want_dbags:
+        # gradients accumulate straight into the optimiser's flat buffer (packed-order views of it)
+        grads = st.sink
+    else:
+        sizes = [t.numel() for t in st.tensors]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dlogits.device)
+        grads = [g.view_as(t) for g, t in zip(flat.split(sizes), st.tensors)]
     top, layers = _structs(st.tensors, cfg.n_layers)
     gtop, glayers = _structs(grads, cfg.n_layers)
     step = StampMilTrainStep(*st.step_args, st.inv_rm.data_ptr())
@@ -188,6 +214,8 @@ class _MilBwdFn(torch.autograd.Function):
         dbags, grads = _run_backward(st, dlogits, want_dbags)
         if dbags is None:
             dbags = dlogits.new_zeros(0)
+        if st.sink is not None and not want_dbags:
+            return (dbags.to(st.bags_dtype),)        # the parameter gradients are already where they belong
         return (dbags.to(st.bags_dtype), *grads)
 
     @staticmethod
@@ -221,7 +249,7 @@ class _MilTrainFn(torch.autograd.Function):
         if buf is None or buf.numel() < need or buf.device != dev:
             buf = model._train_ctx = torch.empty(need, dtype=torch.uint8, device=dev)
         model._train_gen += 1
-        tensors = [p.detach().float().contiguous() for p in params]
+        tensors = [p.detach().float().contiguous() for p in params]     # (views of flat_param: no copies)
         top, layers = _structs(tensors, cfg.n_layers)
         bags32 = bags.detach().float().contiguous()
         coords32 = coords.detach().float().contiguous()
@@ -234,6 +262,8 @@ class _MilTrainFn(torch.autograd.Function):
         st.model, st.cfg, st.gen, st.buf = model, cfg, model._train_gen, buf
         st.tensors, st.inv_rm, st.step_args = tensors, inv_rm, (p_proj, p_ff, seed)
         st.shape, st.bags_dtype = (B, N), bags.dtype
+        st.sink = model._grad_sink_views
+        model._grad_sink_views = None
         model._train_state = st          # handed to setup_context (the functorch-compatible Function protocol)
         return logits
 
@@ -247,6 +277,8 @@ class _MilTrainFn(torch.autograd.Function):
         want = bool(ctx.needs_input_grad[1])
         ctx.st.model._train_state = None    # the hand-over slot only; ctx keeps the state (no model<->state cycle)
         dbags, *grads = _MilBwdFn.apply(dlogits, ctx.st, want)
+        if not grads:                       # gradient sink: nothing for autograd to route (see mil_forward_with_grad)
+            grads = [None] * (len(ctx.needs_input_grad) - 7)
         return (None, dbags if want else None, None, None, None, None, None, *grads)
 
 
@@ -276,8 +308,16 @@ def mil_forward_with_grad(model: VisionTransformer, bags: Tensor, coords: Tensor
             inv_rm = (1.0 / torch.cat([s.running_mean for s in _scalers(model)]).float()).reshape(L, H).contiguous()
         else:
             inv_rm = torch.ones(L, H, device=bags.device)
-    params = _packed_params(model)
     Fin = bags.shape[2]
+    opt = model._flat_opt() if model._flat_opt is not None else None
+    if (opt is not None and model.training and not bags.requires_grad and Fin % 8 == 0 and opt.owns(model)
+            and not torch._C._functorch.is_functorch_wrapped_tensor(bags)):
+        # parameters and gradients live in packed order inside the optimiser's flat buffers: the kernels read the
+        # packed views directly (no torch.cat) and accumulate into flat_grad (no per-parameter adds by autograd).
+        # class_token rides along as the differentiable input that makes autograd call the backward.
+        packed, model._grad_sink_views = opt.packed_views()
+        return _MilTrainFn.apply(model, bags, coords, inv_rm, p_proj, p_ff, seed, *packed, model.class_token).to(bags.dtype)
+    params = _packed_params(model)
     if Fin % 8:
         # input widths that are not a multiple of 8 (the reference's acceptance test trains on 25 features): zero
         # columns on both sides of the projection; autograd slices the padded gradients back
@@ -340,10 +380,20 @@ class FusedAdamW(torch.optim.Optimizer):
     The parameters are re-pointed into one contiguous buffer (``p.data`` become views) and so are their
     ``.grad``; ``flat_grad`` is also what :class:`stamp_b200.sharding.FlatGradAllReducer` all-reduces.
     Being a ``torch.optim.Optimizer`` it works with ``OneCycleLR`` (which cycles ``lr`` and ``betas[0]``).
-    One parameter group only; the moments and the step count travel in ``state_dict()`` (key ``"fused"``)."""
+    One parameter group only; the moments and the step count travel in ``state_dict()`` (key ``"fused"``).
+
+    Built with ``model=``, the training backward of that model adds its parameter gradients into ``flat_grad`` itself
+    instead of handing them to autograd (as long as every ``p.grad`` is still the view this class installed):
+    ``loss.backward()`` then behaves as usual, gradient accumulation over several backwards included, but
+    ``torch.autograd.grad(loss, parameters)`` and per-parameter autograd hooks see nothing -- build the optimiser
+    without ``model=`` where those are needed."""
 
     def __init__(self, params: Iterable[Tensor], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 1e-2) -> None:
+                 weight_decay: float = 1e-2, model: VisionTransformer | None = None) -> None:
+        """``model``: lay the flat buffers out in the order the training kernels consume the parameters (per-head
+        Linear weights of a layer adjacent, :func:`_packed_groups`), so that the packed operands are views of
+        ``flat_param`` and the backward accumulates straight into ``flat_grad``.  ``params`` must then be exactly the
+        model's trainable parameters."""
         params = list(params)
         if any(isinstance(p, dict) for p in params):
             raise ValueError("FusedAdamW keeps ONE flat buffer: parameter groups are not supported")
@@ -355,14 +405,35 @@ class FusedAdamW(torch.optim.Optimizer):
             if p.dtype != torch.float32:
                 raise TypeError("FusedAdamW keeps fp32 master parameters")
         self._built = False
+        self._groups: list[tuple[int, tuple[int, ...]] | None] | None = None
+        if model is not None:
+            groups = _packed_groups(model)
+            ordered = [p for g in groups if g is not None for p in g]
+            if len(ordered) != len(params) or {id(p) for p in ordered} != {id(p) for p in params}:
+                raise ValueError("FusedAdamW(model=...) needs exactly the model's trainable parameters")
+            params = ordered
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         dev = params[0].device
-        # every parameter starts on a 256-byte boundary: the GEMM / vector kernels need 16-byte aligned bases
+        # every parameter (with a model: every packed group) starts on a 256-byte boundary: the GEMM / vector kernels
+        # need 16-byte aligned bases; inside a group the members follow each other without gaps
         sizes = [p.numel() for p in params]
         offs, total = [], 0
-        for n in sizes:
-            offs.append(total)
-            total += (n + 63) // 64 * 64
+        if model is None:
+            for n in sizes:
+                offs.append(total)
+                total += (n + 63) // 64 * 64
+        else:
+            self._groups = []
+            for g in groups:
+                if g is None:
+                    self._groups.append(None)
+                    continue
+                rows = sum(p.shape[0] if p.dim() > 0 else 1 for p in g)
+                self._groups.append((total, (rows, *g[0].shape[1:])))
+                for p in g:
+                    offs.append(total)
+                    total += p.numel()
+                total = (total + 63) // 64 * 64
         self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros_like(self.flat_param)
         self.exp_avg = torch.zeros_like(self.flat_param)
@@ -376,7 +447,41 @@ class FusedAdamW(torch.optim.Optimizer):
                 p.grad = self.flat_grad[o:o + n].view_as(p)
         self._step = 0
         self._built = True
+        if model is not None:
+            import weakref
+
+            self._model_ref = weakref.ref(model)
+            self._dummy = torch.zeros(64, dtype=torch.float32, device=dev)   # slot without parameters (MHA bias_scale)
+            model._flat_opt = weakref.ref(self)
         bump_weights_epoch()
+
+    def owns(self, model) -> bool:
+        """True while ``model``'s parameters are still the views of ``flat_param`` this optimiser created."""
+        if self._groups is None or getattr(self, "_model_ref", lambda: None)() is not model:
+            return False
+        pbase, gbase = self.flat_param.data_ptr(), self.flat_grad.data_ptr()
+        for p, o in zip(self._params, self._offs):
+            g = p.grad
+            if g is None or p.data_ptr() != pbase + 4 * o or g.data_ptr() != gbase + 4 * o:
+                return False
+        return True
+
+    def packed_views(self) -> tuple[list[Tensor], list[Tensor]]:
+        """(packed parameter operands, matching gradient accumulators) as views of the flat buffers, in the order of
+        the training kernels' structs."""
+        ps, gs = [], []
+        for g in self._groups:
+            if g is None:
+                ps.append(self._dummy)
+                gs.append(self._dummy)
+                continue
+            off, shape = g
+            n = 1
+            for d in shape:
+                n *= d
+            ps.append(self.flat_param[off:off + n].view(shape))
+            gs.append(self.flat_grad[off:off + n].view(shape))
+        return ps, gs
 
     def add_param_group(self, param_group) -> None:
         if getattr(self, "_built", False):
@@ -451,7 +556,9 @@ class FusedAdamW(torch.optim.Optimizer):
 def configure_optimizers(model: VisionTransformer, *, total_steps: int, max_lr: float = 1e-4,
                          div_factor: float = 25.0):
     """``Base.configure_optimizers`` (models/__init__.py:133-141): AdamW(lr=1e-3 placeholder) + OneCycleLR."""
-    opt = FusedAdamW(model.parameters(), lr=1e-3)
+    # all parameters trainable (the reference never freezes any): packed-order layout, gradients land in flat_grad
+    packed = all(p.requires_grad for p in model.parameters())
+    opt = FusedAdamW(model.parameters(), lr=1e-3, model=model if packed else None)
     sched = torch.optim.lr_scheduler.OneCycleLR(optimizer=opt, total_steps=total_steps, max_lr=max_lr,
                                                 div_factor=div_factor)
     return opt, sched

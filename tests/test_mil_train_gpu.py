@@ -424,6 +424,62 @@ def test_eval_forward_after_optimizer_step_uses_new_weights(cuda_device, use_ali
     assert stale > 10 * rel and rel < 3e-3, (float(stale), float(rel))
 
 
+@pytest.mark.parametrize("use_alibi", [False, True])
+def test_packed_order_optimizer_receives_gradients_directly(cuda_device, use_alibi):
+    """FusedAdamW(model=...) lays parameters and gradients out in the kernels' packed order: the backward adds into
+    flat_grad itself.  Same seeds, same dropout masks: the gradients equal the ones autograd routes for a twin model
+    without that optimiser, they accumulate over two backwards, and detaching one .grad falls back to autograd."""
+    import copy
+
+    from stamp_b200 import train as T
+
+    sd = mil_oracle.init_state_dict(dim_input=64, dim_output=2, dim_model=128, n_heads=2, dim_feedforward=128,
+                                    seed=23, use_alibi=use_alibi)
+    bags, coords = mil_oracle.synthetic_bag(150, 64, seed=5, batch=3, signal=True)
+    targets = torch.nn.functional.one_hot(torch.arange(3) % 2, 2).float()
+    dev = lambda t: t.to(cuda_device)
+    batch = (dev(bags), dev(coords), None, dev(targets))
+    model = _model(sd, 2, cuda_device, dropout=0.0 if not use_alibi else 0.1, p_ff=0.1).train()
+    twin = copy.deepcopy(model).train()
+    opt = T.FusedAdamW(model.parameters(), lr=1e-3, model=model)
+    assert opt.owns(model) and not opt.owns(twin)
+    names = [n for n, _ in model.named_parameters()]
+
+    def grads_of(m, n_backwards):
+        torch.manual_seed(99)                     # the dropout seed is drawn from torch's generator
+        for _ in range(n_backwards):
+            T.training_step(m, batch, None).backward()
+        return {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+
+    def compare(got, want, what):
+        for n in names:
+            scale = want[n].abs().max().clamp_min(1e-6)
+            err = float((got[n] - want[n]).abs().max() / scale)
+            # same kernels, same inputs: only the order of the fp32 atomics differs
+            assert err < 2e-3, (what, n, err)
+
+    want1 = grads_of(twin, 1)
+    got1 = grads_of(model, 1)
+    assert all(p.grad.data_ptr() >= opt.flat_grad.data_ptr() for p in model.parameters())
+    compare(got1, want1, "one backward")
+    twin.zero_grad()
+    opt.zero_grad()
+    assert float(opt.flat_grad.abs().max()) == 0.0
+    compare(grads_of(model, 2), grads_of(twin, 2), "two accumulated backwards")
+    # a detached gradient: autograd routes again, relink() folds the result back
+    opt.zero_grad()
+    twin.zero_grad()
+    model.class_token.grad = None
+    assert not opt.owns(model)
+    got = grads_of(model, 1)
+    opt.relink()
+    assert opt.owns(model)
+    compare(got, grads_of(twin, 1), "fallback through autograd")
+    before = model.class_token.detach().clone()
+    opt.step()
+    assert float((model.class_token.detach() - before).abs().max()) > 0
+
+
 def test_fused_adamw_state_dict_relink_and_groups(cuda_device):
     """Checkpoint / resume keeps the Adam moments and the bias-correction step; gradients detached from the flat
     buffer (model.zero_grad(set_to_none=True), stray .grad tensors) are folded back in; one group only."""

@@ -68,7 +68,11 @@ def test_tiles_to_heatmap_pipeline(cuda_device):
     cam = T.gradcam_per_category(model, feats.float().to(cuda_device), coords.to(cuda_device))
     assert cam.shape == (36, 2) and torch.allclose(cam.sum(0), torch.ones(2, device=cuda_device), atol=1e-4)
     vals, idx = topk(cam[:, 1].contiguous(), 8)
-    assert idx.shape == (8,) and torch.equal(idx.cpu(), cam[:, 1].cpu().topk(8).indices)
+    # (after a few steps on 6 slides the map is nearly flat and fp32 ties are common: compare the selected VALUES;
+    # tie order is covered where the reference fixes it, test_heatmaps_gpu / test_kernels_gpu)
+    col = cam[:, 1].cpu()
+    assert idx.shape == (8,) and len(set(idx.tolist())) == 8
+    assert torch.equal(vals.cpu(), col.topk(8).values) and torch.equal(col[idx.cpu().long()], vals.cpu())
 
 
 def test_crossval_on_resident_bags(cuda_device):
