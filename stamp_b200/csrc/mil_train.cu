@@ -323,6 +323,15 @@ cast_transpose_kernel(const float* __restrict__ w, int R, int C, uint16_t* __res
 
 // sum over bags of all pairwise token distances (class token at (0,0) included): the statistic the
 // training-mode _RunningMeanScaler consumes (vision_tranformer.py:23-31: mean over the [B,S,S] cdist).
+// grid (query blocks of 256, bags, key splits): the keys of a split are staged 256 at a time in shared memory (every
+// lane reads the same key: broadcast), four independent fp32 partial sums per thread, sqrt.approx (2^-22 relative:
+// the statistic is a mean over S^2 terms), fp64 from the 256-key partials upwards.
+constexpr int DIST_SPLITS = 8;
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;\n" : "=f"(r) : "f"(x));
+    return r;
+}
 __global__ void __launch_bounds__(256)
 dist_sum_kernel(const float2* __restrict__ coords_s, int S, double* __restrict__ out) {
     __shared__ float2 ck[256];
@@ -331,20 +340,33 @@ dist_sum_kernel(const float2* __restrict__ coords_s, int S, double* __restrict__
     const float2* c = coords_s + static_cast<long long>(b) * S;
     const int q = blockIdx.x * 256 + threadIdx.x;
     const float2 cq = (q < S) ? __ldg(c + q) : make_float2(0.f, 0.f);
+    const int per = ((S + DIST_SPLITS - 1) / DIST_SPLITS + 255) / 256 * 256;
+    const int k_begin = blockIdx.z * per, k_end = min(S, k_begin + per);
     double tot = 0.0;
-    for (int k0 = 0; k0 < S; k0 += 256) {
+    for (int k0 = k_begin; k0 < k_end; k0 += 256) {
         __syncthreads();
         const int k = k0 + threadIdx.x;
-        ck[threadIdx.x] = (k < S) ? __ldg(c + k) : make_float2(0.f, 0.f);
+        ck[threadIdx.x] = (k < k_end) ? __ldg(c + k) : make_float2(0.f, 0.f);
         __syncthreads();
-        const int n = min(256, S - k0);
-        float s = 0.f;
-        if (q < S)
-            for (int j = 0; j < n; ++j) {
-                const float dx = cq.x - ck[j].x, dy = cq.y - ck[j].y;
-                s += sqrtf(fmaf(dx, dx, dy * dy));
-            }
-        tot += static_cast<double>(s);
+        const int n = min(256, k_end - k0);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (int j = n & ~3; j < n; ++j) {
+            const float dx = cq.x - ck[j].x, dy = cq.y - ck[j].y;
+            s0 += sqrt_approx(fmaf(dx, dx, dy * dy));
+        }
+#pragma unroll 4
+        for (int j = 0; j < (n & ~3); j += 4) {
+            const float2 a = ck[j], a1 = ck[j + 1], a2 = ck[j + 2], a3 = ck[j + 3];
+            float dx = cq.x - a.x, dy = cq.y - a.y;
+            s0 += sqrt_approx(fmaf(dx, dx, dy * dy));
+            dx = cq.x - a1.x; dy = cq.y - a1.y;
+            s1 += sqrt_approx(fmaf(dx, dx, dy * dy));
+            dx = cq.x - a2.x; dy = cq.y - a2.y;
+            s2 += sqrt_approx(fmaf(dx, dx, dy * dy));
+            dx = cq.x - a3.x; dy = cq.y - a3.y;
+            s3 += sqrt_approx(fmaf(dx, dx, dy * dy));
+        }
+        if (q < S) tot += static_cast<double>((s0 + s1) + (s2 + s3));
     }
     tot = warp_sum_d(tot);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tot;
@@ -762,7 +784,7 @@ int stamp_pairwise_dist_mean(const float* coords, int B, int N, float* mean_out,
     double* dsum = reinterpret_cast<double*>(static_cast<uint8_t*>(workspace) + au(static_cast<size_t>(M) * 8));
     SB_TRY(mil_prepare(coords, nullptr, coords_s, nullptr, B, N, stream));
     if (cudaMemsetAsync(dsum, 0, sizeof(double), stream) != cudaSuccess) return SB_ERR_CUDA;
-    dim3 grid(static_cast<unsigned>((S + 255) / 256), B);
+    dim3 grid(static_cast<unsigned>((S + 255) / 256), B, DIST_SPLITS);
     dist_sum_kernel<<<grid, 256, 0, stream>>>(coords_s, static_cast<int>(S), dsum);
     dist_mean_finish_kernel<<<1, 1, 0, stream>>>(dsum, static_cast<double>(B) * S * S, mean_out);
     count_launch(2);
