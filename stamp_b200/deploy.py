@@ -33,16 +33,51 @@ def _stream_pool(device: torch.device, n: int) -> list[torch.cuda.Stream]:
     return _STREAMS[key]
 
 
+class _GraphedForward:
+    """One captured batch-1 forward (22 launches -> one graph launch) for a fixed bag shape on a fixed stream: static
+    input buffers the bag is copied into (straight from pinned host memory when it comes from the host), static
+    output.  Valid for the packed weights it was captured with (``model._packed`` identity)."""
+
+    def __init__(self, model: VisionTransformer, stream: torch.cuda.Stream, feats: Tensor, coords: Tensor, device):
+        self.feats = torch.empty((1, *feats.shape), dtype=feats.dtype, device=device)
+        self.coords = torch.empty((1, *coords.shape), dtype=torch.float32, device=device)
+        self.feats.copy_(feats, non_blocking=True)
+        self.coords.copy_(coords, non_blocking=True)
+        self._run(model)                      # eager once: packs the weights, sizes this stream's workspace
+        self.packed = model._packed
+        stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=stream):
+            self.probs = self._run(model)
+
+    def _run(self, model: VisionTransformer) -> Tensor:
+        return torch.softmax(model(self.feats, coords=self.coords, mask=None).float(), dim=1)
+
+    def __call__(self, feats: Tensor, coords: Tensor) -> Tensor:
+        self.feats[0].copy_(feats, non_blocking=True)
+        self.coords[0].copy_(coords, non_blocking=True)
+        self.graph.replay()
+        return self.probs.clone()
+
+
+_GRAPHS: dict[tuple, _GraphedForward] = {}
+_SEEN: set[tuple] = set()          # shapes that ran eagerly once: the next occurrence is captured
+_MAX_GRAPHS = 24
+
+
 @torch.inference_mode()
 def predict_bags(model: VisionTransformer, bags: Iterable[tuple[Tensor, Tensor]],
-                 device: torch.device | str = "cuda", n_streams: int = 3) -> Tensor:
+                 device: torch.device | str = "cuda", n_streams: int = 3, graphs: bool = True) -> Tensor:
     """``bags`` yields ``(feats [N, F] fp16 | fp32, coords [N, 2])`` tensors (one patient each, on the host or already
     on the device); returns the class probabilities ``[n_patients, C]`` on the host.
 
     Bags are independent batch-1 forwards (as in the reference's predict loop); they are issued round-robin on
     ``n_streams`` CUDA streams, each with its own workspace, so the host->device copy of one bag and the short,
     latency-bound kernels of another (a 4096-tile bag fills less than one wave of the GPU in most of its launches)
-    overlap the attention kernels of a third."""
+    overlap the attention kernels of a third.  With ``graphs`` a host-resident bag shape seen for the second time on
+    a stream is captured as a CUDA graph and replayed from then on, the bag being copied from pinned memory straight
+    into the graph's input buffer (validation loops and cohorts of fixed-size bags repeat their
+    shapes; a batch-1 forward is 22 launches of 4-75 us, so the host issue rate is what a graph saves)."""
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("predict_bags runs on a CUDA device only (no CPU fallback)")
@@ -54,8 +89,33 @@ def predict_bags(model: VisionTransformer, bags: Iterable[tuple[Tensor, Tensor]]
     out: list[Tensor] = []
     keep: list[tuple] = []             # pinned sources stay alive until their copies have run
     for i, (feats, coords) in enumerate(bags):
-        s = streams[i % len(streams)]
+        si = i % len(streams)
+        s = streams[si]
         with torch.cuda.stream(s):
+            key = (id(model), device.index, si, len(streams), tuple(feats.shape), feats.dtype)
+            # (device-resident bags run eagerly: measured 3 % faster than replaying through the static input buffer)
+            if graphs and not feats.is_cuda and feats.dtype in (torch.float16, torch.float32):
+                g = _GRAPHS.get(key)
+                if g is not None and g.packed is not model._packed:
+                    g = None                                   # weights changed since the capture
+                    del _GRAPHS[key]
+                if g is None and key in _SEEN:
+                    if len(_GRAPHS) >= _MAX_GRAPHS:
+                        _GRAPHS.clear()
+                        _SEEN.clear()
+                    src_f = feats if feats.is_cuda or feats.is_pinned() else feats.pin_memory()
+                    g = _GRAPHS[key] = _GraphedForward(model, s, src_f, coords.float(), device)
+                if len(_SEEN) > 4096:
+                    _SEEN.clear()
+                _SEEN.add(key)
+                if g is not None:
+                    if not feats.is_cuda:
+                        f = feats if feats.is_pinned() else feats.pin_memory()
+                        c = coords if coords.is_pinned() else coords.pin_memory()
+                        keep.append((f, c))
+                        feats, coords = f, c
+                    out.append(g(feats, coords.float() if coords.is_cuda else coords))
+                    continue
             if not feats.is_cuda:
                 f = feats if feats.is_pinned() else feats.pin_memory()
                 c = coords if coords.is_pinned() else coords.pin_memory()

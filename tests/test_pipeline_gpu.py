@@ -113,3 +113,46 @@ def test_crossval_on_resident_bags(cuda_device):
     label = {p.pid: p.label for p in pats}
     hits = sum(int(r.probs[i].argmax()) == label[pid] for r in res for i, pid in enumerate(r.test_patients))
     assert hits >= 30, hits
+
+
+def test_prefetch_to_device_keeps_order_and_values(cuda_device):
+    """The host->device feed of the training loop: batches arrive on the device in order, bit-identical, None entries
+    pass through, and the generator drains its queue at the end."""
+    from stamp_b200.bags import prefetch_to_device
+
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.randn(3, 50, 16, generator=g).half(), torch.rand(3, 50, 2, generator=g), None,
+                torch.eye(2)[torch.arange(3) % 2]) for _ in range(5)]
+    seen = 0
+    for i, (bags, coords, sizes, targets) in enumerate(prefetch_to_device(iter(batches), cuda_device, depth=3)):
+        assert bags.is_cuda and coords.is_cuda and targets.is_cuda and sizes is None
+        assert torch.equal(bags.cpu(), batches[i][0]) and torch.equal(coords.cpu(), batches[i][1])
+        seen += 1
+    assert seen == 5
+    assert list(prefetch_to_device(iter([]), cuda_device)) == []
+
+
+def test_predict_bags_graph_replay_matches_eager(cuda_device):
+    """deploy.predict_bags captures a repeated bag shape as a CUDA graph: same probabilities as the eager path, from
+    host and device bags, also after the weights change (the capture is dropped with the packed weights)."""
+    from stamp_b200 import deploy
+    from stamp_b200.mil import VisionTransformer, bump_weights_epoch
+
+    torch.manual_seed(3)
+    model = VisionTransformer(dim_output=3, dim_input=64, dim_model=128, n_layers=2, n_heads=2, dim_feedforward=128,
+                              dropout=0.0, use_alibi=True).to(cuda_device).eval()
+    g = torch.Generator().manual_seed(9)
+    bags = [(torch.randn(300, 64, generator=g).half(), torch.rand(300, 2, generator=g) * 5000) for _ in range(9)]
+    bags += [(torch.randn(77, 64, generator=g).half(), torch.rand(77, 2, generator=g) * 5000)]      # an odd one out
+    eager = deploy.predict_bags(model, iter(bags), cuda_device, graphs=False)
+    deploy._GRAPHS.clear(); deploy._SEEN.clear()
+    replay = deploy.predict_bags(model, iter(bags), cuda_device)                 # captures from the 4th bag on
+    assert len(deploy._GRAPHS) == 3 and torch.allclose(replay, eager, atol=1e-6)
+    dev_bags = [(f.to(cuda_device), c.to(cuda_device)) for f, c in bags]
+    assert torch.allclose(deploy.predict_bags(model, iter(dev_bags), cuda_device), eager, atol=1e-6)
+    with torch.no_grad():
+        model.mlp_head[0].bias[0].add_(1.0)          # (a shift of ALL logits would not move the softmax)
+    bump_weights_epoch()
+    after = deploy.predict_bags(model, iter(bags), cuda_device)
+    assert torch.allclose(after, deploy.predict_bags(model, iter(bags), cuda_device, graphs=False), atol=1e-6)
+    assert (after - eager).abs().max() > 1e-3
