@@ -549,6 +549,13 @@ def run_b200(args) -> None:
         crossval_out = crossval_block(dev, rank, world)
         torch.cuda.empty_cache()
 
+    # ---- the other tile encoders of the reference on the same kernels (rank 0, N = 1)
+    extractors_out = None
+    if rank == 0 and world == 1 and not args.skip_configs:
+        from bench_extra import extractors_block
+
+        extractors_out = extractors_block(dev, peak_tf)
+
     # ---- the reference's own GPU path (eager torch on this GPU) for the same three stages (rank 0, N = 1)
     torch_gpu = None
     if rank == 0 and world == 1 and not args.skip_mil and not args.skip_torch_baseline:
@@ -577,7 +584,8 @@ def run_b200(args) -> None:
                        "sharding": f"slides[rank::{world}], no data-path collective"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "mil": mil_out, "mil_train": train_out,
-            "other_configs": {"virchow2_cohort": cohort_out, "crossval": crossval_out, **(extra_out or {})},
+            "other_configs": {"virchow2_cohort": cohort_out, "crossval": crossval_out, **(extra_out or {}),
+                              "other_extractors": extractors_out},
             "torch_gpu_baseline": torch_gpu, "hbm_kernels": hbm_out,
         }
         print(json.dumps(line), flush=True)

@@ -305,7 +305,8 @@ int stamp_adamw_step(float* params, const float* grads, float* exp_avg, float* e
  * One stain matrix is fitted per group of `tiles_per_fit` consecutive tiles (<= 0: one fit over the
  * whole batch) and applied per pixel.  Optional outputs: he_out [G,3,2] (columns H, E),
  * maxc_out [G,2], valid_out [G] (0 = fewer than 16 tissue pixels: tiles passed through).
- * H*W*3 must be a multiple of 48; in/out 16-byte aligned; workspace 256-byte aligned.
+ * H*W*3 must be a multiple of 48; in/out 16-byte aligned; workspace 256-byte aligned; at most 65535 fit groups
+ * per call.  Seven launches, all asynchronous on `stream`.
  * ------------------------------------------------------------------------------------------- */
 size_t stamp_macenko_workspace_bytes(int n_tiles, int tiles_per_fit);
 int stamp_macenko_u8(const uint8_t* in, uint8_t* out, int n_tiles, int H, int W, int tiles_per_fit,
