@@ -178,11 +178,13 @@ dropout_mask_kernel(uint8_t* __restrict__ out, long long n, uint32_t thresh, uin
 
 // LayerNorm backward, one warp per row:  dx += rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;
 // dgamma += sum_rows dy * xhat,  dbeta += sum_rows dy  (register partials per lane, smem reduce, atomics).
+// out16 (optional): the updated dx as bf16 through a dropout mask (thresh 0: plain cast) -- the operand of the next
+// weight-gradient / data-gradient GEMMs, which would otherwise be a separate pass over dx (mask_cast_kernel).
 template <int MAXV>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int d,
-              float eps) {
+              float eps, uint16_t* __restrict__ out16, uint32_t thresh, float mscale, uint64_t sseed) {
     extern __shared__ float sh[];   // 2 * d
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int nvec = d >> 2;
@@ -247,6 +249,16 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
                 o.z += rstd * (g[i].z - m1 - v[i].z * m2);
                 o.w += rstd * (g[i].w - m1 - v[i].w * m2);
                 *reinterpret_cast<float4*>(dr + idx * 4) = o;
+                if (out16 != nullptr) {
+                    const long long e0 = row * d + idx * 4;     // element index of the mask = position in [M, d]
+                    if (thresh != 0u) {
+                        o.x = keep_elem(sseed, e0 + 0, thresh) ? o.x * mscale : 0.f;
+                        o.y = keep_elem(sseed, e0 + 1, thresh) ? o.y * mscale : 0.f;
+                        o.z = keep_elem(sseed, e0 + 2, thresh) ? o.z * mscale : 0.f;
+                        o.w = keep_elem(sseed, e0 + 3, thresh) ? o.w * mscale : 0.f;
+                    }
+                    *reinterpret_cast<uint2*>(out16 + e0) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+                }
             }
         }
     }
@@ -662,14 +674,17 @@ int mask_cast(const float* in, uint16_t* out, long long n, uint32_t thresh, floa
 }
 
 int ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
-           int rows, int d, cudaStream_t stream) {
+           int rows, int d, cudaStream_t stream, uint16_t* out16 = nullptr, uint32_t thresh = 0u, float mscale = 1.f,
+           uint64_t sseed = 0) {
     if ((d % 4) != 0 || d > 1024) return SB_ERR_UNSUPPORTED;
     int blocks = (rows + 7) / 8;
     if (blocks > 148 * 4) blocks = 148 * 4;
     const size_t sh = 2 * static_cast<size_t>(d) * sizeof(float);
-    ProfScope prof(PROF_ROWOP, static_cast<double>(rows) * d * 16.0, stream);
-    if (d <= 512) ln_bwd_kernel<4><<<blocks, 256, sh, stream>>>(dy, x, gamma, dx, dgamma, dbeta, rows, d, 1e-5f);
-    else ln_bwd_kernel<8><<<blocks, 256, sh, stream>>>(dy, x, gamma, dx, dgamma, dbeta, rows, d, 1e-5f);
+    ProfScope prof(PROF_ROWOP, static_cast<double>(rows) * d * (out16 != nullptr ? 18.0 : 16.0), stream);
+    if (d <= 512)
+        ln_bwd_kernel<4><<<blocks, 256, sh, stream>>>(dy, x, gamma, dx, dgamma, dbeta, rows, d, 1e-5f, out16, thresh, mscale, sseed);
+    else
+        ln_bwd_kernel<8><<<blocks, 256, sh, stream>>>(dy, x, gamma, dx, dgamma, dbeta, rows, d, 1e-5f, out16, thresh, mscale, sseed);
     count_launch();
     return last_status();
 }
@@ -980,7 +995,10 @@ int stamp_mil_train_backward(const StampMilConfig* cfg, const StampMilTrainTop* 
         float* x_mid = xbuf(2 * l + 1);
 
         // ---- feed-forward block: x_out = x_mid + drop(ff2(drop(gelu(ff1(LN2(x_mid)))))) ----
-        SB_TRY(mask_cast(dx, g16b, Md, th_ff, ik_ff, site_seed(step->seed, 2 + 2 * l), stream));   // dy [M,d]
+        // dy [M,d] = bf16(dropout mask . dx): written by the LayerNorm backward of the layer above (below), by a
+        // pass of its own only for the top layer
+        if (l == cfg->n_layers - 1)
+            SB_TRY(mask_cast(dx, g16b, Md, th_ff, ik_ff, site_seed(step->seed, 2 + 2 * l), stream));
         SB_TRY(wgrad(g16b, d, h, ff, gy.ff2_w, ff, M, d, ff, wsc, wsb, stream));
         SB_TRY(colsum_bf16(g16b, d, M, d, gy.ff2_b, stream));
         {
@@ -999,10 +1017,8 @@ int stamp_mil_train_backward(const StampMilConfig* cfg, const StampMilTrainTop* 
             GemmParams p = gp_bf16(M, d, ff, ST_32, g32, d, nullptr);                               // d xn2 [M,d]
             SB_TRY(gemm_tn(g16a, ff, lb + L.l_w_ff1T, ff, p, stream));
         }
-        SB_TRY(ln_bwd(g32, x_mid, y.ln2_w, dx, gy.ln2_w, gy.ln2_b, M, d, stream));                  // dx = d x_mid
-
-        // ---- attention block: x_mid = x_in + fc(attn(qkv(LN1(x_in)))) ----
-        SB_TRY(mask_cast(dx, g16b, Md, 0u, 1.f, 0, stream));
+        // dx = d x_mid, and its bf16 copy for the attention block: x_mid = x_in + fc(attn(qkv(LN1(x_in))))
+        SB_TRY(ln_bwd(g32, x_mid, y.ln2_w, dx, gy.ln2_w, gy.ln2_b, M, d, stream, g16b));
         SB_TRY(wgrad(g16b, d, att, d, gy.fc_w, d, M, d, d, wsc, wsb, stream));
         SB_TRY(colsum_bf16(g16b, d, M, d, gy.fc_b, stream));
         {
@@ -1028,7 +1044,12 @@ int stamp_mil_train_backward(const StampMilConfig* cfg, const StampMilTrainTop* 
             GemmParams p = gp_bf16(M, d, 3 * d, ST_32, g32, d, nullptr);                            // d xn1 [M,d]
             SB_TRY(gemm_tn(g16c, 3LL * d, lb + L.l_w_qkvT, 3LL * d, p, stream));
         }
-        SB_TRY(ln_bwd(g32, x_in, y.ln1_w, dx, gy.ln1_w, gy.ln1_b, M, d, stream));                   // dx = d x_in
+        // dx = d x_in; for the layer below also dy of its feed-forward block (its output dropout mask applied)
+        if (l > 0)
+            SB_TRY(ln_bwd(g32, x_in, y.ln1_w, dx, gy.ln1_w, gy.ln1_b, M, d, stream, g16b, th_ff, ik_ff,
+                          site_seed(step->seed, 2 + 2 * (l - 1))));
+        else
+            SB_TRY(ln_bwd(g32, x_in, y.ln1_w, dx, gy.ln1_w, gy.ln1_b, M, d, stream));
     }
 
     // class token rows, then project_features
