@@ -46,9 +46,10 @@ except ImportError:
         VIRCHOW2 = "virchow2"
 
     class Encoder(ABC):  # type: ignore[no-redef]
-        """Stand-alone stand-in for stamp.encoding.encoder.Encoder (same constructor and abstract methods,
-        encoder/__init__.py:29-41); only used when the ``stamp`` package is not installed.  The feature-file walk
-        (``encode_slides_`` / ``encode_patients_``) is the reference's own code and needs its package."""
+        """Stand-alone stand-in for stamp.encoding.encoder.Encoder (same constructor, abstract methods and
+        feature-file walk, encoder/__init__.py:29-229); only used when the ``stamp`` package is not installed.
+        Feature files go through ``stamp_b200.features`` (h5lite) instead of h5py; the output folder carries no code
+        hash of the reference's sources (``generate_hash`` appends this module's own)."""
 
         def __init__(self, model, identifier, precision: torch.dtype, required_extractors: list) -> None:
             self.model, self.identifier = model, identifier
@@ -60,11 +61,81 @@ except ImportError:
         @abstractmethod
         def _generate_patient_embedding(self, feats_list: list[Tensor], device, **kwargs) -> np.ndarray: ...
 
-        def encode_slides_(self, *args, **kwargs) -> None:
-            raise ImportError("encode_slides_ is STAMP's own h5 walk (src/stamp/encoding/encoder/__init__.py:42-93): "
-                              "install the stamp package; stamp_b200 then subclasses its Encoder")
+        def _encode_dir(self, output_dir, level: str, generate_hash: bool):
+            from pathlib import Path
 
-        encode_patients_ = encode_slides_
+            name = f"{self.identifier}-{level}"
+            if generate_hash:
+                name += f"-{_code_hash()}"
+            out = Path(output_dir) / name
+            out.mkdir(parents=True, exist_ok=True)
+            return out
+
+        def _validate_and_read_features(self, h5_path: str):
+            from . import features
+
+            feats, coords, extractor = features.read_tile_features(h5_path)
+            if extractor not in self.required_extractors:
+                raise ValueError(f"Features must be extracted with one of {self.required_extractors}. "
+                                 f"Features located in {h5_path} are extracted with {extractor}")
+            return torch.from_numpy(feats).to(dtype=self.precision), coords
+
+        def _save_features_(self, output_path, feats: np.ndarray, feat_type: str) -> None:
+            from . import features
+
+            features.write_encoded_features(output_path, feats, encoder=str(self.identifier), precision=self.precision,
+                                            feat_type=feat_type, code_hash=_code_hash())
+
+        def encode_slides_(self, output_dir, feat_dir, device, generate_hash: bool = False, **kwargs) -> None:
+            """encoder/__init__.py:42-93: every ``*.h5`` under ``feat_dir`` -> one slide embedding file under
+            ``output_dir/<identifier>-slide``, keeping the relative folder structure; existing outputs are skipped,
+            files from the wrong extractor are reported and skipped."""
+            import logging
+            from pathlib import Path
+
+            encode_dir = self._encode_dir(output_dir, "slide", generate_hash)
+            self.model.to(device).eval()
+            for h5_path in sorted(Path(feat_dir).rglob("*.h5")):
+                output_path = (encode_dir / h5_path.relative_to(feat_dir)).with_suffix(".h5")
+                if output_path.exists():
+                    continue
+                try:
+                    feats, coords = self._validate_and_read_features(str(h5_path))
+                except ValueError as e:
+                    logging.getLogger("stamp").warning(str(e))
+                    continue
+                emb = self._generate_slide_embedding(feats, device, coords=coords)
+                self._save_features_(output_path, emb, "slide")
+
+        def encode_patients_(self, output_dir, feat_dir, slide_table_path, patient_label: str, filename_label: str,
+                             device, generate_hash: bool = False, **kwargs) -> None:
+            """encoder/__init__.py:95-156: the slide table groups feature files by patient; one embedding file per
+            patient under ``output_dir/<identifier>-pat``."""
+            import os
+            from pathlib import Path
+
+            import pandas as pd
+
+            encode_dir = self._encode_dir(output_dir, "pat", generate_hash)
+            self.model.to(device).eval()
+            table_path = Path(slide_table_path)
+            table = pd.read_excel(table_path) if table_path.suffix == ".xlsx" else pd.read_csv(table_path)
+            for patient_id, group in table.groupby(patient_label):
+                output_path = (encode_dir / str(patient_id)).with_suffix(".h5")
+                if output_path.exists():
+                    continue
+                feats_list = [self._validate_and_read_features(os.path.join(feat_dir, row[filename_label]))[0]
+                              for _, row in group.iterrows()]
+                if not feats_list:
+                    continue
+                emb = self._generate_patient_embedding(feats_list, device, **kwargs)
+                self._save_features_(output_path, emb, "patient")
+
+    def _code_hash() -> str:
+        import hashlib
+        from pathlib import Path
+
+        return hashlib.sha256(Path(__file__).read_bytes()).hexdigest()[:8]
 
 _EagleBase = Encoder
 if BOUND_TO_REFERENCE:

@@ -168,3 +168,31 @@ def extract_slide_features(extractor: Extractor, tiles_u8: Tensor, device: torch
     feats_host.copy_(feats_dev, non_blocking=True)
     main.synchronize()
     return feats_host
+
+
+def extract_to_feature_files(extractor: Extractor, slides, output_dir: str | Path, *, tile_size_um: float = 256.0,
+                             tile_size_px: int = 224, device: torch.device | str = "cuda", batch_size: int = 192,
+                             code_hash: str | None = None, rank: int = 0, world_size: int = 1) -> list[Path]:
+    """The slide loop of ``extract_`` (src/stamp/preprocessing/__init__.py:276-366) downstream of tiling: ``slides``
+    yields ``(relative_name, tiles_u8 [N, H, W, 3], coords_um [N, 2])``; every slide becomes
+    ``output_dir/<identifier>[-<code_hash>]/<relative_name>.h5`` with the reference's datasets and attributes.
+    Slides whose file already exists, and slides without tiles, are skipped like in the reference (:281-286,337-339).
+    The file of slide i is written by a ``FeatureWriter`` thread while slide i+1 runs on the GPU; with
+    ``world_size > 1`` rank r takes the slides r, r + world_size, ... (no data-path collective; pass an iterable
+    already sharded by ``sharding.shard_lpt`` for size-aware assignment and leave ``world_size`` at 1)."""
+    from .features import FeatureWriter
+
+    out_dir = Path(output_dir) / (f"{extractor.identifier}-{code_hash}" if code_hash else str(extractor.identifier))
+    written: list[Path] = []
+    with FeatureWriter() as writer:
+        for i, (name, tiles_u8, coords_um) in enumerate(slides):
+            if i % world_size != rank:
+                continue
+            path = (out_dir / name).with_suffix(".h5")
+            if path.exists() or len(tiles_u8) == 0:
+                continue
+            feats = extract_slide_features(extractor, tiles_u8, device=device, batch_size=batch_size)
+            writer.submit(path, feats, coords_um, extractor=str(extractor.identifier), tile_size_um=tile_size_um,
+                          tile_size_px=tile_size_px, code_hash=code_hash or "")
+            written.append(path)
+    return written

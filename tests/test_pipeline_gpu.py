@@ -156,3 +156,47 @@ def test_predict_bags_graph_replay_matches_eager(cuda_device):
     after = deploy.predict_bags(model, iter(bags), cuda_device)
     assert torch.allclose(after, deploy.predict_bags(model, iter(bags), cuda_device, graphs=False), atol=1e-6)
     assert (after - eager).abs().max() > 1e-3
+
+
+def test_feature_files_between_extraction_and_training(cuda_device, tmp_path):
+    """BASELINE configs[0] end to end with the files in between: tiles -> ``extract_to_feature_files`` (``.h5`` per slide
+    with the reference's datasets / attributes, written by the background thread) -> ``load_cohort_to_device`` (one
+    HBM-resident fp16 tensor) -> deploy on the resident bags; the file round trip is bit-exact."""
+    from oracle import vit_oracle as vo
+    from stamp_b200 import features, h5lite
+    from stamp_b200.deploy import predict_bags
+    from stamp_b200.extractor import Extractor, extract_slide_features, extract_to_feature_files, pil_to_u8_hwc
+    from stamp_b200.mil import VisionTransformer
+    from stamp_b200.vit import TileEncoder, VitArch
+
+    torch.manual_seed(0)
+    cfg = vo.tiny_config(depth=2)
+    arch = VitArch(cfg.name, patch=cfg.patch, dim=cfg.dim, depth=cfg.depth, heads=cfg.heads,
+                   mlp_hidden=cfg.mlp_hidden, mlp=cfg.mlp, reg_tokens=cfg.reg_tokens)
+    ext = Extractor(model=TileEncoder(arch, vo.make_weights(cfg), max_batch=32).to(cuda_device).eval(),
+                    transform=pil_to_u8_hwc, identifier="tiny")
+    slides = []
+    for s in range(4):
+        n = 10 + 7 * s
+        cells = torch.randperm(64, generator=torch.Generator().manual_seed(s))[:n]
+        coords = torch.stack([(cells % 8).float(), (cells // 8).float()], dim=-1) * 256.0
+        slides.append((f"cohort/slide_{s}.svs", vo.synthetic_tiles(n, seed=s), coords))
+    slides.append(("cohort/empty.svs", torch.zeros((0, 224, 224, 3), dtype=torch.uint8), torch.zeros((0, 2))))
+    written = extract_to_feature_files(ext, slides, tmp_path, device=cuda_device, batch_size=16, code_hash="0a1b2c3d")
+    assert [p.relative_to(tmp_path).as_posix() for p in written] == [f"tiny-0a1b2c3d/cohort/slide_{s}.h5" for s in range(4)]
+    assert extract_to_feature_files(ext, slides, tmp_path, device=cuda_device, code_hash="0a1b2c3d") == []  # all exist
+    direct = extract_slide_features(ext, slides[2][1], cuda_device, batch_size=16)
+    with h5lite.File(written[2]) as h5:
+        assert h5["feats"].dtype == torch.zeros(1).half().numpy().dtype and h5.attrs["extractor"] == "tiny"
+        assert h5.attrs["tile_size_px"] == 224 and h5.attrs["feat_type"] == "tile"
+        assert torch.equal(torch.from_numpy(h5["feats"][()]), direct)
+        assert torch.equal(torch.from_numpy(features.get_coords(h5).coords_um), slides[2][2])
+    cohort = features.load_cohort_to_device({"p0": written[:2], "p1": written[2:]}, cuda_device)
+    assert cohort.feats.is_cuda and cohort.offsets == [0, 10 + 17, 10 + 17 + 24 + 31]
+    f1, c1 = cohort.bag(1)
+    assert torch.equal(f1[:24].cpu(), direct) and torch.equal(c1[:24].cpu(), slides[2][2])
+    model = VisionTransformer(dim_output=2, dim_input=arch.dim, dim_model=128, n_layers=2, n_heads=2,
+                              dim_feedforward=128, dropout=0.0, use_alibi=True).to(cuda_device).eval()
+    probs = predict_bags(model, (cohort.bag(i) for i in range(len(cohort))), cuda_device)
+    host = predict_bags(model, (features.read_bag(ps) for ps in (written[:2], written[2:])), cuda_device)
+    assert probs.shape == (2, 2) and torch.allclose(probs, host, atol=1e-6)
