@@ -67,6 +67,21 @@ def has_enough_texture(tiles: Tensor, cutoff: float) -> Tensor:
     return edge_scores(tiles) >= cutoff
 
 
+def foreground_coords(slide_dimensions: tuple[int, int], tile_size_slide_px: int, thumbnail,
+                      brightness_cutoff: int | None) -> list[tuple[int, int]]:
+    """Brightness rejection of ``_foreground_coords`` (src/stamp/preprocessing/tiling.py:250-277): level-0 pixel
+    coordinates (x, y) of the tiles whose thumbnail pixel is darker than ``brightness_cutoff`` (all tiles for
+    ``None``), in the reference's row-major order.  ``thumbnail`` is what ``slide.get_thumbnail(2 * grid)`` returns
+    (a PIL image): it is resized to one pixel per tile and converted to 32-bit grayscale exactly as there.  A few
+    hundred pixels per slide -- host work, nothing for the GPU."""
+    w, h = int(slide_dimensions[0]), int(slide_dimensions[1])
+    grid = (-(-w // tile_size_slide_px), -(-h // tile_size_slide_px))
+    gray = np.array(thumbnail.resize(grid).convert("I"))
+    fg = gray < brightness_cutoff if brightness_cutoff is not None else np.ones_like(gray, dtype=bool)
+    ys, xs = np.nonzero(fg[: len(range(0, h, tile_size_slide_px)), : len(range(0, w, tile_size_slide_px))])
+    return [(int(x) * tile_size_slide_px, int(y) * tile_size_slide_px) for y, x in zip(ys, xs)]
+
+
 def tiles_from_cache_file(cache_file_path: str | Path, *, max_workers: int = 8,
                           pin_memory: bool = True) -> tuple[Tensor, Tensor, dict]:
     """Reads a STAMP tile cache (``_tiles_from_cache_file``, src/stamp/preprocessing/tiling.py:380-406: a zip with

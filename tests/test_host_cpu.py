@@ -248,6 +248,44 @@ def test_bag_plumbing_matches_the_reference_functions():
         assert torch.equal(a, b)
 
 
+def test_brightness_rejection_matches_the_reference_function():
+    """tiling.foreground_coords against the reference's _foreground_coords (src/stamp/preprocessing/tiling.py:250-277)
+    executed from its source with a stand-in slide object (openslide is not installed)."""
+    import numpy as np
+    from PIL import Image
+
+    ref_file = Path("/root/reference/src/stamp/preprocessing/tiling.py")
+    if not ref_file.exists():
+        pytest.skip("reference checkout not present on this machine")
+    from stamp_b200.tiling import foreground_coords
+
+    ref = _reference_functions(ref_file, ["_foreground_coords"])
+    import numpy.typing as npt
+
+    ref.update(np=np, cast=lambda _t, v: v, npt=npt,
+               _XYCoords=lambda x, y: (int(x), int(y)), SlidePixels=int)
+    rng = np.random.default_rng(3)
+    for (w, h), tile in [((5000, 3100), 448), ((4096, 4096), 512), ((1000, 700), 333)]:
+        base = rng.integers(0, 256, size=(h // 20, w // 20, 3), dtype=np.uint8)
+        base[: h // 60] = 250                                     # a bright background band
+
+        class Slide:
+            dimensions = (w, h)
+
+            @staticmethod
+            def get_thumbnail(size):
+                img = Image.fromarray(base)
+                img.thumbnail(size)                                # what openslide's get_thumbnail ends with
+                return img
+
+        for cutoff in (224, 128, None):
+            want = list(ref["_foreground_coords"](Slide, tile, cutoff))
+            grid = np.ceil(np.array(Slide.dimensions) / tile).astype(np.uint32)
+            got = foreground_coords(Slide.dimensions, tile, Slide.get_thumbnail(tuple(grid * 2)), cutoff)
+            assert got == want and (cutoff is not None or len(got) == grid[0] * grid[1])
+        assert 0 < len(foreground_coords(Slide.dimensions, tile, Slide.get_thumbnail(tuple(grid * 2)), 224)) < grid[0] * grid[1]
+
+
 def test_titan_wrapper_input_preparation():
     """titan.py:47-53 (um -> int64 px) and :131-168 (virtual slide: slides side by side along x)."""
     import numpy as np
