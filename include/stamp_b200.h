@@ -325,6 +325,25 @@ int stamp_tile_texture_u8(const uint8_t* tiles, int n_tiles, int H, int W, int l
                           int* edge_count, uint8_t* edges_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Resampling of uint8 RGB tiles (extractor transforms that resize the tile before the model), bit-exact with
+ * Pillow's Image.resize for 8-bit images.
+ * replaces: transforms.Resize(256, interpolation=BICUBIC) + transforms.CenterCrop(224),
+ *   src/stamp/preprocessing/extractor/gigapath.py:20-27 (torchvision -> PIL Image.resize -> Resample.c:
+ *   horizontal then vertical pass, 22-bit fixed-point coefficients, intermediate image rounded to uint8).
+ * tiles uint8 [n_tiles, Hin, Win, 3]; out uint8 [n_tiles, Hc, Wc, 3] = rows crop_y .. crop_y+Hc and columns
+ * crop_x .. crop_x+Wc of the resampled image.  coef_* int32 [out_size, ksize] (coefficients scaled by 2^22),
+ * bounds_* int32 [out_size, 2] (first input index, tap count), both on the device, as Pillow's precompute_coeffs /
+ * normalize_coeffs_8bpc produce them (stamp_b200/resize.py computes them in double).  rows_per_strip output rows
+ * per CTA; max_in_rows = the most input rows any strip needs.  stamp_resize_u8_smem_bytes: dynamic shared memory
+ * of the launch (0 for invalid arguments; must not exceed 227 KB).
+ * ------------------------------------------------------------------------------------------- */
+size_t stamp_resize_u8_smem_bytes(int Win, int Wc, int ksize_x, int max_in_rows);
+int stamp_resize_u8(const uint8_t* tiles, int n_tiles, int Hin, int Win, uint8_t* out, int Hc, int Wc,
+                    int crop_y, int crop_x, const int* coef_x, const int* bounds_x, int ksize_x,
+                    const int* coef_y, const int* bounds_y, int ksize_y, int rows_per_strip, int max_in_rows,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Slide-level pooling.
  * stamp_gated_attn_pool -- CHIEF's gated-attention MIL pooling:
  *   h = ReLU(W1 x + b1); A_raw = Wc (tanh(Wa h + ba) * sigmoid(Wb h + bb)) + bc;

@@ -97,6 +97,10 @@ UNI2 = VitConfig("uni2", patch=14, dim=1536, depth=24, heads=24, mlp_hidden=8192
 H_OPTIMUS = VitConfig("h_optimus_0", patch=14, dim=1536, depth=40, heads=24, mlp_hidden=8192, mlp="swiglu",
                       reg_tokens=4, no_embed_class=True, mean=(0.707223, 0.578729, 0.703617),
                       std=(0.211883, 0.230117, 0.177517))
+# Prov-GigaPath tile encoder, src/stamp/preprocessing/extractor/gigapath.py:14-35: timm vit_giant_patch14_dinov2 with the
+# hub config's patch_size 16 / img_size 224 (embed 1536, depth 40, 24 heads, SwiGLUPacked int(1536 * 5.33334) = 8192,
+# class token with its own position row); its transform resamples the tile first (oracle/resize_oracle.py)
+GIGAPATH = VitConfig("gigapath", patch=16, dim=1536, depth=40, heads=24, mlp_hidden=8192, mlp="swiglu")
 
 
 def tiny_config(mlp: str = "gelu", reg_tokens: int = 0, patch: int = 16, depth: int = 2,

@@ -6,7 +6,7 @@ accepts an instance directly (src/stamp/preprocessing/__init__.py:117,237-238), 
 the device, calls ``model(batch)`` under ``inference_mode`` and stores ``.half().cpu()``
 (:243,322-327).  ``identifier`` is what lands in the output folder name and the ``extractor`` h5
 attribute, so the factories below keep the reference's identifiers (the ``ExtractorName`` values
-"uni", "virchow2", "uni2", "h-optimus-0", "h-optimus-1"; src/stamp/preprocessing/config.py:13-33).
+"uni", "virchow2", "uni2", "h-optimus-0", "h-optimus-1", "gigapath"; src/stamp/preprocessing/config.py:13-33).
 When ``stamp`` is importable the factories return instances of the reference's own ``Extractor``.
 
 The transform returns the tile as a uint8 HWC tensor (legal: the reference's ``empty`` extractor
@@ -25,7 +25,7 @@ import numpy as np
 import torch
 from torch import Tensor, nn
 
-from .vit import (H_OPTIMUS_ARCH, UNI2_ARCH, UNI_ARCH, VIRCHOW2_ARCH, TileEncoder, VitArch,
+from .vit import (GIGAPATH_ARCH, H_OPTIMUS_ARCH, UNI2_ARCH, UNI_ARCH, VIRCHOW2_ARCH, TileEncoder, VitArch,
                   random_state_dict)
 
 ExtractorModel = TypeVar("ExtractorModel", bound=nn.Module)
@@ -126,6 +126,13 @@ def h_optimus_1(weights=None, max_batch: int = 64) -> Extractor[TileEncoder]:
     """H-optimus-1, same architecture and preprocessing (reference: .../extractor/h_optimus_1.py)."""
     return _make(H_OPTIMUS_ARCH, "h-optimus-1", weights, "hf-hub:bioptimus/H-optimus-1",
                  dict(init_values=1e-5, dynamic_img_size=False), max_batch)
+
+
+def gigapath(weights=None, max_batch: int = 64) -> Extractor[TileEncoder]:
+    """Prov-GigaPath tile encoder, ViT-g/16 (reference: .../extractor/gigapath.py:14-35).  Its transform
+    (Resize(256, BICUBIC) + CenterCrop(224) + ToTensor + Normalize) runs on the GPU: the resampling bit-exact with
+    Pillow (stamp_b200/resize.py), the rest inside the patch kernel."""
+    return _make(GIGAPATH_ARCH, "gigapath", weights, "hf_hub:prov-gigapath/prov-gigapath", {}, max_batch)
 
 
 def extract_slide_features(extractor: Extractor, tiles_u8: Tensor, device: torch.device | str = "cuda",

@@ -39,6 +39,7 @@ class VitArch:
     mean: tuple = IMAGENET_MEAN
     std: tuple = IMAGENET_STD
     no_embed_class: bool = False  # timm: pos_embed has n_patches rows, prefix tokens get no position
+    pre_resize: int = 0  # > 0: transforms.Resize(pre_resize, BICUBIC) + CenterCrop(img) ahead of the model (GigaPath)
 
     @property
     def n_patches(self) -> int:
@@ -82,6 +83,10 @@ UNI2_ARCH = VitArch("uni2", patch=14, dim=1536, depth=24, heads=24, mlp_hidden=8
 H_OPTIMUS_ARCH = VitArch("h_optimus", patch=14, dim=1536, depth=40, heads=24, mlp_hidden=8192, mlp="swiglu",
                          reg_tokens=4, no_embed_class=True, mean=(0.707223, 0.578729, 0.703617),
                          std=(0.211883, 0.230117, 0.177517))
+# gigapath.py:14-35: timm vit_giant_patch14_dinov2 with patch 16 at 224 px (embed 1536, depth 40, 24 heads, SwiGLUPacked
+# 8192, class token inside the position table); the transform's Resize(256, BICUBIC) + CenterCrop(224) runs on the GPU
+GIGAPATH_ARCH = VitArch("gigapath", patch=16, dim=1536, depth=40, heads=24, mlp_hidden=8192, mlp="swiglu",
+                        pre_resize=256)
 
 
 class StampVitConfig(C.Structure):
@@ -225,7 +230,7 @@ class TileEncoder(nn.Module):
         self._structs = (cfg, w, blocks)
 
     def launches_per_batch(self) -> int:
-        return 3 + 7 * self.arch.depth + 1
+        return 3 + 7 * self.arch.depth + 1 + (1 if self.arch.pre_resize else 0)
 
     @torch.no_grad()
     def forward(self, tiles: Tensor) -> Tensor:
@@ -238,6 +243,10 @@ class TileEncoder(nn.Module):
             tiles = tiles.permute(0, 2, 3, 1)
         tiles = tiles.contiguous()
         a = self.arch
+        if a.pre_resize:
+            from .resize import resize_center_crop
+
+            tiles = resize_center_crop(tiles, a.pre_resize, a.img)
         if tiles.dim() != 4 or tiles.shape[1:] != (a.img, a.img, 3):
             raise ValueError(f"expected tiles [B,{a.img},{a.img},3], got {tuple(tiles.shape)}")
         lib = _bind()
