@@ -280,11 +280,11 @@ def torch_gpu_block(dev, ours: dict) -> dict:
 def extractors_block(dev, peak_tf: float, batch: int = 96) -> dict:
     """the other tile encoders the reference ships (uni2.py:18-32, h_optimus_0.py:14-28) on the same
     kernels -- device-resident tiles/s at batch 96 with random-init weights of the architecture."""
-    from stamp_b200.vit import H_OPTIMUS_ARCH, UNI2_ARCH, TileEncoder, random_state_dict
+    from stamp_b200.vit import GIGAPATH_ARCH, H_OPTIMUS_ARCH, UNI2_ARCH, TileEncoder, random_state_dict
 
     out = {}
     tiles = torch.randint(0, 255, (batch, 224, 224, 3), dtype=torch.uint8, device=dev)
-    for name, arch in (("uni2_h", UNI2_ARCH), ("h_optimus_0", H_OPTIMUS_ARCH)):
+    for name, arch in (("uni2_h", UNI2_ARCH), ("h_optimus_0", H_OPTIMUS_ARCH), ("gigapath", GIGAPATH_ARCH)):
         enc = TileEncoder(arch, random_state_dict(arch), max_batch=batch).to(dev).eval()
         for _ in range(3):
             enc(tiles)
@@ -300,6 +300,7 @@ def extractors_block(dev, peak_tf: float, batch: int = 96) -> dict:
                      "roofline_frac": tps * arch.flops_per_tile() / 1e12 / peak_tf}
         del enc
         torch.cuda.empty_cache()
-    out["note"] = "ViT-H/14 (UNI2-h, 24 blocks) and ViT-g/14 (H-optimus-0, 40 blocks): SwiGLU, 8 / 4 register tokens, " \
-                  "head dimension 64, same GEMM / attention / LayerNorm kernels as UNI and Virchow2"
+    out["note"] = "ViT-H/14 (UNI2-h, 24 blocks), ViT-g/14 (H-optimus-0, 40 blocks) and ViT-g/16 (Prov-GigaPath, 40 " \
+                  "blocks, incl. its Resize(256, bicubic) + CenterCrop(224) on the GPU): SwiGLU, 8 / 4 / 0 register " \
+                  "tokens, head dimension 64, same GEMM / attention / LayerNorm kernels as UNI and Virchow2"
     return out
