@@ -547,7 +547,7 @@ def run_b200(args) -> None:
         del mt, mo_, px
 
     # ---- BASELINE configs[2] and configs[3] as specified, every rank takes part (bench_extra.py)
-    cohort_out = crossval_out = None
+    cohort_out = crossval_out = encoding_out = None
     if not args.skip_mil and not args.skip_configs:
         from bench_extra import cohort_block, crossval_block
 
@@ -556,6 +556,9 @@ def run_b200(args) -> None:
         torch.cuda.empty_cache()
         crossval_out = crossval_block(dev, rank, world)
         torch.cuda.empty_cache()
+        from bench_extra import encoding_block
+
+        encoding_out = encoding_block(dev, rank, world)
 
     # ---- the other tile encoders of the reference on the same kernels (rank 0, N = 1)
     extractors_out = None
@@ -592,7 +595,8 @@ def run_b200(args) -> None:
                        "sharding": f"slides[rank::{world}], no data-path collective"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "mil": mil_out, "mil_train": train_out,
-            "other_configs": {"virchow2_cohort": cohort_out, "crossval": crossval_out, **(extra_out or {}),
+            "other_configs": {"virchow2_cohort": cohort_out, "crossval": crossval_out, "slide_encoding": encoding_out,
+                              **(extra_out or {}),
                               "other_extractors": extractors_out},
             "torch_gpu_baseline": torch_gpu, "hbm_kernels": hbm_out,
         }

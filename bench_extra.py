@@ -277,6 +277,69 @@ def torch_gpu_block(dev, ours: dict) -> dict:
     return out
 
 
+def encoding_block(dev, rank: int, world: int, slides_per_gpu: int = 32) -> dict | None:
+    """SURVEY.md 8e, slide-level encoding: the cohort's slides (2 000..10 000 tiles of 768-d features, seed 7) are
+    sharded by tile count (``shard_lpt``, no collective); every rank runs the reference's ``encode_slides_`` walk
+    (encoding/encoder/__init__.py:42-93) over ITS feature files with the CHIEF encoder: read ``.h5`` -> host->device
+    -> gated-attention pooling kernels -> device->host -> slide-level ``.h5``.  The per-rank feature files are written
+    before the timed region (they are the input of this stage)."""
+    import shutil
+    import tempfile
+    from pathlib import Path
+
+    import torch.distributed as dist
+
+    from stamp_b200 import features
+    from stamp_b200.encoder import ChiefB200
+    from stamp_b200.sharding import shard_lpt
+
+    sizes = cohort_sizes()[: min(256, slides_per_gpu * world)]
+    mine = shard_lpt(list(range(len(sizes))), sizes, rank, world)
+    gen = torch.Generator().manual_seed(3)
+    sd = {"attention_net.0.weight": torch.randn(512, 768, generator=gen) * 0.04, "attention_net.0.bias": torch.zeros(512),
+          "attention_net.3.attention_a.0.weight": torch.randn(256, 512, generator=gen) * 0.05,
+          "attention_net.3.attention_a.0.bias": torch.zeros(256),
+          "attention_net.3.attention_b.0.weight": torch.randn(256, 512, generator=gen) * 0.05,
+          "attention_net.3.attention_b.0.bias": torch.zeros(256),
+          "attention_net.3.attention_c.weight": torch.randn(1, 256, generator=gen) * 0.06,
+          "attention_net.3.attention_c.bias": torch.zeros(1)}
+    enc = ChiefB200(sd)
+    root = Path(tempfile.mkdtemp(prefix=f"stamp_b200_enc_r{rank}_"))
+    try:
+        feat_dir = root / "chief-ctranspath"
+        pool = torch.randn(12_000, 768, generator=gen).half()
+        for i in mine:
+            off = (i * 37) % 2000
+            features.write_tile_features(feat_dir / f"slide_{i:03d}.h5", pool[off:off + sizes[i]],
+                                         torch.rand(sizes[i], 2, generator=gen) * 5e4, extractor="chief-ctranspath",
+                                         tile_size_um=256.0, tile_size_px=224)
+        if hasattr(enc, "_encode_dir"):                         # stand-alone Encoder (no stamp package): warm-up
+            enc.encode_slides_(root / "warm", feat_dir, dev, generate_hash=False)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        enc.encode_slides_(root / "out", feat_dir, dev, generate_hash=False)
+        torch.cuda.synchronize()
+        span = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        n_out = len(list((root / "out").rglob("*.h5")))
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    if world > 1:
+        dist.all_reduce(span, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    assert n_out == len(mine), (n_out, len(mine))
+    secs = float(span)
+    return {"metric": "slide embeddings/sec, CHIEF encode_slides_ over feature files (SURVEY 8e: slide-level encoding)",
+            "slides": len(sizes), "tiles": sum(sizes), "n_gpus": world, "value": len(sizes) / secs, "unit": "slides/s",
+            "tiles_per_s": sum(sizes) / secs, "wall_s": secs,
+            "sharding": "shard_lpt on tile counts, no collective",
+            "note": "end to end per slide: fp16 feature file (h5lite) -> fp32 -> H2D -> pooling kernels -> D2H -> "
+                    "slide-level .h5; bound by the host-side file read / fp16->fp32 conversion, the pooling kernels "
+                    "take < 1 ms per slide"}
+
+
 def extractors_block(dev, peak_tf: float, batch: int = 96) -> dict:
     """the other tile encoders the reference ships (uni2.py:18-32, h_optimus_0.py:14-28) on the same
     kernels -- device-resident tiles/s at batch 96 with random-init weights of the architecture."""
