@@ -46,3 +46,24 @@ run("qkv", 3072, 1024, ops.ACT_NONE)
 run("fc2 (residual)", 1024, 4096, ops.ACT_NONE, resid=True)
 run("proj (residual)", 1024, 1024, ops.ACT_NONE, resid=True)
 run("virchow fc1 SwiGLU", 6832, 1280, ops.ACT_NONE, store=ops.ST_SWIGLU16)
+
+
+def run_cublas(name, N, K):
+    """The library GEMM (cuBLAS through torch.matmul, fp16 in / fp16 out, no bias, no activation) at the same shape:
+    what "peak at this shape" means for a K = 1024 product, next to the 8192^3 figure of MEASURED_PEAKS.json."""
+    a = (torch.randn(M, K, device=dev) * 0.5).half()
+    w = (torch.randn(N, K, device=dev) * 0.03).half()
+    out = torch.empty(M, N, device=dev, dtype=torch.float16)
+    us = timed(lambda: torch.matmul(a, w.t(), out=out))
+    print(f"cuBLAS {name:21s} {us:8.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s")
+
+
+run_cublas("fc1 shape", 4096, 1024)
+run_cublas("qkv shape", 3072, 1024)
+run_cublas("fc2 shape", 1024, 4096)
+run_cublas("proj shape", 1024, 1024)
+a = torch.randn(8192, 8192, device=dev).half()
+b = torch.randn(8192, 8192, device=dev).half()
+o = torch.empty(8192, 8192, device=dev, dtype=torch.float16)
+us = timed(lambda: torch.matmul(a, b, out=o))
+print(f"cuBLAS 8192^3 (burst)        {us:8.1f} us  {2.0 * 8192**3 / us / 1e6:7.1f} TFLOP/s")

@@ -1,7 +1,7 @@
 """One warm unit of work between cudaProfilerStart/Stop, for ncu launch lists:
 
     ncu --profile-from-start off --metrics gpu__time_duration.sum,... --csv --log-file out.csv \\
-        python scripts/profile_region.py {vit_l16|virchow2|mil_deploy|mil_train|macenko}
+        python scripts/profile_region.py {vit_l16|virchow2|gigapath|resize|mil_deploy|mil_train|macenko}
 """
 import sys
 from pathlib import Path
@@ -20,6 +20,18 @@ if what in ("vit_l16", "virchow2"):
     enc = TileEncoder(arch, random_state_dict(arch), max_batch=B).to(dev).eval()
     tiles = torch.randint(0, 255, (B, 224, 224, 3), dtype=torch.uint8, device=dev)
     unit = lambda: enc(tiles)
+elif what == "gigapath":
+    from stamp_b200.vit import GIGAPATH_ARCH, TileEncoder, random_state_dict
+
+    enc = TileEncoder(GIGAPATH_ARCH, random_state_dict(GIGAPATH_ARCH), max_batch=96).to(dev).eval()
+    tiles = torch.randint(0, 255, (96, 224, 224, 3), dtype=torch.uint8, device=dev)
+    unit = lambda: enc(tiles)
+elif what == "resize":
+    from bench_extra import synthetic_he_tiles
+    from stamp_b200.resize import resize_center_crop
+
+    tiles = synthetic_he_tiles(768, 3, dev)
+    unit = lambda: resize_center_crop(tiles, 256, 224)
 elif what == "mil_deploy":
     from stamp_b200.mil import VisionTransformer
 

@@ -21,6 +21,7 @@
 #include "stamp_b200.h"
 
 namespace sb {
+constexpr int RS_ROW_SLACK = 5;                 // intermediate rows the fixed-tap vertical pass may read past the last one
 namespace {
 
 constexpr int RS_THREADS = 256;
@@ -31,6 +32,10 @@ __device__ __forceinline__ int clip8(int ss) {
     return ss < 0 ? 0 : (ss > 255 ? 255 : ss);
 }
 
+// KS > 0: both passes run exactly KS taps per output (the tables are zero-padded beyond each output's tap count, the
+// staging buffers have KS rows / 32 bytes of slack, so the surplus taps read initialised-or-not bytes times zero);
+// KS = 0: tap counts from the bounds table (any filter support).
+template <int KS>
 __global__ void __launch_bounds__(RS_THREADS)
 resize_u8_kernel(const uint8_t* __restrict__ src, int Hin, int Win, uint8_t* __restrict__ dst, int Hc, int Wc,
                  int cy, int cx, const int* __restrict__ kx, const int* __restrict__ bx, int ksx,
@@ -47,7 +52,7 @@ resize_u8_kernel(const uint8_t* __restrict__ src, int Hin, int Win, uint8_t* __r
     const int in_stride = Win * 3, out_stride = Wc * 3;
 
     uint8_t* tmp = rs_smem + ((static_cast<size_t>(max_in_rows) * in_stride + 32 + 15) & ~size_t(15));
-    int* kxs = reinterpret_cast<int*>(tmp + ((static_cast<size_t>(max_in_rows) * out_stride + 15) & ~size_t(15)));
+    int* kxs = reinterpret_cast<int*>(tmp + ((static_cast<size_t>(max_in_rows + RS_ROW_SLACK) * out_stride + 15) & ~size_t(15)));
     int* bxs = kxs + Wc * ksx;
 
     // ---- stage the input rows (one contiguous byte range of the tile) and the strip's horizontal coefficients
@@ -72,10 +77,22 @@ resize_u8_kernel(const uint8_t* __restrict__ src, int Hin, int Win, uint8_t* __r
         const int xmin = bxs[xo * 2], n = bxs[xo * 2 + 1];
         const int* k = kxs + xo * ksx;
         const uint8_t* p = s + xmin * 3 + c;
-        for (int i = 0; i < nin; ++i, p += in_stride) {
-            int ss = 1 << (RS_PRECISION_BITS - 1);
-            for (int t = 0; t < n; ++t) ss += static_cast<int>(p[t * 3]) * k[t];
-            tmp[i * out_stride + col] = static_cast<uint8_t>(clip8(ss));
+        if constexpr (KS > 0) {
+            int kr[KS];
+#pragma unroll
+            for (int t = 0; t < KS; ++t) kr[t] = k[t];
+            for (int i = 0; i < nin; ++i, p += in_stride) {
+                int ss = 1 << (RS_PRECISION_BITS - 1);
+#pragma unroll
+                for (int t = 0; t < KS; ++t) ss += static_cast<int>(p[t * 3]) * kr[t];
+                tmp[i * out_stride + col] = static_cast<uint8_t>(clip8(ss));
+            }
+        } else {
+            for (int i = 0; i < nin; ++i, p += in_stride) {
+                int ss = 1 << (RS_PRECISION_BITS - 1);
+                for (int t = 0; t < n; ++t) ss += static_cast<int>(p[t * 3]) * k[t];
+                tmp[i * out_stride + col] = static_cast<uint8_t>(clip8(ss));
+            }
         }
     }
     __syncthreads();
@@ -91,13 +108,19 @@ resize_u8_kernel(const uint8_t* __restrict__ src, int Hin, int Win, uint8_t* __r
             const int* k = ky + yo * ksy;
             int a0 = 1 << (RS_PRECISION_BITS - 1), a1 = a0, a2 = a0, a3 = a0;
             const uint8_t* p = tmp + ymin * out_stride + w * 4;
-            for (int t = 0; t < n; ++t, p += out_stride) {
+            auto tap = [&](int kt) {
                 const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
-                const int kt = __ldg(k + t);
                 a0 += static_cast<int>(v & 255u) * kt;
                 a1 += static_cast<int>((v >> 8) & 255u) * kt;
                 a2 += static_cast<int>((v >> 16) & 255u) * kt;
                 a3 += static_cast<int>(v >> 24) * kt;
+                p += out_stride;
+            };
+            if constexpr (KS > 0) {
+#pragma unroll
+                for (int t = 0; t < KS; ++t) tap(__ldg(k + t));
+            } else {
+                for (int t = 0; t < n; ++t) tap(__ldg(k + t));
             }
             const uint32_t o = static_cast<uint32_t>(clip8(a0)) | (static_cast<uint32_t>(clip8(a1)) << 8) |
                                (static_cast<uint32_t>(clip8(a2)) << 16) | (static_cast<uint32_t>(clip8(a3)) << 24);
@@ -122,7 +145,7 @@ resize_u8_kernel(const uint8_t* __restrict__ src, int Hin, int Win, uint8_t* __r
 extern "C" size_t stamp_resize_u8_smem_bytes(int Win, int Wc, int ksx, int max_in_rows) {
     if (Win <= 0 || Wc <= 0 || ksx <= 0 || max_in_rows <= 0) return 0;
     const size_t in_bytes = (static_cast<size_t>(max_in_rows) * Win * 3 + 32 + 15) & ~size_t(15);
-    const size_t tmp_bytes = (static_cast<size_t>(max_in_rows) * Wc * 3 + 15) & ~size_t(15);
+    const size_t tmp_bytes = (static_cast<size_t>(max_in_rows + sb::RS_ROW_SLACK) * Wc * 3 + 15) & ~size_t(15);
     return in_bytes + tmp_bytes + static_cast<size_t>(Wc) * (ksx + 2) * sizeof(int);
 }
 
@@ -138,19 +161,26 @@ extern "C" int stamp_resize_u8(const uint8_t* tiles, int n_tiles, int Hin, int W
     if (n_tiles > 65535) return SB_ERR_UNSUPPORTED;
     const size_t bytes = stamp_resize_u8_smem_bytes(Win, Wc, ksize_x, max_in_rows);
     if (bytes > 227 * 1024) return SB_ERR_UNSUPPORTED;
-    static size_t configured = 0;
-    if (bytes > configured) {
-        if (cudaFuncSetAttribute(resize_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)) !=
-            cudaSuccess)
-            return SB_ERR_CUDA;
-        configured = bytes;
+    const bool five = ksize_x == 5 && ksize_y == 5;           // bicubic / bilinear without down-sampling
+    static size_t configured[2] = {0, 0};
+    if (bytes > configured[five]) {
+        const cudaError_t ce = five ? cudaFuncSetAttribute(resize_u8_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                           static_cast<int>(bytes))
+                                    : cudaFuncSetAttribute(resize_u8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                           static_cast<int>(bytes));
+        if (ce != cudaSuccess) return SB_ERR_CUDA;
+        configured[five] = bytes;
     }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ProfScope prof(PROF_MACENKO, static_cast<double>(n_tiles) * (static_cast<double>(Hin) * Win + static_cast<double>(Hc) * Wc) * 3.0,
                    stream);
     const dim3 grid((Hc + rows_per_strip - 1) / rows_per_strip, n_tiles);
-    resize_u8_kernel<<<grid, RS_THREADS, bytes, stream>>>(tiles, Hin, Win, out, Hc, Wc, crop_y, crop_x, coef_x, bounds_x,
-                                                          ksize_x, coef_y, bounds_y, ksize_y, rows_per_strip, max_in_rows);
+    if (five)
+        resize_u8_kernel<5><<<grid, RS_THREADS, bytes, stream>>>(tiles, Hin, Win, out, Hc, Wc, crop_y, crop_x, coef_x, bounds_x,
+                                                                 ksize_x, coef_y, bounds_y, ksize_y, rows_per_strip, max_in_rows);
+    else
+        resize_u8_kernel<0><<<grid, RS_THREADS, bytes, stream>>>(tiles, Hin, Win, out, Hc, Wc, crop_y, crop_x, coef_x, bounds_x,
+                                                                 ksize_x, coef_y, bounds_y, ksize_y, rows_per_strip, max_in_rows);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
