@@ -1,5 +1,11 @@
-"""Small run of the long-bag tcgen05 kernels, the tcgen05 weight-gradient kernel and the texture filter for
-compute-sanitizer (development aid):  compute-sanitizer --tool memcheck python scripts/sanitize_probe.py"""
+"""Small runs of every kernel family for compute-sanitizer (development aid / evidence under profiles/):
+
+    compute-sanitizer --tool memcheck python scripts/sanitize_probe.py
+
+MIL training step and inference forward at a ragged bag length (333 tiles: tcgen05 long-bag attention forward v3,
+backward, weight gradients, row ops, fused AdamW), the ViT tile encoder for head dimensions 64 and 80 (GEMM epilogues
+incl. GELU / SwiGLU / residual reduce-add, streaming attention, LayerNorm, patch kernel) on a ragged batch, Macenko,
+the tissue-texture filter, the bicubic resampling, CHIEF pooling + top-k."""
 import sys
 from pathlib import Path
 
@@ -7,8 +13,12 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import torch
 
 from stamp_b200 import train as T
+from stamp_b200.encoder import GatedAttentionPool, topk
+from stamp_b200.macenko import macenko_normalize
 from stamp_b200.mil import VisionTransformer
+from stamp_b200.resize import resize_center_crop
 from stamp_b200.tiling import canny_edge_counts
+from stamp_b200.vit import TileEncoder, VitArch, random_state_dict
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -22,7 +32,31 @@ loss = T.data_parallel_step(m, opt, (bags, coords, None, y), None)
 m.eval()
 with torch.inference_mode():
     out = m(bags, coords=coords, mask=None)
-tiles = torch.randint(0, 255, (3, 224, 224, 3), dtype=torch.uint8, device=dev)
-cnt = canny_edge_counts(tiles)
+    out16 = m(bags.half(), coords=coords, mask=None)
 torch.cuda.synchronize()
-print("probe ok", float(loss), out.tolist(), cnt.tolist())
+print("mil ok", float(loss), out.tolist(), out16.tolist())
+
+tiles = torch.randint(0, 255, (5, 224, 224, 3), dtype=torch.uint8, device=dev)
+for arch in (VitArch("hd64", dim=128, depth=2, heads=2, mlp_hidden=512),
+             VitArch("hd80", patch=14, dim=160, depth=2, heads=2, mlp_hidden=432, mlp="swiglu", reg_tokens=4),
+             VitArch("resized", dim=128, depth=1, heads=2, mlp_hidden=512, pre_resize=256)):
+    enc = TileEncoder(arch, random_state_dict(arch), max_batch=3).to(dev).eval()
+    f = enc(tiles)
+    torch.cuda.synchronize()
+    print("vit ok", arch.name, f.shape, bool(torch.isfinite(f).all()))
+
+norm = macenko_normalize(tiles)
+cnt = canny_edge_counts(tiles)
+rs = resize_center_crop(tiles, 112, 97)
+g = torch.Generator().manual_seed(3)
+sd = {"attention_net.0.weight": torch.randn(512, 768, generator=g) * 0.04, "attention_net.0.bias": torch.zeros(512),
+      "attention_net.3.attention_a.0.weight": torch.randn(256, 512, generator=g) * 0.05,
+      "attention_net.3.attention_a.0.bias": torch.zeros(256),
+      "attention_net.3.attention_b.0.weight": torch.randn(256, 512, generator=g) * 0.05,
+      "attention_net.3.attention_b.0.bias": torch.zeros(256),
+      "attention_net.3.attention_c.weight": torch.randn(1, 256, generator=g) * 0.06,
+      "attention_net.3.attention_c.bias": torch.zeros(1)}
+pooled = GatedAttentionPool(sd).to(dev)(torch.randn(777, 768, device=dev))
+vals, idx = topk(pooled["attention_raw"].squeeze(0).contiguous(), 25)
+torch.cuda.synchronize()
+print("side kernels ok", norm.shape, cnt.tolist(), rs.shape, idx[:3].tolist())
