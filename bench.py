@@ -528,7 +528,45 @@ def run_b200(args) -> None:
 
         rs_ms = timed(lambda: resize_center_crop(mt, 256, 224))
         rs_gbs = 2 * mt.numel() / rs_ms / 1e6
+        # cached-tile JPEG decode (tiling.py:380-406): Pillow thread pool vs host Huffman + GPU kernels, 768 tiles
+        import io as _io
+
+        import numpy as np
+        from concurrent.futures import ThreadPoolExecutor as _Pool
+
+        from PIL import Image as _Image
+
+        from stamp_b200 import jpeg as _jpeg
+
+        _blobs = []
+        for _t in mt[:96].cpu().numpy():
+            _b = _io.BytesIO()
+            _Image.fromarray(_t).save(_b, format="jpeg")
+            _blobs.append(_b.getvalue())
+        _blobs = _blobs * 8
+        _pil = lambda b: np.asarray(_Image.open(_io.BytesIO(b)).convert("RGB"))
+        with _Pool(8) as _ex:
+            _t0 = time.perf_counter(); list(_ex.map(_pil, _blobs)); jp_pil = len(_blobs) / (time.perf_counter() - _t0)
+        _info, _coef, _quant = _jpeg.entropy_decode(_blobs, max_workers=8, pin=True)
+        _t0 = time.perf_counter(); _jpeg.entropy_decode(_blobs, max_workers=8, out=(_coef, _quant)); jp_huff = len(_blobs) / (time.perf_counter() - _t0)
+        _cd, _qd = _coef.to(dev), _quant.to(dev)
+        jp_ms = timed(lambda: _jpeg.decode_coefficients(_info, _cd, _qd, out=mo_))
+        jp_gbs = (_cd.numel() * 2 + mo_.numel()) / jp_ms / 1e6
+        torch.cuda.synchronize()
+        _t0 = time.perf_counter()
+        _jpeg.entropy_decode(_blobs, max_workers=8, out=(_coef, _quant))
+        _jpeg.decode_coefficients(_info, _coef.to(dev, non_blocking=True), _quant.to(dev, non_blocking=True), out=mo_)
+        torch.cuda.synchronize()
+        jp_e2e = len(_blobs) / (time.perf_counter() - _t0)
+        del _cd, _qd
         hbm_out = {
+            "jpeg_tile_decode": {"metric": "cached-tile JPEG decode (tiling.py:380-406), 224 px 4:2:0 tiles, bit-exact with Pillow",
+                                 "gpu_kernels_tiles_per_s": 768 / jp_ms * 1e3, "achieved_GBps": jp_gbs, "peak_GBps": hbm_gbs,
+                                 "frac": jp_gbs / hbm_gbs, "algorithmic_bytes_per_tile": 2 * 75264 + 150528,
+                                 "host_huffman_8_threads_tiles_per_s": jp_huff, "e2e_8_threads_tiles_per_s": jp_e2e,
+                                 "pillow_8_threads_tiles_per_s": jp_pil,
+                                 "note": "host: marker parsing + Huffman decode (C++, GIL released); GPU: dequantise, islow IDCT, fancy "
+                                         "chroma up-sampling, YCbCr->RGB; e2e = Huffman + H2D of int16 coefficients + kernels, not overlapped"},
             "texture_filter": {"metric": "Canny tissue-texture filter (tiling.py:279-291), tiles/s", "tiles_per_s": 768 / tex_ms * 1e3,
                                "achieved_GBps": tex_gbs, "peak_GBps": hbm_gbs, "frac": tex_gbs / hbm_gbs,
                                "algorithmic_bytes_per_tile": 150528,

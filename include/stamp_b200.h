@@ -325,6 +325,38 @@ int stamp_tile_texture_u8(const uint8_t* tiles, int n_tiles, int H, int W, int l
                           int* edge_count, uint8_t* edges_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Decode of cached JPEG tiles, bit-exact with Pillow (libjpeg-turbo defaults: islow inverse DCT, fancy chroma
+ * up-sampling, fixed-point YCbCr -> RGB).
+ * replaces: Image.open(tile_fp) + img.load() per cached tile in _tiles_from_cache_file,
+ *   src/stamp/preprocessing/tiling.py:380-406.
+ * Baseline / extended sequential Huffman JPEG, 8 bit, three components in one interleaved scan, 4:2:0 or 4:4:4
+ * (what Pillow's Image.save(format="jpeg") writes); anything else returns STAMP_ERR_UNSUPPORTED.
+ * Host side (no GPU work, re-entrant, callable from many threads):
+ *   stamp_jpeg_read_header     geometry and quantisation tables of one file;
+ *   stamp_jpeg_coef_count      int16 coefficients per tile (every block of every component, padded to whole MCUs);
+ *   stamp_jpeg_entropy_decode  Huffman decode of one file into quantised coefficients, component-major
+ *                              [Y blocks | Cb blocks | Cr blocks][64] in natural (row-major) order, and its
+ *                              quantisation tables uint16 [3][64]; `expect` (may be NULL) pins the geometry.
+ * Device side:
+ *   stamp_jpeg_decode_coefs_u8 coef int16 [n_tiles][coef_count], quant uint16 [n_tiles][3][64] (both on the device,
+ *                              16-byte aligned) -> out uint8 [n_tiles, height, width, 3]; workspace holds the
+ *                              component planes (stamp_jpeg_workspace_bytes).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct StampJpegInfo {
+    int width, height, n_comp;
+    int h[3], v[3];              /* sampling factors per component */
+    int mcus_x, mcus_y;          /* MCUs per row / column */
+    uint16_t quant[3][64];       /* per component, natural order */
+} StampJpegInfo;
+int stamp_jpeg_read_header(const uint8_t* data, size_t n, StampJpegInfo* info);
+size_t stamp_jpeg_coef_count(const StampJpegInfo* info);
+int stamp_jpeg_entropy_decode(const uint8_t* data, size_t n, const StampJpegInfo* expect, int16_t* coef,
+                              uint16_t* quant);
+size_t stamp_jpeg_workspace_bytes(const StampJpegInfo* info, int n_tiles);
+int stamp_jpeg_decode_coefs_u8(const StampJpegInfo* info, const int16_t* coef, const uint16_t* quant, int n_tiles,
+                               uint8_t* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Resampling of uint8 RGB tiles (extractor transforms that resize the tile before the model), bit-exact with
  * Pillow's Image.resize for 8-bit images.
  * replaces: transforms.Resize(256, interpolation=BICUBIC) + transforms.CenterCrop(224),

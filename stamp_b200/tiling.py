@@ -128,3 +128,50 @@ def tiles_from_cache_file(cache_file_path: str | Path, *, max_workers: int = 8,
     with ThreadPoolExecutor(max_workers=max_workers) as ex:
         list(ex.map(work, range(1, len(blobs))))
     return out, torch.tensor(coords, dtype=torch.float32), params
+
+
+def tiles_from_cache_file_gpu(cache_file_path: str | Path, device: torch.device | str = "cuda", *, max_workers: int = 8,
+                              batch: int = 512) -> tuple[Tensor, Tensor, dict]:
+    """``tiles_from_cache_file`` with the tiles born on the GPU: for a JPEG cache (the reference's default,
+    ``tile_ext = "jpg"``) the host only Huffman-decodes (``stamp_b200.jpeg.entropy_decode``, a thread pool over the
+    tiles), the inverse DCT / chroma up-sampling / colour conversion run on ``device`` in batches of ``batch`` tiles.
+    Returns the same pixels as the Pillow path (bit-exact), as a uint8 ``[N, H, W, 3]`` CUDA tensor.  Caches in another
+    image format, or JPEG variants Pillow does not write by default (progressive, CMYK), raise -- use
+    ``tiles_from_cache_file`` for those."""
+    from . import jpeg
+
+    device = torch.device(device)
+    path = Path(cache_file_path)
+    with ZipFile(path, "r") as zf:
+        params = json.loads(zf.read("tiler_params.json").decode())
+        ext = params.get("tile_ext", "jpg")
+        if ext.lower() not in ("jpg", "jpeg"):
+            raise ValueError(f"tile cache holds {ext!r} tiles; the GPU decoder reads JPEG caches only")
+        pat = re.compile(rf"tile_\((\d+\.\d+), (\d+\.\d+)\)\.{re.escape(ext)}")
+        names, coords = [], []
+        for name in zf.namelist():
+            m = pat.fullmatch(name)
+            if m is not None:
+                names.append(name)
+                coords.append((float(m.group(1)), float(m.group(2))))
+        blobs = [zf.read(n) for n in names]
+    if not names:
+        return torch.empty((0, 0, 0, 3), dtype=torch.uint8, device=device), torch.empty((0, 2)), params
+    info = jpeg.read_header(blobs[0])
+    out = torch.empty((len(blobs), info.height, info.width, 3), dtype=torch.uint8, device=device)
+    batch = min(batch, len(blobs))
+    n = jpeg.coef_count(info)
+    # two pinned staging sets: the pool Huffman-decodes batch i+1 while batch i crosses PCIe and runs its kernels
+    stage = [(torch.empty((batch, n), dtype=torch.int16).pin_memory(), torch.empty((batch, 3, 64), dtype=torch.int16).pin_memory())
+             for _ in range(2)]
+    copied: list[torch.cuda.Event | None] = [None, None]
+    for i, s in enumerate(range(0, len(blobs), batch)):
+        part = blobs[s:s + batch]
+        if copied[i % 2] is not None:
+            copied[i % 2].synchronize()
+        _, coef, quant = jpeg.entropy_decode(part, max_workers=max_workers, out=stage[i % 2])
+        cd, qd = coef.to(device, non_blocking=True), quant.to(device, non_blocking=True)
+        copied[i % 2] = torch.cuda.Event()
+        copied[i % 2].record()
+        jpeg.decode_coefficients(info, cd, qd, out=out[s:s + len(part)])
+    return out, torch.tensor(coords, dtype=torch.float32), params

@@ -1,0 +1,79 @@
+"""Cached-tile JPEG decode on the CPU: the oracle against Pillow (bit for bit), and the product's host half (marker
+parsing + Huffman decoding in libstamp_b200.so, no GPU work) against the oracle's coefficients."""
+
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import jpeg_oracle as jo
+from oracle import vit_oracle as vo
+
+
+def _jpeg(img: np.ndarray, **kw) -> bytes:
+    from PIL import Image
+
+    b = io.BytesIO()
+    Image.fromarray(img).save(b, format="jpeg", **kw)
+    return b.getvalue()
+
+
+def _cases():
+    rng = np.random.default_rng(0)
+    he = vo.synthetic_tiles(2, seed=1).numpy()
+    noise = rng.integers(0, 256, (224, 224, 3), dtype=np.uint8)
+    return [("h&e, Pillow defaults (q75, 4:2:0)", he[0], {}),
+            ("h&e, q95, 4:4:4", he[1], dict(quality=95, subsampling=0)),
+            ("noise, q75", noise, {}),
+            ("noise, q30, 64 x 80", noise[:64, :80], dict(quality=30)),
+            ("37 x 53 (partial MCUs), 4:2:0", noise[:37, :53], {}),
+            ("37 x 53, 4:4:4, q90", noise[:37, :53], dict(quality=90, subsampling=0)),
+            ("restart markers", he[0], dict(restart_marker_blocks=7)),
+            ("optimised Huffman tables", he[1], dict(optimize=True)),
+            ("saturated checkerboard", (np.indices((64, 64)).sum(0) % 2 * 255).astype(np.uint8)[..., None].repeat(3, -1), {})]
+
+
+@pytest.mark.parametrize("name,img,kw", _cases(), ids=[c[0] for c in _cases()])
+def test_oracle_is_pillow_bit_for_bit(name, img, kw):
+    from PIL import Image
+
+    data = _jpeg(img, **kw)
+    want = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+    assert np.array_equal(jo.decode(data), want)
+
+
+@pytest.mark.parametrize("name,img,kw", _cases(), ids=[c[0] for c in _cases()])
+def test_host_entropy_decoder_matches_oracle(name, img, kw):
+    from stamp_b200 import jpeg
+
+    data = _jpeg(img, **kw)
+    info, coef, quant = jpeg.entropy_decode([data], max_workers=1)
+    h, w, comps, q, co = jo.parse(data)
+    assert (info.height, info.width, info.n_comp) == (h, w, 3)
+    assert [(info.h[i], info.v[i]) for i in range(3)] == [c[1:3] for c in comps]
+    assert np.array_equal(coef[0].numpy(), np.concatenate([co[i].reshape(-1) for i in range(3)]))
+    for i, c in enumerate(comps):
+        assert np.array_equal(quant[0, i].numpy().astype(np.uint16), q[c[3]].astype(np.uint16))
+
+
+def test_host_decoder_batches_and_rejects_what_it_does_not_read():
+    from PIL import Image
+
+    from stamp_b200 import _lib, jpeg
+
+    tiles = vo.synthetic_tiles(9, seed=4).numpy()
+    blobs = [_jpeg(t) for t in tiles]
+    info, coef, quant = jpeg.entropy_decode(blobs, max_workers=4)
+    _, one, _ = jpeg.entropy_decode(blobs[5:6], max_workers=1)
+    assert coef.shape == (9, 28 * 28 * 64 + 2 * 14 * 14 * 64) and torch.equal(coef[5], one[0])
+    gray = io.BytesIO()
+    Image.fromarray(tiles[0][..., 0]).save(gray, format="jpeg")
+    prog = _jpeg(tiles[0], progressive=True)
+    for bad in (gray.getvalue(), prog, b"\xff\xd8\xff\xd9", blobs[0][: len(blobs[0]) // 3], b"not a jpeg at all"):
+        with pytest.raises(_lib.StampB200Error):
+            jpeg.entropy_decode([bad], max_workers=1)
+    with pytest.raises(_lib.StampB200Error):          # one geometry per batch
+        jpeg.entropy_decode([blobs[0], _jpeg(tiles[1][:64, :64])], max_workers=1)
+    with pytest.raises(RuntimeError):
+        jpeg.decode_jpeg_tiles(blobs, "cpu")

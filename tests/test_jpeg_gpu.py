@@ -1,0 +1,72 @@
+"""Cached-tile JPEG decode on the GPU (host Huffman decode + csrc/jpeg.cu) against Pillow itself: bit-exact."""
+
+import io
+import json
+import zipfile
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _jpeg(img: np.ndarray, **kw) -> bytes:
+    from PIL import Image
+
+    b = io.BytesIO()
+    Image.fromarray(img).save(b, format="jpeg", **kw)
+    return b.getvalue()
+
+
+def _pillow(blob: bytes) -> np.ndarray:
+    from PIL import Image
+
+    return np.asarray(Image.open(io.BytesIO(blob)).convert("RGB"))
+
+
+@pytest.mark.parametrize("h,w,kw", [
+    (224, 224, {}),                                   # the reference's cache: Pillow defaults, quality 75, 4:2:0
+    (224, 224, dict(quality=95, subsampling=0)),      # 4:4:4
+    (256, 256, dict(quality=50)),
+    (37, 53, {}),                                     # partial MCUs, odd width and height
+    (37, 53, dict(subsampling=0, quality=90)),
+    (16, 16, dict(quality=100)),                      # a single MCU: every edge rule of the chroma up-sampling at once
+    (224, 224, dict(restart_marker_blocks=5, optimize=True)),
+])
+def test_gpu_decode_is_pillow_bit_for_bit(cuda_device, h, w, kw):
+    from oracle import vit_oracle as vo
+    from stamp_b200.jpeg import decode_jpeg_tiles
+
+    rng = np.random.default_rng(h * 1000 + w)
+    he = vo.synthetic_tiles(3, seed=h + w, img=max(h, w) if max(h, w) % 2 == 0 else 224).numpy()[:, :h, :w]
+    imgs = [he[0], he[1], he[2], rng.integers(0, 256, (h, w, 3), dtype=np.uint8),
+            (np.indices((h, w)).sum(0) % 2 * 255).astype(np.uint8)[..., None].repeat(3, -1)]
+    blobs = [_jpeg(np.ascontiguousarray(i), **kw) for i in imgs]
+    got = decode_jpeg_tiles(blobs, cuda_device, max_workers=2)
+    assert got.shape == (len(blobs), h, w, 3) and got.dtype == torch.uint8 and got.is_cuda
+    want = np.stack([_pillow(b) for b in blobs])
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_tile_cache_zip_decoded_on_the_gpu(cuda_device, tmp_path):
+    """_tiles_from_cache_file (tiling.py:380-406) with the tiles born in HBM: same pixels, coordinates and order as the
+    Pillow reader; a 700-tile cache goes through in batches."""
+    from oracle import vit_oracle as vo
+    from stamp_b200.tiling import tiles_from_cache_file, tiles_from_cache_file_gpu
+
+    tiles = vo.synthetic_tiles(40, seed=9).numpy()
+    path = tmp_path / "slide.abc.zip"
+    with zipfile.ZipFile(path, "w") as zf:
+        zf.writestr("tiler_params.json", json.dumps({"tile_ext": "jpg", "tile_size_um": 256.0, "tile_size_px": 224}))
+        for i in range(700):
+            zf.writestr(f"tile_({256.0 * (i % 30)}, {256.0 * (i // 30)}).jpg", _jpeg(np.roll(tiles[i % 40], i, axis=1)))
+        zf.writestr("thumbnail.jpg", _jpeg(tiles[0][:64, :64]))          # not a tile: ignored by both readers
+    host, coords_h, params_h = tiles_from_cache_file(path, pin_memory=False)
+    dev, coords_d, params_d = tiles_from_cache_file_gpu(path, cuda_device, batch=256)
+    assert dev.is_cuda and dev.shape == (700, 224, 224, 3) and params_d == params_h
+    assert torch.equal(coords_d, coords_h) and torch.equal(dev.cpu(), host)
+    with zipfile.ZipFile(tmp_path / "png.zip", "w") as zf:
+        zf.writestr("tiler_params.json", json.dumps({"tile_ext": "png"}))
+    with pytest.raises(ValueError):
+        tiles_from_cache_file_gpu(tmp_path / "png.zip", cuda_device)
