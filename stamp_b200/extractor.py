@@ -139,11 +139,20 @@ def extract_slide_features(extractor: Extractor, tiles_u8: Tensor, device: torch
                            batch_size: int = 192) -> Tensor:
     """The hot loop of ``extract_`` (src/stamp/preprocessing/__init__.py:322-327) for tiles already
     decoded to a host uint8 tensor [N, H, W, 3]: pinned double-buffered H2D copies on a side
-    stream overlap the encoder; features come back as one fp16 host tensor [N, D]."""
+    stream overlap the encoder; features come back as one fp16 host tensor [N, D].  CUDA tiles (decoded on the
+    GPU) are consumed in place."""
     device = torch.device(device)
     model = extractor.model
     n = tiles_u8.shape[0]
     feats_host = torch.empty((n, model.arch.dim), dtype=torch.float16).pin_memory()
+    if tiles_u8.is_cuda:
+        # tiles already in HBM (decoded there: tiling.tiles_from_cache_file_gpu): nothing to stream in
+        feats_dev = torch.empty((n, model.arch.dim), dtype=torch.float16, device=tiles_u8.device)
+        for s in range(0, n, batch_size):
+            feats_dev[s:s + batch_size] = model(tiles_u8[s:s + batch_size])
+        feats_host.copy_(feats_dev, non_blocking=True)
+        torch.cuda.current_stream(tiles_u8.device).synchronize()
+        return feats_host
     if not tiles_u8.is_pinned():
         tiles_u8 = tiles_u8.pin_memory()
     copy_stream = torch.cuda.Stream(device=device)

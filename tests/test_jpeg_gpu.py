@@ -66,6 +66,16 @@ def test_tile_cache_zip_decoded_on_the_gpu(cuda_device, tmp_path):
     dev, coords_d, params_d = tiles_from_cache_file_gpu(path, cuda_device, batch=256)
     assert dev.is_cuda and dev.shape == (700, 224, 224, 3) and params_d == params_h
     assert torch.equal(coords_d, coords_h) and torch.equal(dev.cpu(), host)
+    # ... and straight into the tile encoder: features from GPU-born tiles == features from the host tiles
+    from stamp_b200.extractor import Extractor, extract_slide_features, pil_to_u8_hwc
+    from stamp_b200.vit import TileEncoder, VitArch
+
+    cfg = vo.tiny_config(depth=1)
+    arch = VitArch(cfg.name, patch=cfg.patch, dim=cfg.dim, depth=cfg.depth, heads=cfg.heads, mlp_hidden=cfg.mlp_hidden)
+    ext = Extractor(model=TileEncoder(arch, vo.make_weights(cfg), max_batch=64).to(cuda_device).eval(),
+                    transform=pil_to_u8_hwc, identifier="tiny")
+    assert torch.equal(extract_slide_features(ext, dev[:100], cuda_device, batch_size=48),
+                       extract_slide_features(ext, host[:100], cuda_device, batch_size=48))
     with zipfile.ZipFile(tmp_path / "png.zip", "w") as zf:
         zf.writestr("tiler_params.json", json.dumps({"tile_ext": "png"}))
     with pytest.raises(ValueError):
