@@ -78,7 +78,9 @@ except ImportError:
             if extractor not in self.required_extractors:
                 raise ValueError(f"Features must be extracted with one of {self.required_extractors}. "
                                  f"Features located in {h5_path} are extracted with {extractor}")
-            return torch.from_numpy(feats).to(dtype=self.precision), coords
+            # features stay in their storage dtype (fp16) on the host: the subclasses move them to the device first
+            # and widen there (a host fp16 -> fp32 pass over a 10 k-tile slide costs more than the pooling kernels)
+            return torch.from_numpy(feats), coords
 
         def _save_features_(self, output_path, feats: np.ndarray, feat_type: str) -> None:
             from . import features
@@ -246,7 +248,7 @@ class ChiefB200(Encoder):
 
     def _generate_slide_embedding(self, feats: Tensor, device, **kwargs) -> np.ndarray:
         self.model.to(device)
-        out = self.model(feats.to(device))
+        out = self.model(feats.to(device).to(self.precision))
         return out["WSI_feature"].float().squeeze().cpu().numpy()
 
     def _generate_patient_embedding(self, feats_list: list[Tensor], device, **kwargs) -> np.ndarray:
@@ -268,7 +270,7 @@ class EagleB200(_EagleBase):
         if agg_feats is None:
             raise ValueError("agg_feats is required for slide embedding")
         self.model.to(device)
-        attn = self.model(feats.to(device))["attention_raw"].squeeze(0).contiguous()
+        attn = self.model(feats.to(device).to(self.precision))["attention_raw"].squeeze(0).contiguous()
         k = min(25, attn.shape[0])
         _, idx = topk(attn, k)
         agg = agg_feats.to(device).float().contiguous()

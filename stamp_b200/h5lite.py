@@ -715,7 +715,11 @@ class Dataset:
         return self.shape[0]
 
     def __getitem__(self, key: Any) -> Any:
-        arr = self._r.read_dataset(self._msgs, self.shape, self._dtype, self._esize)
+        if self.shape and self._dtype is not _VLEN_STR and self._dtype.byteorder != ">" and int(np.prod(self.shape)) > 0:
+            arr = np.empty(self.shape, dtype=self._dtype)      # contiguous storage: one read straight into the result
+            self.read_direct(arr)
+        else:
+            arr = self._r.read_dataset(self._msgs, self.shape, self._dtype, self._esize)
         if key is Ellipsis or (isinstance(key, tuple) and len(key) == 0):
             return arr
         return arr[key]
@@ -738,7 +742,7 @@ class Dataset:
                 if self._r.fp.readinto(memoryview(dest).cast("B")) != dest.nbytes:
                     raise H5Error(f"{self.name}: short read")
                 return
-        dest[...] = self[()]
+        dest[...] = self._r.read_dataset(self._msgs, self.shape, self._dtype, self._esize)
 
 
 class Group:
