@@ -104,11 +104,10 @@ inline int decode_symbol(BitReader& br, const HuffTable& t) {
     }
     int len = LOOK + 1;
     int32_t code = static_cast<int32_t>(br.peek(len));
-    while (len <= 16 && code > t.maxcode[len]) {
-        ++len;
+    while (code > t.maxcode[len]) {
+        if (++len > 16) return -1;   // no code of any length matches: corrupt data
         code = static_cast<int32_t>(br.peek(len));
     }
-    if (len > 16) return -1;
     br.skip(len);
     return t.symbols[(code + t.valoff[len]) & 0xFF];
 }

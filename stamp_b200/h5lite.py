@@ -45,6 +45,25 @@ def _pad8(n: int) -> int:
     return (n + 7) & ~7
 
 
+_PARSE_ERRORS = (struct.error, IndexError, ValueError, TypeError, OverflowError, MemoryError, RecursionError,
+                 UnicodeDecodeError, zlib.error)
+
+
+class _guard:
+    """Turns whatever a corrupt structure makes the parser raise into H5Error (an OSError, like h5py's)."""
+
+    def __init__(self, what: str) -> None:
+        self.what = what
+
+    def __enter__(self) -> None:
+        return None
+
+    def __exit__(self, exc_type, exc, _tb) -> bool:  # noqa: ANN001
+        if exc_type is not None and issubclass(exc_type, _PARSE_ERRORS) and not issubclass(exc_type, H5Error):
+            raise H5Error(f"{self.what}: truncated or corrupt HDF5 structure ({exc_type.__name__}: {exc})") from exc
+        return False
+
+
 # --------------------------------------------------------------------------------------------------
 # datatypes <-> numpy
 # --------------------------------------------------------------------------------------------------
@@ -87,6 +106,8 @@ def _decode_dtype(buf: bytes) -> tuple[Any, int]:
         raise H5Error(f"datatype message version {ver}")
     order = ">" if b0 & 1 else "<"
     if cls == 0:
+        if size not in (1, 2, 4, 8):
+            raise H5Error(f"fixed-point type of {size} bytes")
         return np.dtype(f"{order}{'i' if b0 & 0x08 else 'u'}{size}"), size
     if cls == 1:
         if size not in (2, 4, 8):
@@ -694,9 +715,10 @@ class Dataset:
         dtype = next((b for t, b in msgs if t == 0x03), None)
         if space is None or dtype is None:
             raise H5Error(f"{name}: not a dataset")
-        shape = reader.parse_dataspace(space)
-        self.shape: tuple[int, ...] = shape if shape is not None else ()
-        self._dtype, self._esize = _decode_dtype(dtype)
+        with _guard(name):
+            shape = reader.parse_dataspace(space)
+            self.shape: tuple[int, ...] = shape if shape is not None else ()
+            self._dtype, self._esize = _decode_dtype(dtype)
         self._attrs: dict[str, Any] | None = None
 
     @property
@@ -706,7 +728,8 @@ class Dataset:
     @property
     def attrs(self) -> dict[str, Any]:
         if self._attrs is None:
-            self._attrs = self._r.attributes(self._msgs)
+            with _guard(self.name):
+                self._attrs = self._r.attributes(self._msgs)
         return self._attrs
 
     def __len__(self) -> int:
@@ -715,14 +738,21 @@ class Dataset:
         return self.shape[0]
 
     def __getitem__(self, key: Any) -> Any:
+        with _guard(self.name):
+            arr = self._read_all()
+        if key is Ellipsis or (isinstance(key, tuple) and len(key) == 0):
+            return arr
+        return arr[key]
+
+    def _read_all(self) -> Any:
+        if self._dtype is not _VLEN_STR and int(np.prod(self.shape, dtype=np.float64)) * self._esize > 64 * max(self._r.file_size, 1 << 20):
+            raise H5Error(f"{self.name}: dataspace {self.shape} is larger than the file could hold")
         if self.shape and self._dtype is not _VLEN_STR and self._dtype.byteorder != ">" and int(np.prod(self.shape)) > 0:
             arr = np.empty(self.shape, dtype=self._dtype)      # contiguous storage: one read straight into the result
             self.read_direct(arr)
         else:
             arr = self._r.read_dataset(self._msgs, self.shape, self._dtype, self._esize)
-        if key is Ellipsis or (isinstance(key, tuple) and len(key) == 0):
-            return arr
-        return arr[key]
+        return arr
 
     def __array__(self, dtype=None, copy=None):  # noqa: ANN001
         arr = self[()]
@@ -753,7 +783,8 @@ class Group:
     @property
     def attrs(self) -> dict[str, Any]:
         if self._attrs is None:
-            self._attrs = self._r.attributes(self._msgs)
+            with _guard(self.name):
+                self._attrs = self._r.attributes(self._msgs)
         return self._attrs
 
     def keys(self):
@@ -777,9 +808,10 @@ class Group:
         for part in [p for p in name.split("/") if p]:
             if not isinstance(node, Group) or part not in node._links:
                 raise KeyError(f"Unable to open object (object {part!r} doesn't exist)")
-            msgs = self._r.messages(node._links[part])
-            links = self._r.links(msgs)
             path = f"{node.name.rstrip('/')}/{part}"
+            with _guard(path):
+                msgs = self._r.messages(node._links[part])
+                links = self._r.links(msgs)
             node = Group(self._r, path, msgs, links) if links is not None else Dataset(self._r, path, msgs)
         return node
 
@@ -801,15 +833,13 @@ class File:
         self._wattrs = _AttrsWriter()
         if mode == "r":
             try:
-                reader = _Reader(self._fp)
-                msgs = reader.messages(reader.root_ohdr)
-                links = reader.links(msgs)
+                with _guard(self.filename):
+                    reader = _Reader(self._fp)
+                    msgs = reader.messages(reader.root_ohdr)
+                    links = reader.links(msgs)
                 if links is None:
                     raise H5Error("root object is not a group")
                 self._root = Group(reader, "/", msgs, links)
-            except (struct.error, IndexError, ValueError) as e:
-                self.close()
-                raise H5Error(f"{self.filename}: truncated or corrupt HDF5 structure ({e})") from e
             except Exception:
                 self.close()
                 raise

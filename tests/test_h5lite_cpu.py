@@ -316,3 +316,41 @@ def test_encoder_feature_file_walk(tmp_path):
         want = np.concatenate([mats["a"], mats["sub/b"]]).astype(np.float32).mean(0)
         np.testing.assert_allclose(h5["feats"][()], want, rtol=1e-6)
         assert h5.attrs["feat_type"] == "patient"
+
+
+def test_reader_survives_corrupt_files():
+    """2 000 random mutations of a valid feature file (byte flips in the metadata, truncations, overwritten
+    addresses): the reader either reads the file or raises H5Error / KeyError -- never a raw parser exception, never an
+    allocation sized by a corrupt dataspace."""
+    buf = io.BytesIO()
+    with h5lite.File(buf, "w") as w:
+        w["coords"], w["feats"] = np.random.rand(50, 2), np.random.rand(50, 16).astype(np.float16)
+        w.attrs["unit"], w.attrs["tile_size_um"], w.attrs["extractor"] = "um", 256.0, "uni"
+    good = buf.getvalue()
+    rng = np.random.default_rng(1)
+    outcomes = {"ok": 0, "rejected": 0}
+    for _ in range(2000):
+        a = bytearray(good)
+        mode = rng.integers(0, 3)
+        if mode == 0:
+            for _ in range(rng.integers(1, 5)):
+                a[int(rng.integers(0, 1800))] = int(rng.integers(0, 256))
+        elif mode == 1:
+            a = a[: int(rng.integers(0, len(a)))]
+        else:
+            i = int(rng.integers(0, 1800))
+            a[i:i + 8] = rng.integers(0, 256, 8, dtype=np.uint8).tobytes()
+        try:
+            with h5lite.File(io.BytesIO(bytes(a))) as f:
+                for k in list(f.keys()):
+                    try:
+                        d = f[k]
+                        if isinstance(d, h5lite.Dataset):
+                            d[()], d.attrs
+                    except (OSError, KeyError):
+                        pass
+                dict(f.attrs)
+            outcomes["ok"] += 1
+        except OSError:
+            outcomes["rejected"] += 1
+    assert outcomes["ok"] > 100 and outcomes["rejected"] > 100, outcomes
