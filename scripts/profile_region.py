@@ -1,7 +1,7 @@
 """One warm unit of work between cudaProfilerStart/Stop, for ncu launch lists:
 
     ncu --profile-from-start off --metrics gpu__time_duration.sum,... --csv --log-file out.csv \\
-        python scripts/profile_region.py {vit_l16|virchow2|gigapath|resize|mil_deploy|mil_train|macenko}
+        python scripts/profile_region.py {vit_l16|virchow2|gigapath|resize|jpeg|mil_deploy|mil_train|macenko}
 """
 import sys
 from pathlib import Path
@@ -32,6 +32,23 @@ elif what == "resize":
 
     tiles = synthetic_he_tiles(768, 3, dev)
     unit = lambda: resize_center_crop(tiles, 256, 224)
+elif what == "jpeg":
+    import io
+
+    from PIL import Image
+
+    from bench_extra import synthetic_he_tiles
+    from stamp_b200 import jpeg
+
+    blobs = []
+    for t in synthetic_he_tiles(96, 3, dev).cpu().numpy():
+        b = io.BytesIO()
+        Image.fromarray(t).save(b, format="jpeg")
+        blobs.append(b.getvalue())
+    info, coef, quant = jpeg.entropy_decode(blobs * 8, max_workers=8)
+    cd, qd = coef.to(dev), quant.to(dev)
+    out = torch.empty((768, 224, 224, 3), dtype=torch.uint8, device=dev)
+    unit = lambda: jpeg.decode_coefficients(info, cd, qd, out=out)
 elif what == "mil_deploy":
     from stamp_b200.mil import VisionTransformer
 

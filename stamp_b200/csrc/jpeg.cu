@@ -8,9 +8,9 @@
 //   h2v2_fancy_upsample  (jdsample.c)  triangle filter 3/4 - 1/4, vertical then horizontal, biases 8 / 7
 //   ycc_rgb_convert      (jdcolor.c)   16-bit fixed-point YCbCr -> RGB
 // Two kernels per batch: (1) one thread per 8x8 block writes the component planes (Y at full resolution, Cb / Cr at
-// half or full resolution); (2) one thread per 2x2 output pixels up-samples the chroma around it and converts.  The
+// half or full resolution); (2) one thread per group of output pixels up-samples the chroma around it and converts.  The
 // planes of a batch (225 KB per 224 px tile) stay in L2 between the two launches; HBM sees the coefficients once and
-// the RGB tiles once.
+// the RGB tiles once.  (4:2:0: one thread per FOUR chroma samples = 2 x 8 output pixels.)
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -139,55 +139,83 @@ __device__ __forceinline__ void ycc_to_rgb(int y, int cb, int cr, uint8_t* o) {
     o[2] = static_cast<uint8_t>(clamp8(y + ((116130 * cb + 32768) >> 16)));                      // FIX(1.77200)
 }
 
-// 4:2:0 -- one thread per chroma sample = 2 x 2 output pixels
+// 4:2:0 -- one thread per 4 chroma samples of a chroma row = 2 rows x 8 columns of output pixels: the vertical sums
+// of the six chroma columns it touches are formed once, the luma and the output move as 64-bit words
 __global__ void __launch_bounds__(256)
 jpeg_color420_kernel(const uint8_t* __restrict__ planes, uint8_t* __restrict__ out, JpegGeom g, int n_tiles, int H, int W) {
     const int ds_w = (W + 1) >> 1, ds_h = (H + 1) >> 1;
+    const int groups = (ds_w + 3) >> 2;
     const long long gid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (gid >= static_cast<long long>(n_tiles) * ds_w * ds_h) return;
-    const int tile = static_cast<int>(gid / (ds_w * ds_h));
-    const int rem = static_cast<int>(gid - static_cast<long long>(tile) * ds_w * ds_h);
-    const int cy = rem / ds_w, cx = rem - cy * ds_w;
+    if (gid >= static_cast<long long>(n_tiles) * groups * ds_h) return;
+    const int tile = static_cast<int>(gid / (groups * ds_h));
+    const int rem = static_cast<int>(gid - static_cast<long long>(tile) * groups * ds_h);
+    const int cy = rem / groups, cx0 = (rem - cy * groups) * 4;
     const uint8_t* base = planes + tile * g.plane_bytes_per_tile;
-    const int ypitch = g.bx[0] * 8, cpitch = g.bx[1] * 8;
-    // chroma neighbourhood with replicated edges (context rows / first-last column special cases of libjpeg)
+    const int ypitch = g.bx[0] * 8, cpitch = g.bx[1] * 8;   // multiples of 8; the planes are padded to whole blocks
+    // chroma rows with replicated edges (libjpeg's context rows), columns cx0-1 .. cx0+4 clamped to the plane
     const int ym = max(cy - 1, 0), yp = min(cy + 1, ds_h - 1);
-    const int xm = max(cx - 1, 0), xp = min(cx + 1, ds_w - 1);
-    int up[2][4];   // [plane][output pixel of the 2 x 2 quad: (0,0) (0,1) (1,0) (1,1)]
+    const int xl = max(cx0 - 1, 0);
+    int up[2][2][8];   // [plane][output row][output column]
 #pragma unroll
     for (int pl = 0; pl < 2; ++pl) {
         const uint8_t* cp = base + g.plane_off[1 + pl];
-        const int a0 = cp[ym * cpitch + xm], a1 = cp[ym * cpitch + cx], a2 = cp[ym * cpitch + xp];
-        const int b0 = cp[cy * cpitch + xm], b1 = cp[cy * cpitch + cx], b2 = cp[cy * cpitch + xp];
-        const int c0 = cp[yp * cpitch + xm], c1 = cp[yp * cpitch + cx], c2 = cp[yp * cpitch + xp];
-        // vertical: 3 * nearest + next-nearest row; upper output row looks up, lower looks down
-        const int t_l = 3 * b0 + a0, t_c = 3 * b1 + a1, t_r = 3 * b2 + a2;
-        const int u_l = 3 * b0 + c0, u_c = 3 * b1 + c1, u_r = 3 * b2 + c2;
+        int t[6], u[6];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const uint8_t* row = cp + (r == 0 ? ym : (r == 1 ? cy : yp)) * cpitch;
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(row + cx0);     // cx0 % 4 == 0, pitch % 8 == 0
+            int v[6];
+            v[0] = row[xl];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[1 + k] = min(cx0 + k, ds_w - 1) == cx0 + k ? static_cast<int>((w >> (8 * k)) & 255u) : 0;
+            // columns past the last chroma sample replicate it (right edge of the image)
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (cx0 + k > ds_w - 1) v[1 + k] = v[k];
+            v[5] = (cx0 + 4 <= ds_w - 1) ? static_cast<int>(row[cx0 + 4]) : v[4];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                if (r == 0) t[k] = v[k];
+                else if (r == 1) { t[k] += 3 * v[k]; u[k] = 3 * v[k]; }
+                else u[k] += v[k];
+            }
+        }
         // horizontal: even column looks left (bias 8), odd column looks right (bias 7); at the plane's first / last
-        // column the missing neighbour is the column itself (xm == cx / xp == cx), which reproduces the special cases
-        up[pl][0] = (3 * t_c + t_l + 8) >> 4;
-        up[pl][1] = (3 * t_c + t_r + 7) >> 4;
-        up[pl][2] = (3 * u_c + u_l + 8) >> 4;
-        up[pl][3] = (3 * u_c + u_r + 7) >> 4;
+        // column the neighbour is the column itself, which reproduces libjpeg's special cases
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            up[pl][0][2 * k] = (3 * t[1 + k] + t[k] + 8) >> 4;
+            up[pl][0][2 * k + 1] = (3 * t[1 + k] + t[2 + k] + 7) >> 4;
+            up[pl][1][2 * k] = (3 * u[1 + k] + u[k] + 8) >> 4;
+            up[pl][1][2 * k + 1] = (3 * u[1 + k] + u[2 + k] + 7) >> 4;
+        }
     }
     const uint8_t* yp0 = base + g.plane_off[0];
     uint8_t* o = out + static_cast<long long>(tile) * H * W * 3;
+    const int x0 = 2 * cx0;
+    const int ncol = min(8, W - x0);
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
         const int y = 2 * cy + dy;
         if (y >= H) break;
-        uint8_t px[6];
-        const int x0 = 2 * cx;
-        ycc_to_rgb(yp0[y * ypitch + x0], up[0][2 * dy], up[1][2 * dy], px);
-        const bool two = x0 + 1 < W;
-        if (two) ycc_to_rgb(yp0[y * ypitch + x0 + 1], up[0][2 * dy + 1], up[1][2 * dy + 1], px + 3);
+        const uint2 yw = *reinterpret_cast<const uint2*>(yp0 + y * ypitch + x0);   // x0 % 8 == 0
+        uint8_t px[24];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int yy = static_cast<int>(((k < 4 ? yw.x : yw.y) >> (8 * (k & 3))) & 255u);
+            ycc_to_rgb(yy, up[0][dy][k], up[1][dy][k], px + 3 * k);
+        }
         uint8_t* d = o + (static_cast<long long>(y) * W + x0) * 3;
-        if (two && ((reinterpret_cast<uintptr_t>(d) & 1) == 0)) {
-            reinterpret_cast<uint16_t*>(d)[0] = static_cast<uint16_t>(px[0] | (px[1] << 8));
-            reinterpret_cast<uint16_t*>(d)[1] = static_cast<uint16_t>(px[2] | (px[3] << 8));
-            reinterpret_cast<uint16_t*>(d)[2] = static_cast<uint16_t>(px[4] | (px[5] << 8));
+        if (ncol == 8 && (reinterpret_cast<uintptr_t>(d) & 7) == 0) {
+            uint32_t w32[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                w32[k] = px[4 * k] | (px[4 * k + 1] << 8) | (px[4 * k + 2] << 16) | (static_cast<uint32_t>(px[4 * k + 3]) << 24);
+            reinterpret_cast<uint2*>(d)[0] = make_uint2(w32[0], w32[1]);
+            reinterpret_cast<uint2*>(d)[1] = make_uint2(w32[2], w32[3]);
+            reinterpret_cast<uint2*>(d)[2] = make_uint2(w32[4], w32[5]);
         } else {
-            for (int k = 0; k < (two ? 6 : 3); ++k) d[k] = px[k];
+            for (int k = 0; k < 3 * ncol; ++k) d[k] = px[k];
         }
     }
 }
@@ -256,8 +284,8 @@ extern "C" int stamp_jpeg_decode_coefs_u8(const StampJpegInfo* info, const int16
     const long long blocks = static_cast<long long>(n_tiles) * g.blocks_per_tile;
     jpeg_idct_kernel<<<static_cast<unsigned>((blocks + 127) / 128), 128, 0, stream>>>(coef, quant, planes, g, n_tiles);
     if (info->h[0] == 2) {
-        const long long quads = static_cast<long long>(n_tiles) * ((W + 1) / 2) * ((H + 1) / 2);
-        jpeg_color420_kernel<<<static_cast<unsigned>((quads + 255) / 256), 256, 0, stream>>>(planes, out, g, n_tiles, H, W);
+        const long long groups = static_cast<long long>(n_tiles) * (((W + 1) / 2 + 3) / 4) * ((H + 1) / 2);
+        jpeg_color420_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, stream>>>(planes, out, g, n_tiles, H, W);
     } else {
         const long long px = static_cast<long long>(n_tiles) * H * W;
         jpeg_color444_kernel<<<static_cast<unsigned>((px + 255) / 256), 256, 0, stream>>>(planes, out, g, n_tiles, H, W);
