@@ -340,6 +340,85 @@ def encoding_block(dev, rank: int, world: int, slides_per_gpu: int = 32) -> dict
                     "take < 1 ms per slide"}
 
 
+def cache_to_features_block(dev, n_tiles: int = 6144, batch: int = 192) -> dict:
+    """One cached slide end to end, the way `stamp preprocess` sees a slide whose tiles are already in the tile cache
+    (tiling.py:380-406 -> preprocessing/__init__.py:306-366): JPEG tile cache (zip) -> tiles -> Canny tissue filter ->
+    UNI ViT-L/16 -> fp16 features + coordinates -> the slide's `.h5`.  Timed twice: tiles decoded by Pillow on a thread
+    pool into pinned host memory (the reference's decoder) and tiles Huffman-decoded on the host, finished on the GPU."""
+    import io
+    import json
+    import shutil
+    import tempfile
+    import zipfile
+    from pathlib import Path
+
+    from PIL import Image
+
+    from stamp_b200 import features
+    from stamp_b200.extractor import extract_cache_features, extract_slide_features, uni
+    from stamp_b200.tiling import has_enough_texture, tiles_from_cache_file, tiles_from_cache_file_gpu
+
+    ext = uni(weights="random", max_batch=batch)
+    ext.model.to(dev).eval()
+    root = Path(tempfile.mkdtemp(prefix="stamp_b200_cache_"))
+    try:
+        pool = synthetic_he_tiles(128, seed=11, device=dev).cpu().numpy()
+        blobs = []
+        for t in pool:
+            b = io.BytesIO()
+            Image.fromarray(t).save(b, format="jpeg")
+            blobs.append(b.getvalue())
+        path = root / "slide.zip"
+        with zipfile.ZipFile(path, "w", compression=zipfile.ZIP_STORED) as zf:
+            zf.writestr("tiler_params.json", json.dumps({"tile_ext": "jpg", "tile_size_um": 256.0, "tile_size_px": 224}))
+            for i in range(n_tiles):
+                zf.writestr(f"tile_({256.0 * (i % 64)}, {256.0 * (i // 64)}).jpg", blobs[i % len(blobs)])
+
+        def run(gpu_decode: bool, out_name: str) -> tuple[float, int]:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if gpu_decode:
+                tiles, coords, _ = tiles_from_cache_file_gpu(path, dev, max_workers=8)
+                keep = has_enough_texture(tiles, 0.02)
+                tiles, coords = tiles[keep], coords[keep.cpu()]
+            else:
+                tiles, coords, _ = tiles_from_cache_file(path, max_workers=8)
+                keep = torch.cat([has_enough_texture(tiles[s:s + 768].to(dev), 0.02) for s in range(0, len(tiles), 768)]).cpu()
+                tiles, coords = tiles[keep], coords[keep]
+            feats = extract_slide_features(ext, tiles.contiguous(), dev, batch_size=batch)
+            features.write_tile_features(root / out_name, feats, coords.numpy(), extractor="uni", tile_size_um=256.0,
+                                         tile_size_px=224)
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0, int(keep.sum())
+
+        def run_pipelined(out_name: str) -> tuple[float, int]:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            feats, coords, _ = extract_cache_features(ext, path, dev, batch_size=batch, canny_cutoff=0.02, max_workers=8)
+            features.write_tile_features(root / out_name, feats, coords.numpy(), extractor="uni", tile_size_um=256.0,
+                                         tile_size_px=224)
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0, feats.shape[0]
+
+        run(True, "warm.h5")
+        run_pipelined("warm2.h5")
+        t_pipe, kept_pipe = run_pipelined("pipe.h5")
+        t_gpu, kept = run(True, "gpu.h5")
+        t_pil, kept_p = run(False, "pil.h5")
+        ref_feats = torch.from_numpy(features.read_tile_features(str(root / "pil.h5"))[0])
+        same = all(torch.equal(torch.from_numpy(features.read_tile_features(str(root / n))[0]), ref_feats)
+                   for n in ("gpu.h5", "pipe.h5")) and kept_pipe == kept
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    return {"metric": "cached slide -> feature file, tiles/s (JPEG tile cache -> tissue filter -> UNI ViT-L/16 -> .h5)",
+            "tiles": n_tiles, "tiles_kept": kept, "pipelined_tiles_per_s": n_tiles / t_pipe,
+            "gpu_decode_tiles_per_s": n_tiles / t_gpu,
+            "pillow_decode_tiles_per_s": n_tiles / t_pil, "identical_feature_files": bool(same and kept == kept_p),
+            "note": "8 host threads in both arms; GPU arm: Huffman on the host, IDCT / up-sampling / colour on the GPU, "
+                    "tiles never leave HBM (pipelined: extractor.extract_cache_features, decode of batch i+1 overlaps the encoder on "
+                    "batch i); Pillow arm: decoded tiles staged in pinned memory and streamed in"}
+
+
 def extractors_block(dev, peak_tf: float, batch: int = 96) -> dict:
     """the other tile encoders the reference ships (uni2.py:18-32, h_optimus_0.py:14-28) on the same
     kernels -- device-resident tiles/s at batch 96 with random-init weights of the architecture."""

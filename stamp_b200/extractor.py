@@ -212,3 +212,113 @@ def extract_to_feature_files(extractor: Extractor, slides, output_dir: str | Pat
                           tile_size_px=tile_size_px, code_hash=code_hash or "")
             written.append(path)
     return written
+
+
+def extract_cache_features(extractor: Extractor, cache_file_path: str | Path, device: torch.device | str = "cuda", *,
+                           batch_size: int = 192, canny_cutoff: float | None = 0.02, max_workers: int = 8
+                           ) -> tuple[Tensor, Tensor, dict]:
+    """A cached slide straight to features: what ``extract_`` does for a slide whose tiles are in the JPEG tile cache
+    (``_tiles_from_cache_file`` src/stamp/preprocessing/tiling.py:380-406 feeding the loop at
+    preprocessing/__init__.py:306-327), as a three-stage pipeline that keeps the tile encoder busy:
+
+      host thread   zip -> Huffman decode of batch i+1 (thread pool, GIL released) -> pinned staging -> H2D
+      side stream   inverse DCT / up-sampling / colour of batch i+1, Canny tissue filter (``canny_cutoff``; the
+                    reference applies it before caching, ``None`` skips it)
+      main stream   tile encoder on the kept tiles of batch i
+
+    Returns (features fp16 [n_kept, D] on the host, coordinates [n_kept, 2] in microns, tiler parameters); pixels,
+    decisions and therefore features are those of the Pillow + OpenCV path."""
+    import json
+    import queue
+    import re
+    import threading
+    from zipfile import ZipFile
+
+    from . import jpeg
+    from .tiling import has_enough_texture
+
+    device = torch.device(device)
+    model = extractor.model
+    zf = ZipFile(Path(cache_file_path), "r")
+    params = json.loads(zf.read("tiler_params.json").decode())
+    ext = params.get("tile_ext", "jpg")
+    if ext.lower() not in ("jpg", "jpeg"):
+        zf.close()
+        raise ValueError(f"tile cache holds {ext!r} tiles; the GPU decoder reads JPEG caches only")
+    pat = re.compile(rf"tile_\((\d+\.\d+), (\d+\.\d+)\)\.{re.escape(ext)}")
+    names, coords = [], []
+    for name in zf.namelist():
+        m = pat.fullmatch(name)
+        if m is not None:
+            names.append(name)
+            coords.append((float(m.group(1)), float(m.group(2))))
+    coords_t = torch.tensor(coords, dtype=torch.float32).reshape(-1, 2)
+    if not names:
+        zf.close()
+        return torch.empty((0, model.arch.dim), dtype=torch.float16), coords_t, params
+    info = jpeg.read_header(zf.read(names[0]))
+    n_coef = jpeg.coef_count(info)
+    starts = list(range(0, len(names), batch_size))
+    side = torch.cuda.Stream(device=device)
+    main = torch.cuda.current_stream(device)
+    stage = [(torch.empty((batch_size, n_coef), dtype=torch.int16).pin_memory(),
+              torch.empty((batch_size, 3, 64), dtype=torch.int16).pin_memory()) for _ in range(2)]
+    copied: list[torch.cuda.Event | None] = [None, None]
+    ready: queue.Queue = queue.Queue(maxsize=2)
+
+    def producer() -> None:
+        try:
+            for i, s in enumerate(starts):
+                part = [zf.read(n) for n in names[s:s + batch_size]]   # the zip is read here, behind the encoder
+                if copied[i % 2] is not None:
+                    copied[i % 2].synchronize()              # the staging set's previous H2D copy has finished
+                _, coef, quant = jpeg.entropy_decode(part, max_workers=max_workers, out=stage[i % 2])
+                with torch.cuda.stream(side):
+                    cd, qd = coef.to(device, non_blocking=True), quant.to(device, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                copied[i % 2] = ev
+                ready.put((s, len(part), cd, qd))
+            ready.put(None)
+        except BaseException as e:  # noqa: BLE001 - handed to the consumer
+            ready.put(e)
+        finally:
+            zf.close()
+
+    th = threading.Thread(target=producer, name="stamp-b200-jpeg-feed", daemon=True)
+    th.start()
+    feats_dev, kept_idx = [], []
+    while True:
+        item = ready.get()
+        if item is None:
+            break
+        if isinstance(item, BaseException):
+            th.join()
+            raise item
+        s, n, cd, qd = item
+        with torch.cuda.stream(side):
+            tiles = jpeg.decode_coefficients(info, cd, qd)
+            cd.record_stream(side)
+            qd.record_stream(side)
+            if canny_cutoff is not None:
+                keep = torch.nonzero(has_enough_texture(tiles, canny_cutoff)).squeeze(1)   # syncs the side stream only
+                tiles = tiles[keep]
+                kept_idx.append(keep.cpu() + s)
+            else:
+                kept_idx.append(torch.arange(s, s + n))
+            done = torch.cuda.Event()
+            done.record(side)
+        if tiles.shape[0]:
+            main.wait_event(done)
+            tiles.record_stream(main)
+            feats_dev.append(model(tiles))
+    th.join()
+    idx = torch.cat(kept_idx) if kept_idx else torch.empty(0, dtype=torch.long)
+    if feats_dev:
+        feats = torch.cat(feats_dev)
+        host = torch.empty(feats.shape, dtype=torch.float16).pin_memory()
+        host.copy_(feats, non_blocking=True)
+        main.synchronize()
+    else:
+        host = torch.empty((0, model.arch.dim), dtype=torch.float16)
+    return host, coords_t[idx], params

@@ -76,6 +76,26 @@ def test_tile_cache_zip_decoded_on_the_gpu(cuda_device, tmp_path):
                     transform=pil_to_u8_hwc, identifier="tiny")
     assert torch.equal(extract_slide_features(ext, dev[:100], cuda_device, batch_size=48),
                        extract_slide_features(ext, host[:100], cuda_device, batch_size=48))
+    # ... and the pipelined cache -> features path (decode of batch i+1 behind the encoder on batch i, tissue filter in
+    # between) keeps exactly the tiles the Pillow + OpenCV path keeps and returns the same features
+    from stamp_b200.extractor import extract_cache_features
+    from stamp_b200.tiling import has_enough_texture
+
+    blank = np.full((224, 224, 3), 236, dtype=np.uint8)
+    path2 = tmp_path / "slide2.zip"
+    with zipfile.ZipFile(path2, "w") as zf:
+        zf.writestr("tiler_params.json", json.dumps({"tile_ext": "jpg", "tile_size_um": 256.0}))
+        for i in range(130):
+            img = blank if i % 7 == 3 else np.roll(tiles[i % 40], 3 * i, axis=0)
+            zf.writestr(f"tile_({256.0 * (i % 12)}, {256.0 * (i // 12)}).jpg", _jpeg(img))
+    host2, coords2, _ = tiles_from_cache_file(path2, pin_memory=False)
+    keep = has_enough_texture(host2.to(cuda_device), 0.02).cpu()
+    assert 0 < int(keep.sum()) < 130 and not bool(keep[3])
+    want = extract_slide_features(ext, host2[keep], cuda_device, batch_size=48)
+    got, got_coords, params2 = extract_cache_features(ext, path2, cuda_device, batch_size=48, canny_cutoff=0.02, max_workers=2)
+    assert params2["tile_size_um"] == 256.0 and torch.equal(got_coords, coords2[keep]) and torch.equal(got, want)
+    every, every_coords, _ = extract_cache_features(ext, path2, cuda_device, batch_size=64, canny_cutoff=None)
+    assert every.shape[0] == 130 and torch.equal(every_coords, coords2)
     with zipfile.ZipFile(tmp_path / "png.zip", "w") as zf:
         zf.writestr("tiler_params.json", json.dumps({"tile_ext": "png"}))
     with pytest.raises(ValueError):
