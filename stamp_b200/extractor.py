@@ -214,16 +214,52 @@ def extract_to_feature_files(extractor: Extractor, slides, output_dir: str | Pat
     return written
 
 
+def _consume(ready, th, side, main, info, model, canny_cutoff, stain_normalize, feats_dev, kept_idx) -> None:
+    """Consumer side of ``extract_cache_features``: GPU decode + tissue filter (+ stain normalisation) on the side
+    stream, tile encoder on the main stream."""
+    from . import jpeg
+    from .tiling import has_enough_texture
+
+    while True:
+        item = ready.get()
+        if item is None:
+            return
+        if isinstance(item, BaseException):
+            raise item
+        s, n, cd, qd = item
+        with torch.cuda.stream(side):
+            tiles = jpeg.decode_coefficients(info, cd, qd)
+            cd.record_stream(side)
+            qd.record_stream(side)
+            if canny_cutoff is not None:
+                keep = torch.nonzero(has_enough_texture(tiles, canny_cutoff)).squeeze(1)   # syncs the side stream only
+                tiles = tiles[keep]
+                kept_idx.append(keep.cpu() + s)
+            else:
+                kept_idx.append(torch.arange(s, s + n))
+            if stain_normalize and tiles.shape[0]:
+                from .macenko import macenko_normalize
+
+                tiles = macenko_normalize(tiles.contiguous())
+            done = torch.cuda.Event()
+            done.record(side)
+        if tiles.shape[0]:
+            main.wait_event(done)
+            tiles.record_stream(main)
+            feats_dev.append(model(tiles))
+
+
 def extract_cache_features(extractor: Extractor, cache_file_path: str | Path, device: torch.device | str = "cuda", *,
-                           batch_size: int = 192, canny_cutoff: float | None = 0.02, max_workers: int = 8
-                           ) -> tuple[Tensor, Tensor, dict]:
+                           batch_size: int = 192, canny_cutoff: float | None = 0.02, max_workers: int = 8,
+                           stain_normalize: bool = False) -> tuple[Tensor, Tensor, dict]:
     """A cached slide straight to features: what ``extract_`` does for a slide whose tiles are in the JPEG tile cache
     (``_tiles_from_cache_file`` src/stamp/preprocessing/tiling.py:380-406 feeding the loop at
     preprocessing/__init__.py:306-327), as a three-stage pipeline that keeps the tile encoder busy:
 
       host thread   zip -> Huffman decode of batch i+1 (thread pool, GIL released) -> pinned staging -> H2D
       side stream   inverse DCT / up-sampling / colour of batch i+1, Canny tissue filter (``canny_cutoff``; the
-                    reference applies it before caching, ``None`` skips it)
+                    reference applies it before caching, ``None`` skips it), Macenko stain normalisation fitted on
+                    the batch's kept tiles (``stain_normalize``; the new stage of BASELINE configs[2])
       main stream   tile encoder on the kept tiles of batch i
 
     Returns (features fp16 [n_kept, D] on the host, coordinates [n_kept, 2] in microns, tiler parameters); pixels,
@@ -266,9 +302,22 @@ def extract_cache_features(extractor: Extractor, cache_file_path: str | Path, de
     copied: list[torch.cuda.Event | None] = [None, None]
     ready: queue.Queue = queue.Queue(maxsize=2)
 
+    stop = threading.Event()
+
+    def hand_over(item) -> bool:
+        while not stop.is_set():
+            try:
+                ready.put(item, timeout=0.2)
+                return True
+            except queue.Full:
+                continue
+        return False
+
     def producer() -> None:
         try:
             for i, s in enumerate(starts):
+                if stop.is_set():
+                    return
                 part = [zf.read(n) for n in names[s:s + batch_size]]   # the zip is read here, behind the encoder
                 if copied[i % 2] is not None:
                     copied[i % 2].synchronize()              # the staging set's previous H2D copy has finished
@@ -278,41 +327,22 @@ def extract_cache_features(extractor: Extractor, cache_file_path: str | Path, de
                     ev = torch.cuda.Event()
                     ev.record(side)
                 copied[i % 2] = ev
-                ready.put((s, len(part), cd, qd))
-            ready.put(None)
+                if not hand_over((s, len(part), cd, qd)):
+                    return
+            hand_over(None)
         except BaseException as e:  # noqa: BLE001 - handed to the consumer
-            ready.put(e)
+            hand_over(e)
         finally:
             zf.close()
 
     th = threading.Thread(target=producer, name="stamp-b200-jpeg-feed", daemon=True)
     th.start()
     feats_dev, kept_idx = [], []
-    while True:
-        item = ready.get()
-        if item is None:
-            break
-        if isinstance(item, BaseException):
-            th.join()
-            raise item
-        s, n, cd, qd = item
-        with torch.cuda.stream(side):
-            tiles = jpeg.decode_coefficients(info, cd, qd)
-            cd.record_stream(side)
-            qd.record_stream(side)
-            if canny_cutoff is not None:
-                keep = torch.nonzero(has_enough_texture(tiles, canny_cutoff)).squeeze(1)   # syncs the side stream only
-                tiles = tiles[keep]
-                kept_idx.append(keep.cpu() + s)
-            else:
-                kept_idx.append(torch.arange(s, s + n))
-            done = torch.cuda.Event()
-            done.record(side)
-        if tiles.shape[0]:
-            main.wait_event(done)
-            tiles.record_stream(main)
-            feats_dev.append(model(tiles))
-    th.join()
+    try:
+        _consume(ready, th, side, main, info, model, canny_cutoff, stain_normalize, feats_dev, kept_idx)
+    finally:
+        stop.set()        # a consumer error must not leave the feed thread blocked on a full queue
+        th.join()
     idx = torch.cat(kept_idx) if kept_idx else torch.empty(0, dtype=torch.long)
     if feats_dev:
         feats = torch.cat(feats_dev)
