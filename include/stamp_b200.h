@@ -227,6 +227,20 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w,
                       const float* coords, const uint8_t* mask, float* logits, int B, int N,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Ragged batches of the same forward (deploy over bags of different lengths in ONE pass: the dense layers see all
+ * rows of all bags, the long-bag attention kernel walks every bag on its own): the bags are concatenated along the
+ * token axis WITH their class-token row, bag b = rows seq_off[b] .. seq_off[b+1] (S_b = N_b + 1 tokens).
+ *   tokens_f16 fp16 [total_rows, dim_input]: row seq_off[b] is a placeholder (any finite values), the tiles follow;
+ *   coords_s   fp32 [total_rows, 2]: (0, 0) in the class-token rows (vision_tranformer.py:349-351); NULL without ALiBi;
+ *   seq_off    int32 [B + 1] ON THE DEVICE; S_max = the longest bag in tokens; logits fp32 [B, dim_output].
+ * Unmasked forwards with head dimension 64 only (STAMP_ERR_UNSUPPORTED otherwise: call stamp_mil_forward per bag).
+ * Same arithmetic per bag as stamp_mil_forward (rows and bags are independent), hence the same results.
+ * replaces: the per-patient loop of _predict, src/stamp/modeling/deploy.py:390-456. */
+size_t stamp_mil_ragged_workspace_bytes(const StampMilConfig* cfg, int B, int total_rows, int S_max);
+int stamp_mil_forward_ragged(const StampMilConfig* cfg, const StampMilWeights* w, const StampMilLayer* layers,
+                             const void* tokens_f16, const float* coords_s, const int* seq_off, int B, int total_rows,
+                             int S_max, float* logits, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * ALiBi Transformer-MIL training step (forward with checkpoints, backward, loss, optimizer).
  * replaces: LitTileClassifier.training_step -> _step (src/stamp/modeling/models/__init__.py:239-286:

@@ -29,6 +29,12 @@ struct AttnParams {
     // long-bag tcgen05 kernel, third generation (attention_mil_v3.cu): pre-computed 16-bit distance matrix
     // [B, S, ld = S rounded up to 64] scaled by dscale[2b]; slope[h] is then applied in fp32 in the epilogue
     const uint16_t* dist16;
+    // ragged batches (attention_mil_v3.cu only): the bags are concatenated along the token axis, bag b owns the rows
+    // seq_off[b] .. seq_off[b+1] of q / k / v / out (batch strides unused) and of the distance matrix, which then has
+    // ONE row pitch for all bags (dist_ld); S_max = longest bag (grid size); S = total number of rows
+    const int* seq_off;      // device, [B + 1], or null
+    int S_max;
+    long long dist_ld;
     int q_rows;              // 0: every token is a query; n > 0: only the first n tokens' outputs are needed (rows up
                              // to the end of their query tile may still be written)
 };
@@ -53,6 +59,10 @@ size_t mil_dist16_bytes(int B, int S);
 // coords_s [B, S, 2] -> scale [B][2] = {2^-e, 2^e} (largest distance of the bag in (8192, 16384]) and
 // dist16 [B, S, ld] = |x_q - x_k| * 2^-e as fp16 (bf16 != 0: bfloat16)
 size_t mil_dist16_scratch_bytes(int B);
+// ragged form: coords_s [total rows, 2], bag b = rows seq_off[b] .. seq_off[b+1]; dist16 [total rows, ld] with
+// ld >= S_max rounded up to 64 (zeros past each bag's own length)
+int mil_dist16_ragged(const float* coords_s, const int* seq_off, int B, int S_max, long long ld, float* scale,
+                      uint16_t* dist16, void* bbox_scratch, cudaStream_t stream);
 int mil_dist16(const float* coords_s, int B, int S, int bf16, float* scale, uint16_t* dist16, void* bbox_scratch,
                cudaStream_t stream);
 

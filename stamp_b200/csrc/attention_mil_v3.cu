@@ -83,9 +83,13 @@ constexpr int DIST_PARTS = 32;   // partial bounding boxes per bag (one per bloc
 
 // pass 1, grid (DIST_PARTS, B): partial bounding boxes of the token coordinates, bbox[b][part] = {xmin, xmax, ymin, ymax}
 __global__ void __launch_bounds__(256)
-dist_bbox_kernel(const float2* __restrict__ coords, int S, float4* __restrict__ bbox) {
+dist_bbox_kernel(const float2* __restrict__ coords, int S, float4* __restrict__ bbox, const int* __restrict__ seq_off) {
     const int b = blockIdx.y;
     const float2* c = coords + static_cast<long long>(b) * S;
+    if (seq_off != nullptr) {   // ragged batch: bag b = rows seq_off[b] .. seq_off[b+1]
+        c = coords + seq_off[b];
+        S = seq_off[b + 1] - seq_off[b];
+    }
     float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
         const float2 v = __ldg(c + i);
@@ -124,8 +128,17 @@ __device__ __forceinline__ int dist_exponent(const float4* __restrict__ bbox_b) 
 // store per row; a warp writes 512 contiguous bytes).  Block (0, 0) of every bag also publishes scale[b] = {2^-e, 2^e}.
 __global__ void __launch_bounds__(256)
 dist16_kernel(const float2* __restrict__ coords, const float4* __restrict__ bbox, float* __restrict__ scale,
-              uint16_t* __restrict__ out, int S, long long ld, long long batch_stride, int bf16) {
+              uint16_t* __restrict__ out, int S, long long ld, long long batch_stride, int bf16,
+              const int* __restrict__ seq_off) {
     const int b = blockIdx.z;
+    long long row0 = static_cast<long long>(b) * S;
+    if (seq_off != nullptr) {   // ragged batch: common row pitch, bag b starts at row seq_off[b]
+        row0 = seq_off[b];
+        S = seq_off[b + 1] - seq_off[b];
+        batch_stride = 0;
+        out += row0 * ld;
+        if (blockIdx.y * 64 >= S) return;
+    }
     const int e = dist_exponent(bbox + b * DIST_PARTS);     // every warp computes the same value
     const float g = exp2f(static_cast<float>(-e));
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -134,7 +147,7 @@ dist16_kernel(const float2* __restrict__ coords, const float4* __restrict__ bbox
     }
     const int k0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 8;
     if (k0 >= ld) return;
-    const float2* c = coords + static_cast<long long>(b) * S;
+    const float2* c = coords + row0;
     float2 ck[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) ck[j] = (k0 + j < S) ? __ldg(c + k0 + j) : make_float2(0.f, 0.f);
@@ -187,7 +200,17 @@ mil_attn_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
     // the heads of one (bag, query tile) are adjacent CTAs: they stream the same D tiles through L2 together
     const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
     const int q0 = blockIdx.y * 128;
-    const int S = p.S;
+    int S = p.S;
+    int row0 = 0, bc = b;           // first row of the bag inside the tensor maps, batch coordinate
+    if (!TRAIN && p.seq_off != nullptr) {
+        // ragged batch: the bags are concatenated along the row axis of 2-D views.  Rows past a bag's end belong to
+        // the next bag (not zero-filled like in the per-bag maps): their scores are masked by `nvalid`, their V rows
+        // meet P = 0 and zero distance columns, query rows past the end are computed and never stored.
+        row0 = __ldg(p.seq_off + b);
+        S = __ldg(p.seq_off + b + 1) - row0;
+        bc = 0;
+        if (q0 >= S) return;        // uniform for the CTA, before any barrier / tensor-memory allocation
+    }
     const int nkt = (S + 63) / 64;
 
     if (warp == 0 && lane == 0) {
@@ -224,22 +247,22 @@ mil_attn_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
         // ------------------------------------ TMA producer ------------------------------------
         if (lane == 0) {
             mbar_expect_tx(qfull, QT_BYTES);
-            tma_load_3d(sQ, &tm_q, qfull, h * 64, q0, b);
+            tma_load_3d(sQ, &tm_q, qfull, h * 64, row0 + q0, bc);
             // two rings served by one thread, whichever has a free slot: K tiles run up to K_STAGES ahead of the
             // products (the next S must never wait for a load), V / D tiles recycle as their products retire
             int ki = 0, vi = 0;
             while (ki < nkt || vi < nkt) {
                 if (ki < nkt && mbar_try_wait(&kempty[ki % K_STAGES], ((ki / K_STAGES) & 1) ^ 1)) {
                     mbar_expect_tx(&kfull[ki % K_STAGES], KV_BYTES);
-                    tma_load_3d(sK + (ki % K_STAGES) * KV_BYTES, &tm_k, &kfull[ki % K_STAGES], k_col0 + h * 64, ki * 64, b);
+                    tma_load_3d(sK + (ki % K_STAGES) * KV_BYTES, &tm_k, &kfull[ki % K_STAGES], k_col0 + h * 64, row0 + ki * 64, bc);
                     ++ki;
                     continue;
                 }
                 if (vi < nkt && mbar_try_wait(&empty[vi & 1], ((vi >> 1) & 1) ^ 1)) {
                     uint8_t* st = sVD + (vi & 1) * VD_BYTES;
                     mbar_expect_tx(&full[vi & 1], ALIBI ? VD_BYTES : KV_BYTES);
-                    tma_load_3d(st, &tm_v, &full[vi & 1], h * 64, vi * 64, b);
-                    if constexpr (ALIBI) tma_load_3d(st + KV_BYTES, &tm_d, &full[vi & 1], vi * 64, q0, b);
+                    tma_load_3d(st, &tm_v, &full[vi & 1], h * 64, row0 + vi * 64, bc);
+                    if constexpr (ALIBI) tma_load_3d(st + KV_BYTES, &tm_d, &full[vi & 1], vi * 64, row0 + q0, bc);
                     ++vi;
                 }
             }
@@ -394,7 +417,7 @@ mil_attn_v3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
             const float unscale = __ldg(p.dscale + 2 * b + 1);
             coef = (TRAIN ? __ldg(t.inv_rm + h) : __ldg(p.slope + h)) * unscale;
         }
-        const long long obase = b * p.out_batch_stride + static_cast<long long>(row) * p.out_row_stride + h * 64;
+        const long long obase = bc * p.out_batch_stride + static_cast<long long>(row0 + row) * p.out_row_stride + h * 64;
         if constexpr (TRAIN) {
             if (row < S) t.lse2[(static_cast<long long>(b) * p.H + h) * S + row] = ms + log2f(lt);
         }
@@ -475,7 +498,8 @@ int launch_v3(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMa
             return SB_ERR_CUDA;
         configured = true;
     }
-    dim3 grid(p.B * p.H, (p.S + 127) / 128);
+    const int s_grid = (p.seq_off != nullptr) ? p.S_max : p.S;
+    dim3 grid(p.B * p.H, (s_grid + 127) / 128);
     ProfScope prof(PROF_ATTN, 4.0 * p.B * p.H * static_cast<double>(p.S) * p.S * 64, stream);
     mil_attn_v3_kernel<ALIBI, TRAIN><<<grid, V3_THREADS, V3Smem::total, stream>>>(tm_q, tm_k, tm_v, tm_d, p, k_col0, t,
                                                                                   g_v3_eager ? 0.f : 8.f);
@@ -504,11 +528,28 @@ int mil_dist16(const float* coords_s, int B, int S, int bf16, float* scale, uint
     const long long ld = (static_cast<long long>(S) + 63) / 64 * 64;
     ProfScope prof(PROF_ROWOP, static_cast<double>(B) * S * ld * 2.0, stream);
     dist_bbox_kernel<<<dim3(DIST_PARTS, B), 256, 0, stream>>>(reinterpret_cast<const float2*>(coords_s), S,
-                                                              static_cast<float4*>(bbox_scratch));
+                                                              static_cast<float4*>(bbox_scratch), nullptr);
     count_launch();
     dim3 grid(static_cast<unsigned>((ld + 255) / 256), static_cast<unsigned>((S + 63) / 64), B);
     dist16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float2*>(coords_s), static_cast<const float4*>(bbox_scratch),
-                                            scale, dist16, S, ld, static_cast<long long>(S) * ld, bf16);
+                                            scale, dist16, S, ld, static_cast<long long>(S) * ld, bf16, nullptr);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+int mil_dist16_ragged(const float* coords_s, const int* seq_off, int B, int S_max, long long ld, float* scale,
+                      uint16_t* dist16, void* bbox_scratch, cudaStream_t stream) {
+    if (coords_s == nullptr || seq_off == nullptr || scale == nullptr || dist16 == nullptr || bbox_scratch == nullptr ||
+        B <= 0 || S_max <= 0 || ld < S_max || (ld % 64) != 0)
+        return SB_ERR_BAD_ARG;
+    if (B > 65535 || S_max > 65535 * 64) return SB_ERR_UNSUPPORTED;
+    ProfScope prof(PROF_ROWOP, static_cast<double>(B) * S_max * ld * 2.0, stream);
+    dist_bbox_kernel<<<dim3(DIST_PARTS, B), 256, 0, stream>>>(reinterpret_cast<const float2*>(coords_s), 0,
+                                                              static_cast<float4*>(bbox_scratch), seq_off);
+    count_launch();
+    dim3 grid(static_cast<unsigned>((ld + 255) / 256), static_cast<unsigned>((S_max + 63) / 64), B);
+    dist16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float2*>(coords_s), static_cast<const float4*>(bbox_scratch),
+                                            scale, dist16, 0, ld, 0, 0, seq_off);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
@@ -518,7 +559,8 @@ size_t mil_dist16_scratch_bytes(int B) { return static_cast<size_t>(B) * DIST_PA
 namespace {
 
 int make_maps(const void* q, const void* v, long long row_stride, long long batch_stride, long long v_rs, long long v_bs,
-              const uint16_t* dist16, int B, int S, CUtensorMap* tm_q, CUtensorMap* tm_k, CUtensorMap* tm_v, CUtensorMap* tm_d) {
+              const uint16_t* dist16, int B, int S, CUtensorMap* tm_q, CUtensorMap* tm_k, CUtensorMap* tm_v, CUtensorMap* tm_d,
+              long long ragged_dist_ld = 0) {
     int rc = make_tmap_3d_f16(tm_q, q, static_cast<int>(row_stride), S, B, row_stride, batch_stride, 64, 128);
     if (rc != SB_OK) return rc;
     rc = make_tmap_3d_f16(tm_k, q, static_cast<int>(row_stride), S, B, row_stride, batch_stride, 64, 64);
@@ -529,7 +571,11 @@ int make_maps(const void* q, const void* v, long long row_stride, long long batc
     if (dist16 != nullptr) {
         const long long ld = (static_cast<long long>(S) + 63) / 64 * 64;
         // inner extent S (not ld): key columns past the bag are zero-filled by the TMA unit
-        rc = make_tmap_3d_f16(tm_d, dist16, S, S, B, ld, static_cast<long long>(S) * ld, 64, 128);
+        if (ragged_dist_ld > 0)   // ragged: one tall matrix [total rows, ld], zeros stored past each bag's length
+            rc = make_tmap_3d_f16(tm_d, dist16, static_cast<int>(ragged_dist_ld), S, 1, ragged_dist_ld,
+                                  static_cast<long long>(S) * ragged_dist_ld, 64, 128);
+        else
+            rc = make_tmap_3d_f16(tm_d, dist16, S, S, B, ld, static_cast<long long>(S) * ld, 64, 128);
     }
     return rc;
 }
@@ -539,7 +585,10 @@ int make_maps(const void* q, const void* v, long long row_stride, long long batc
 // SB_ERR_UNSUPPORTED: outside this kernel's envelope (masked calls, head_dim != 64, short sequences, ALiBi without
 // a distance matrix) -> the caller uses the previous kernels
 int attention_mil_v3_fwd(const AttnParams& p, int head_dim, cudaStream_t stream) {
-    if (!g_v3_enabled || head_dim != 64 || p.mask != nullptr || p.S <= 256) return SB_ERR_UNSUPPORTED;
+    const bool ragged = p.seq_off != nullptr;
+    if (!g_v3_enabled || head_dim != 64 || p.mask != nullptr || (!ragged && p.S <= 256)) return SB_ERR_UNSUPPORTED;
+    if (ragged && (p.S_max <= 0 || p.S_max > p.S || (p.coords != nullptr && (p.dist_ld < p.S_max || (p.dist_ld % 64) != 0))))
+        return SB_ERR_BAD_ARG;
     const bool alibi = p.coords != nullptr;
     if (alibi && (p.dist16 == nullptr || p.dscale == nullptr || p.slope == nullptr)) return SB_ERR_UNSUPPORTED;
     const long long koff = p.k - p.q;
@@ -548,13 +597,16 @@ int attention_mil_v3_fwd(const AttnParams& p, int head_dim, cudaStream_t stream)
     if (koff < 0 || koff + static_cast<long long>(p.H) * 64 > p.row_stride || (koff % 8) != 0 ||
         (reinterpret_cast<uintptr_t>(p.q) & 15) != 0 || (reinterpret_cast<uintptr_t>(p.v) & 15) != 0 ||
         (reinterpret_cast<uintptr_t>(p.out) & 15) != 0 || (p.out_row_stride % 8) != 0 ||
-        static_cast<long long>(p.H) * 64 > v_rs || (p.S + 127) / 128 > 65535 ||
+        static_cast<long long>(p.H) * 64 > v_rs || ((ragged ? p.S_max : p.S) + 127) / 128 > 65535 ||
         (reinterpret_cast<uintptr_t>(p.dist16) & 15) != 0)
         return SB_ERR_UNSUPPORTED;
     if (alibi != (p.out_f32 != 0)) return SB_ERR_UNSUPPORTED;
     CUtensorMap tm_q, tm_k, tm_v, tm_d;
-    const int rc = make_maps(p.q, p.v, p.row_stride, p.batch_stride, v_rs, v_bs, alibi ? p.dist16 : nullptr, p.B, p.S,
-                             &tm_q, &tm_k, &tm_v, &tm_d);
+    // ragged: ONE "bag" of p.S rows in the maps, the kernel adds each bag's first row to the coordinates
+    const int rc = ragged ? make_maps(p.q, p.v, p.row_stride, p.row_stride * p.S, v_rs, v_rs * p.S, alibi ? p.dist16 : nullptr,
+                                      1, p.S, &tm_q, &tm_k, &tm_v, &tm_d, p.dist_ld)
+                          : make_maps(p.q, p.v, p.row_stride, p.batch_stride, v_rs, v_bs, alibi ? p.dist16 : nullptr, p.B, p.S,
+                                      &tm_q, &tm_k, &tm_v, &tm_d);
     if (rc != SB_OK) return rc;
     const V3Out none{};
     return alibi ? launch_v3<true, false>(tm_q, tm_k, tm_v, tm_d, p, static_cast<int>(koff), none, stream)

@@ -98,7 +98,7 @@ int stamp_attention_fwd(const void* q, const void* k, const void* v, long long r
                         const float* dscale, const uint8_t* mask, int mask_mode, void* stream) {
     if (q == nullptr || k == nullptr || v == nullptr || out == nullptr) return STAMP_ERR_BAD_ARG;
     if (mask != nullptr && mask_mode != 1 && mask_mode != 2) return STAMP_ERR_BAD_ARG;
-    sb::AttnParams p;
+    sb::AttnParams p{};
     p.q = static_cast<const __half*>(q);
     p.k = static_cast<const __half*>(k);
     p.v = static_cast<const __half*>(v);

@@ -72,11 +72,12 @@ mil_prepare_kernel(const float* __restrict__ coords, const uint8_t* __restrict__
 __global__ void __launch_bounds__(256)
 cls_head_kernel(const float* __restrict__ x, long long row_stride, int d, int d_real, const float* __restrict__ nw,
                 const float* __restrict__ nb, const float* __restrict__ hw, const float* __restrict__ hb,
-                int C, float eps, float* __restrict__ logits) {
+                int C, float eps, float* __restrict__ logits, const int* __restrict__ row_index = nullptr) {
     extern __shared__ float sh[];  // d normalised values + 32 scratch
     float* y = sh;
     float* red = sh + d;
-    const float* xr = x + blockIdx.x * row_stride;
+    // ragged batches: the class token of bag b sits in row row_index[b] (row pitch row_stride)
+    const float* xr = x + (row_index != nullptr ? static_cast<long long>(row_index[blockIdx.x]) : blockIdx.x) * row_stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw_ = blockDim.x >> 5;
     float s = 0.f;
     for (int i = tid; i < d; i += blockDim.x) s += xr[i];
@@ -103,6 +104,13 @@ cls_head_kernel(const float* __restrict__ x, long long row_stride, int d, int d_
         a = warp_sum(a);
         if (lane == 0) logits[static_cast<long long>(blockIdx.x) * C + c] = a + hb[c];
     }
+}
+
+// ragged batches: x[seq_off[b], :] = class_token for every bag b
+__global__ void __launch_bounds__(256)
+fill_cls_rows_kernel(float* __restrict__ x, int d, const int* __restrict__ seq_off, const float* __restrict__ cls) {
+    float* row = x + static_cast<long long>(seq_off[blockIdx.x]) * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) row[i] = __ldg(cls + i);
 }
 
 inline int grid_for(long long total, int block) {
@@ -331,6 +339,141 @@ int stamp_mil_forward(const StampMilConfig* cfg, const StampMilWeights* w, const
     cls_head_kernel<<<B, 256, (d + 32) * sizeof(float), stream>>>(
         x, static_cast<long long>(S) * d, d, d_real, w->norm_w, w->norm_b, w->head_w, w->head_b,
         cfg->dim_output, 1e-5f, logits);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
+}
+
+size_t stamp_mil_ragged_workspace_bytes(const StampMilConfig* cfg, int B, int total_rows, int S_max) {
+    sb::Layout L;
+    if (B <= 0 || total_rows < B || S_max <= 0 || S_max > total_rows || !sb::make_layout(cfg, 1, total_rows - 1, &L)) return 0;
+    if (cfg->dim_model / cfg->n_heads != 64) return 0;
+    size_t o = L.off_dist;   // everything up to the distance matrix is sized by the row count alone
+    const size_t ld = (static_cast<size_t>(S_max) + 63) / 64 * 64;
+    o = sb::align_up(o + static_cast<size_t>(B) * 8, 256);                       // per-bag distance scales
+    const size_t dist = o;
+    if (cfg->use_alibi) o = sb::align_up(o + static_cast<size_t>(total_rows) * ld * 2, 1024);
+    o = sb::align_up(o + sb::mil_dist16_scratch_bytes(B), 256);
+    (void)dist;
+    return o;
+}
+
+int stamp_mil_forward_ragged(const StampMilConfig* cfg, const StampMilWeights* w, const StampMilLayer* layers,
+                             const void* tokens_f16, const float* coords_s_in, const int* seq_off, int B, int total_rows,
+                             int S_max, float* logits, void* workspace, size_t workspace_bytes, void* stream_) {
+    using namespace sb;
+    Layout L;
+    if (B <= 0 || total_rows < B || S_max <= 0 || S_max > total_rows || !make_layout(cfg, 1, total_rows - 1, &L) ||
+        w == nullptr || (cfg->n_layers > 0 && layers == nullptr) || tokens_f16 == nullptr || seq_off == nullptr ||
+        logits == nullptr || workspace == nullptr || (cfg->use_alibi && coords_s_in == nullptr))
+        return SB_ERR_BAD_ARG;
+    const int d = cfg->dim_model, F = cfg->dim_input, H = cfg->n_heads, hd = d / H;
+    if (hd != 64) return SB_ERR_UNSUPPORTED;                 // the long-bag tcgen05 kernel is the only ragged attention
+    if (workspace_bytes < stamp_mil_ragged_workspace_bytes(cfg, B, total_rows, S_max)) return SB_ERR_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0 || (reinterpret_cast<uintptr_t>(tokens_f16) & 15) != 0)
+        return SB_ERR_BAD_ARG;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    float* x = reinterpret_cast<float*>(ws + L.off_x);
+    __half* xn = reinterpret_cast<__half*>(ws + L.off_xn);
+    __half* qkv = reinterpret_cast<__half*>(ws + L.off_qkv);
+    void* att = ws + L.off_att;
+    __half* h = reinterpret_cast<__half*>(ws + L.off_h);
+    const long long ld = (static_cast<long long>(S_max) + 63) / 64 * 64;
+    size_t o = L.off_dist;
+    float* dscale = reinterpret_cast<float*>(ws + o);
+    o = align_up(o + static_cast<size_t>(B) * 8, 256);
+    uint16_t* dist16 = reinterpret_cast<uint16_t*>(ws + o);
+    if (cfg->use_alibi) o = align_up(o + static_cast<size_t>(total_rows) * ld * 2, 1024);
+    void* bbox = ws + o;
+    const int M = total_rows;
+    const bool alibi = cfg->use_alibi != 0;
+    int rc;
+
+    // project_features over every row (the class rows hold don't-care inputs), then the class token into row 0 of
+    // every bag
+    {
+        GemmParams p{};
+        p.M = M; p.N = d; p.K = F;
+        p.act = ACT_GELU; p.store = ST_32; p.out = x; p.ldo = d; p.bias = w->proj_b;
+        rc = gemm_tn(tokens_f16, F, w->proj_w, F, p, stream);
+        if (rc != SB_OK) return rc;
+    }
+    fill_cls_rows_kernel<<<B, 256, 0, stream>>>(x, d, seq_off, w->class_token);
+    count_launch();
+    if (alibi) {
+        rc = mil_dist16_ragged(coords_s_in, seq_off, B, S_max, ld, dscale, dist16, bbox, stream);
+        if (rc != SB_OK) return rc;
+    }
+    const int d_real = (cfg->dim_model_real > 0 && cfg->dim_model_real <= d) ? cfg->dim_model_real : d;
+    const int hd_real = (cfg->head_dim_real > 0 && cfg->head_dim_real <= hd) ? cfg->head_dim_real : hd;
+    const float scale_log2 = (1.0f / sqrtf(static_cast<float>(hd_real))) * 1.4426950408889634f;
+
+    for (int l = 0; l < cfg->n_layers; ++l) {
+        const StampMilLayer& y = layers[l];
+        AttnParams a{};
+        a.out = att; a.B = B; a.S = M; a.S_max = S_max; a.seq_off = seq_off; a.H = H; a.scale_log2 = scale_log2;
+        if (alibi) {   // same sequence as stamp_mil_forward (split-precision V projection and fc), rows = all bags
+            rc = layernorm_padded(x, d, y.ln1_w, y.ln1_b, xn, xn + d, 2LL * d, M, d, d_real, 1e-5f, 0, stream);
+            if (rc != SB_OK) return rc;
+            __half* qk = qkv;
+            __half* v16 = qkv + static_cast<size_t>(M) * 2 * d;
+            GemmParams p{};
+            p.M = M; p.K = d;
+            p.N = 2 * d; p.store = ST_16; p.out = qk; p.ldo = 2 * d; p.bias = y.qkv_b;
+            rc = gemm_tn(xn, 2LL * d, y.qkv_w, d, p, stream);
+            if (rc != SB_OK) return rc;
+            p.N = d; p.K = 3 * d; p.a_kwrap = 2 * d; p.out = v16; p.ldo = d; p.bias = y.qkv_b + 2 * d;
+            rc = gemm_tn(xn, 2LL * d, y.v_w3, 3LL * d, p, stream);
+            if (rc != SB_OK) return rc;
+            a.q = qk; a.k = qk + d; a.row_stride = 2LL * d; a.batch_stride = 0;
+            a.v = v16; a.v_row_stride = d; a.v_batch_stride = 0;
+            a.out_f32 = 1; a.out_lo = reinterpret_cast<float*>(att) + d;
+            a.out_row_stride = 2LL * d; a.out_batch_stride = 0;
+            a.coords = coords_s_in; a.slope = y.slope; a.dscale = dscale; a.dist16 = dist16; a.dist_ld = ld;
+            rc = attention_mil_v3_fwd(a, hd, stream);
+            if (rc != SB_OK) return rc;
+            GemmParams f{};
+            f.M = M; f.N = d; f.K = 3 * d; f.a_kwrap = 2 * d; f.tf32 = 1; f.store = ST_RESID32; f.out = x; f.ldo = d;
+            f.bias = y.fc_b;
+            rc = gemm_tn(att, 2LL * d, y.fc_w, 3LL * d, f, stream);
+            if (rc != SB_OK) return rc;
+        } else {
+            rc = layernorm_padded(x, d, y.ln1_w, y.ln1_b, xn, nullptr, d, M, d, d_real, 1e-5f, 0, stream);
+            if (rc != SB_OK) return rc;
+            GemmParams p{};
+            p.M = M; p.N = 3 * d; p.K = d;
+            p.store = ST_16; p.out = qkv; p.ldo = 3 * d; p.bias = y.qkv_b;
+            rc = gemm_tn(xn, d, y.qkv_w, d, p, stream);
+            if (rc != SB_OK) return rc;
+            a.q = qkv; a.k = qkv + d; a.v = qkv + 2 * d;
+            a.row_stride = 3LL * d; a.batch_stride = 0;
+            a.out_f32 = 0; a.out_row_stride = d; a.out_batch_stride = 0;
+            rc = attention_mil_v3_fwd(a, hd, stream);
+            if (rc != SB_OK) return rc;
+            GemmParams f{};
+            f.M = M; f.N = d; f.K = d; f.store = ST_RESID32; f.out = x; f.ldo = d; f.bias = y.fc_b;
+            rc = gemm_tn(att, d, y.fc_w, d, f, stream);
+            if (rc != SB_OK) return rc;
+        }
+        rc = layernorm_padded(x, d, y.ln2_w, y.ln2_b, xn, nullptr, d, M, d, d_real, 1e-5f, 0, stream);
+        if (rc != SB_OK) return rc;
+        {
+            GemmParams p{};
+            p.M = M; p.N = cfg->dim_ff; p.K = d;
+            p.act = ACT_GELU; p.store = ST_16; p.out = h; p.ldo = cfg->dim_ff; p.bias = y.ff1_b;
+            rc = gemm_tn(xn, d, y.ff1_w, d, p, stream);
+            if (rc != SB_OK) return rc;
+        }
+        {
+            GemmParams p{};
+            p.M = M; p.N = d; p.K = cfg->dim_ff;
+            p.store = ST_RESID32; p.out = x; p.ldo = d; p.bias = y.ff2_b;
+            rc = gemm_tn(h, cfg->dim_ff, y.ff2_w, cfg->dim_ff, p, stream);
+            if (rc != SB_OK) return rc;
+        }
+    }
+    cls_head_kernel<<<B, 256, (d + 32) * sizeof(float), stream>>>(x, d, d, d_real, w->norm_w, w->norm_b, w->head_w,
+                                                                 w->head_b, cfg->dim_output, 1e-5f, logits, seq_off);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }

@@ -53,6 +53,12 @@ def _bind() -> C.CDLL:
         lib.stamp_mil_forward.argtypes = [C.POINTER(StampMilConfig), C.POINTER(StampMilWeights),
                                           C.POINTER(StampMilLayer), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.stamp_mil_ragged_workspace_bytes.restype = C.c_size_t
+        lib.stamp_mil_ragged_workspace_bytes.argtypes = [C.POINTER(StampMilConfig), C.c_int, C.c_int, C.c_int]
+        lib.stamp_mil_forward_ragged.restype = C.c_int
+        lib.stamp_mil_forward_ragged.argtypes = [C.POINTER(StampMilConfig), C.POINTER(StampMilWeights),
+                                                 C.POINTER(StampMilLayer), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                 C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         lib._mil_bound = True
     return lib
 
@@ -308,6 +314,70 @@ class VisionTransformer(nn.Module):
                                       f16(mat(ffn[1].weight, ffp, dc)), f32(vec(ffn[1].bias, ffp)),
                                       f16(mat(ffn[4].weight, dc, ffp)), f32(vec(ffn[4].bias, dc)))
         return (key, keep, cfg, w, layers)
+
+    def supports_ragged(self) -> bool:
+        """True when bags of different lengths can go through ONE forward (``forward_ragged``): the unmasked inference
+        path with head dimension 64 (native or zero-padded), which is the reference's default configuration."""
+        return self._shape_plan()["hp"] == 64
+
+    def pack_ragged(self, bags: list[tuple[Tensor, Tensor]], pin: bool = True) -> tuple[Tensor, Tensor, Tensor, int]:
+        """[(feats [N_b, F], coords [N_b, 2])] on the host -> the operands of ``forward_ragged``: fp16 tokens
+        [total, F'] with a placeholder row in front of every bag (the class-token row), fp32 coordinates [total, 2]
+        with (0, 0) there, int32 row offsets [B + 1], and the longest bag in tokens.  ``F'`` is the kernels' input
+        width (zero-padded when the model's is not a multiple of 8)."""
+        _, _, cfg, _, _ = self._pack()
+        sizes = [int(f.shape[0]) + 1 for f, _ in bags]
+        off = [0]
+        for n in sizes:
+            off.append(off[-1] + n)
+        total, Fin = off[-1], self._cfg["dim_input"]
+        tokens = torch.empty((total, cfg.dim_input), dtype=torch.float16, pin_memory=pin)
+        coords = torch.empty((total, 2), dtype=torch.float32, pin_memory=pin)
+        if cfg.dim_input != Fin:
+            tokens[:, Fin:] = 0
+        for (f, c), o, n in zip(bags, off, sizes):
+            if f.dim() != 2 or f.shape[1] != Fin or tuple(c.shape) != (n - 1, 2):
+                raise TypeError(f"expected feats [N,{Fin}] and coords [N,2], got {tuple(f.shape)} / {tuple(c.shape)}")
+            tokens[o] = 0                      # placeholder row of the class token (any finite values)
+            coords[o] = 0
+            tokens[o + 1:o + n, :Fin] = f
+            coords[o + 1:o + n] = c
+        return tokens, coords, torch.tensor(off, dtype=torch.int32), max(sizes)
+
+    @torch.no_grad()
+    def forward_ragged(self, tokens: Tensor, coords: Tensor, seq_off: Tensor, s_max: int) -> Tensor:
+        """ONE inference forward over a ragged batch of bags (``pack_ragged`` layout, on the model's device): the dense
+        layers run over the rows of all bags at once, the attention kernel walks each bag separately ->
+        logits fp32 [B, dim_output], row b identical to ``forward(bag_b[None], coords=..., mask=None)``.
+        What ``_predict`` (src/stamp/modeling/deploy.py:390-456) does patient by patient."""
+        if not tokens.is_cuda or not self.class_token.is_cuda:
+            raise RuntimeError("stamp_b200 VisionTransformer runs on a CUDA device only (no CPU fallback)")
+        if not self.supports_ragged():
+            raise ValueError("ragged batches need head dimension 64 (use forward per bag)")
+        lib = _bind()
+        _, _, cfg, w, layers = self._pack()
+        if tokens.dtype != torch.float16 or tokens.dim() != 2 or tokens.shape[1] != cfg.dim_input or not tokens.is_contiguous():
+            raise TypeError(f"tokens must be a contiguous fp16 [rows, {cfg.dim_input}] tensor (see pack_ragged)")
+        total, B = tokens.shape[0], seq_off.numel() - 1
+        if coords.dtype != torch.float32 or tuple(coords.shape) != (total, 2) or not coords.is_contiguous() or \
+                seq_off.dtype != torch.int32 or not seq_off.is_cuda or B < 1:
+            raise TypeError("coords must be fp32 [rows, 2], seq_off an int32 CUDA tensor [B + 1]")
+        dev = tokens.device
+        logits = torch.empty((B, self._cfg["dim_output"]), dtype=torch.float32, device=dev)
+        need = lib.stamp_mil_ragged_workspace_bytes(C.byref(cfg), B, total, int(s_max))
+        if need == 0:
+            raise ValueError("unsupported MIL configuration / batch for the ragged forward")
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if self._workspace is None or len(self._workspace) > 8:
+            self._workspace = {}
+        ws = self._workspace.get(stream)
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = self._workspace[stream] = torch.empty(need, dtype=torch.uint8, device=dev)
+        code = lib.stamp_mil_forward_ragged(C.byref(cfg), C.byref(w), layers, tokens.data_ptr(), coords.data_ptr(),
+                                            seq_off.data_ptr(), B, total, int(s_max), logits.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), stream)
+        _lib.check(code, "stamp_mil_forward_ragged")
+        return logits
 
     def forward(self, bags: Tensor, *, coords: Tensor, mask: Tensor | None) -> Tensor:
         if bags.dim() != 3 or coords.dim() != 3 or coords.shape[:2] != bags.shape[:2] or coords.shape[2] != 2:

@@ -281,7 +281,52 @@ def test_predict_bags_pipeline_matches_per_bag_forward(cuda_device):
         ref = torch.softmax(mil_oracle.forward(sd, f, c, None), dim=1)[0]
         assert torch.allclose(probs[i], ref, atol=2e-4), (i, probs[i], ref)
     named = predict_patients(model, [f"p{i}" for i in range(len(sizes))], iter(host), cuda_device)
-    assert list(named) == [f"p{i}" for i in range(len(sizes))] and torch.equal(named["p3"], probs[3])
+    # (predict_patients batches the bags raggedly: short bags meet another attention kernel than in predict_bags)
+    assert list(named) == [f"p{i}" for i in range(len(sizes))]
+    for i, (f, c) in enumerate(bags):
+        ref = torch.softmax(mil_oracle.forward(sd, f, c, None), dim=1)[0]
+        assert torch.allclose(named[f"p{i}"], ref, atol=2e-4) and torch.allclose(named[f"p{i}"], probs[i], atol=2e-4)
     assert predict_bags(model, iter([]), cuda_device).shape == (0, 3)
     with pytest.raises(RuntimeError):
         predict_bags(model, iter(host), "cpu")
+
+
+@pytest.mark.parametrize("use_alibi", [True, False])
+def test_ragged_batch_equals_per_bag_forwards(cuda_device, use_alibi):
+    """Bags of different lengths through ONE forward (stamp_mil_forward_ragged): the dense layers run over the rows of
+    all bags, the long-bag attention kernel over each bag; rows and bags are independent, so every bag's logits equal
+    its own batch-1 forward bit for bit (lengths on both sides of the tile sizes, 1-tile bags, > 256 and <= 256)."""
+    from stamp_b200.deploy import predict_bags, predict_bags_ragged
+    from stamp_b200.mil import VisionTransformer
+
+    torch.manual_seed(7)
+    model = VisionTransformer(dim_output=3, dim_input=96, dim_model=128, n_layers=2, n_heads=2, dim_feedforward=256,
+                              dropout=0.0, use_alibi=use_alibi).to(cuda_device).eval()
+    if use_alibi:
+        for layer in model.transformer.layers:
+            for a in layer[0].mhsa.attentions:
+                a.scale_distance.running_mean.fill_(3000.0)
+    assert model.supports_ragged()
+    g = torch.Generator().manual_seed(1)
+    lengths = [700, 1, 63, 64, 65, 127, 128, 129, 1000, 300, 255, 256, 257, 2, 513]
+    bags = [(torch.randn(n, 96, generator=g).half(), torch.rand(n, 2, generator=g) * 20000) for n in lengths]
+    tokens, coords, seq, s_max = model.pack_ragged(bags, pin=False)
+    assert s_max == 1001 and seq.tolist()[-1] == sum(lengths) + len(lengths)
+    with torch.inference_mode():
+        ragged = model.forward_ragged(tokens.to(cuda_device), coords.to(cuda_device), seq.to(cuda_device), s_max)
+        single = torch.cat([model(f.to(cuda_device)[None], coords=c.to(cuda_device)[None], mask=None) for f, c in bags])
+    assert ragged.shape == (len(lengths), 3) and torch.isfinite(ragged).all()
+    # (bags of <= 256 tokens take another attention kernel in the batch-1 path: same math, different tile order)
+    long = torch.tensor([n + 1 > 256 for n in lengths], device=cuda_device)
+    assert torch.equal(ragged[long], single[long])
+    err = ((ragged - single).norm(dim=1) / single.norm(dim=1)).max().item()
+    assert err < 1e-3, err
+    # the deploy loops: ragged batches (several groups: max_rows 1500) == per-bag streams, host and device bags
+    p_ref = predict_bags(model, iter(bags), cuda_device, graphs=False)
+    p_rag = predict_bags_ragged(model, iter(bags), cuda_device, max_rows=1500)
+    # (probabilities: identical for the long bags, within the kernels' tolerance for the short ones, see above)
+    longh = long.cpu()
+    assert p_rag.shape == p_ref.shape and torch.equal(p_rag[longh], p_ref[longh]) and torch.allclose(p_rag, p_ref, atol=5e-4)
+    dev_bags = [(f.to(cuda_device), c.to(cuda_device)) for f, c in bags]
+    p_dev = predict_bags_ragged(model, iter(dev_bags), cuda_device, max_rows=4000, max_bags=4)
+    assert torch.equal(p_dev[longh], p_ref[longh]) and torch.allclose(p_dev, p_ref, atol=5e-4)
