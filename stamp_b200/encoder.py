@@ -288,6 +288,112 @@ class EagleB200(_EagleBase):
                                               agg_feats=torch.cat(agg_feats_list, dim=0))
 
 
+def align_by_coords(ref_coords_um, other_coords_um, other_feats: Tensor, decimals: int = 5) -> tuple[Tensor, np.ndarray]:
+    """eagle.py:303-330: permute ``other_feats`` so that its tiles come in the order of ``ref_coords_um`` (coordinates
+    matched after rounding to ``decimals``; duplicates are consumed first come, first served); raises ``ValueError``
+    when a coordinate is missing on either side."""
+    from collections import defaultdict, deque
+
+    ref = np.round(np.asarray(ref_coords_um, dtype=np.float64), decimals)
+    oth = np.round(np.asarray(other_coords_um, dtype=np.float64), decimals)
+    buckets: dict = defaultdict(deque)
+    for j, key in enumerate(map(tuple, oth)):
+        buckets[key].append(j)
+    perm = np.empty(ref.shape[0], dtype=np.int64)
+    for i, key in enumerate(map(tuple, ref)):
+        if not buckets[key]:
+            raise ValueError(f"Missing coord in other set: {key}")
+        perm[i] = buckets[key].popleft()
+    unused = sum(len(q) for q in buckets.values())
+    if unused != 0:
+        raise ValueError(f"virchow2 features contain {unused} extra coords not in ref.")
+    return other_feats[torch.from_numpy(perm)], np.asarray(other_coords_um)[perm]
+
+
+if not BOUND_TO_REFERENCE:
+    # Stand-alone EAGLE: the feature-file pairing of the reference's ``Eagle`` (eagle.py:40-89, 136-300) -- every slide
+    # has a ctranspath file in ``feat_dir`` and a Virchow2 file of the same name in ``agg_feat_dir``; the two are
+    # checked against the required extractors and brought into the same tile order by their coordinates.
+    def _eagle_read_pair(self, h5_ctp: str, h5_vir2: str, slide_name: str) -> tuple[Tensor, Tensor]:
+        from . import features
+
+        feats, coords, extractor = features.read_tile_features(h5_ctp)
+        if extractor not in self.required_extractors:
+            raise ValueError(f"Features must be extracted with one of {self.required_extractors}. "
+                             f"Features located in {h5_ctp} are extracted with {extractor}")
+        agg, agg_coords, extractor = features.read_tile_features(h5_vir2)
+        if extractor != self.required_agg_extractor:
+            raise ValueError(f"Aggregated features must be extracted with {self.required_agg_extractor} "
+                             f"Features located in {h5_vir2} are extracted with {extractor}")
+        feats_t, agg_t = torch.from_numpy(feats), torch.from_numpy(agg)
+        same = coords.coords_um.shape == agg_coords.coords_um.shape and \
+            np.allclose(coords.coords_um, agg_coords.coords_um, atol=1e-5, rtol=0)
+        if not same:
+            try:
+                agg_t, _ = align_by_coords(coords.coords_um, agg_coords.coords_um, agg_t)
+            except ValueError as e:
+                raise ValueError(f"Coordinates mismatch between ctranspath and virchow2 features for slide "
+                                 f"{slide_name}. Alignment attempt failed: {e}") from e
+        return feats_t, agg_t
+
+    def _eagle_encode_slides(self, output_dir, feat_dir, device, generate_hash: bool = False, **kwargs) -> None:
+        import logging
+        import os
+        from pathlib import Path
+
+        agg_feat_dir = kwargs.get("agg_feat_dir")
+        if not agg_feat_dir:
+            raise ValueError("agg_feat_dir that contains virchow2 features is required for Eagle's encode_slides")
+        encode_dir = self._encode_dir(output_dir, "slide", generate_hash)
+        self.model.to(device).eval()
+        for name in sorted(os.listdir(feat_dir)):
+            if not name.endswith(".h5"):
+                continue
+            output_path = (encode_dir / Path(name).name).with_suffix(".h5")
+            if output_path.exists():
+                continue
+            try:
+                feats, agg = _eagle_read_pair(self, os.path.join(feat_dir, name), os.path.join(agg_feat_dir, name), name)
+            except ValueError as e:
+                logging.getLogger("stamp").warning(str(e))
+                continue
+            self._save_features_(output_path, self._generate_slide_embedding(feats, device, agg), "slide")
+
+    def _eagle_encode_patients(self, output_dir, feat_dir, slide_table_path, patient_label: str, filename_label: str,
+                               device, generate_hash: bool = False, **kwargs) -> None:
+        import logging
+        import os
+        from pathlib import Path
+
+        import pandas as pd
+
+        agg_feat_dir = kwargs.get("agg_feat_dir")
+        if not agg_feat_dir:
+            raise ValueError("agg_feat_dir that contains virchow2 features is required for Eagle's encode_patients")
+        encode_dir = self._encode_dir(output_dir, "pat", generate_hash)
+        self.model.to(device).eval()
+        for patient_id, group in pd.read_csv(slide_table_path).groupby(patient_label):
+            output_path = (encode_dir / str(patient_id)).with_suffix(".h5")
+            if output_path.exists():
+                continue
+            feats_list, agg_list = [], []
+            for _, row in group.iterrows():
+                fn = row[filename_label]
+                try:
+                    feats, agg = _eagle_read_pair(self, os.path.join(feat_dir, fn), os.path.join(agg_feat_dir, fn), Path(fn).stem)
+                except FileNotFoundError as e:
+                    logging.getLogger("stamp").warning(f"[{patient_id}] skip slide (FileNotFoundError): {fn} -> {e}")
+                    continue
+                feats_list.append(feats)
+                agg_list.append(agg)
+            if not feats_list:
+                continue
+            self._save_features_(output_path, self._generate_patient_embedding(feats_list, device, agg_list), "patient")
+
+    EagleB200.encode_slides_ = _eagle_encode_slides          # type: ignore[method-assign]
+    EagleB200.encode_patients_ = _eagle_encode_patients      # type: ignore[method-assign]
+
+
 # ---- TITAN (SURVEY.md 8a row a14): NOT built.  The slide transformer is un-vendored Hugging Face remote code with
 # gated weights; nothing here restates or accelerates it.  What remains are the two pieces of input preparation of the
 # reference's wrapper that are in-tree arithmetic, for callers that feed their own TITAN model. -----------------------

@@ -286,6 +286,37 @@ def test_brightness_rejection_matches_the_reference_function():
         assert 0 < len(foreground_coords(Slide.dimensions, tile, Slide.get_thumbnail(tuple(grid * 2)), 224)) < grid[0] * grid[1]
 
 
+def test_eagle_coordinate_alignment_matches_the_reference_function():
+    """encoder.align_by_coords against the reference's _align_vir2_to_ctp_by_coords (eagle.py:303-330) executed from source:
+    same permutation of the Virchow2 features for shuffled tiles (incl. duplicate coordinates), same errors."""
+    import numpy as np
+
+    ref_file = Path("/root/reference/src/stamp/encoding/encoder/eagle.py")
+    if not ref_file.exists():
+        pytest.skip("reference checkout not present on this machine")
+    from collections import defaultdict, deque
+
+    from stamp_b200.encoder import align_by_coords
+
+    ref = _reference_functions(ref_file, ["_align_vir2_to_ctp_by_coords"])
+    ref.update(np=np, defaultdict=defaultdict, deque=deque)
+    rng = np.random.default_rng(0)
+    coords = rng.integers(0, 40, (200, 2)).astype(np.float64) * 256.0 + 1e-7 * rng.standard_normal((200, 2))
+    coords[17] = coords[5]                                     # a duplicated coordinate
+    perm = rng.permutation(200)
+    other_feats = torch.randn(200, 8)
+    want_f, want_c = ref["_align_vir2_to_ctp_by_coords"](coords, coords[perm], other_feats, decimals=5)
+    got_f, got_c = align_by_coords(coords, coords[perm], other_feats, decimals=5)
+    assert torch.equal(got_f, want_f) and np.array_equal(got_c, want_c)
+    for bad_other in (coords[perm][:-1], np.vstack([coords[perm], coords[:1]])):
+        feats = torch.randn(len(bad_other), 8)
+        with pytest.raises(ValueError) as e_ref:
+            ref["_align_vir2_to_ctp_by_coords"](coords, bad_other, feats)
+        with pytest.raises(ValueError) as e_got:
+            align_by_coords(coords, bad_other, feats)
+        assert str(e_ref.value) == str(e_got.value)
+
+
 def test_titan_wrapper_input_preparation():
     """titan.py:47-53 (um -> int64 px) and :131-168 (virtual slide: slides side by side along x)."""
     import numpy as np

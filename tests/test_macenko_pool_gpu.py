@@ -164,3 +164,56 @@ def test_chief_and_eagle_match_reference_model_golden(cuda_device):
         assert np.allclose(pat, emb, rtol=1e-6, atol=1e-7), name
         with pytest.raises(ValueError):
             eagle._generate_patient_embedding([c["x"]], cuda_device)
+
+
+def test_standalone_eagle_feature_file_walk(cuda_device, tmp_path):
+    """eagle.py:136-300 through the stand-alone EagleB200: ctranspath and Virchow2 feature files paired by name, the
+    Virchow2 tiles stored in another order and re-aligned by coordinates, wrong extractors skipped; slide- and
+    patient-level embeddings equal the direct calls."""
+    import numpy as np
+
+    from stamp_b200 import encoder as E
+    from stamp_b200 import features, h5lite
+
+    if E.BOUND_TO_REFERENCE:
+        pytest.skip("the reference's own Eagle (h5py) is in use")
+    g = torch.Generator().manual_seed(5)
+    sd = {"attention_net.0.weight": torch.randn(512, 768, generator=g) * 0.04, "attention_net.0.bias": torch.zeros(512),
+          "attention_net.3.attention_a.0.weight": torch.randn(256, 512, generator=g) * 0.05,
+          "attention_net.3.attention_a.0.bias": torch.zeros(256),
+          "attention_net.3.attention_b.0.weight": torch.randn(256, 512, generator=g) * 0.05,
+          "attention_net.3.attention_b.0.bias": torch.zeros(256),
+          "attention_net.3.attention_c.weight": torch.randn(1, 256, generator=g) * 0.06,
+          "attention_net.3.attention_c.bias": torch.zeros(1)}
+    enc = E.EagleB200(sd)
+    ctp_dir, vir_dir = tmp_path / "ctranspath", tmp_path / "virchow2"
+    data = {}
+    for name, n in (("s1", 90), ("s2", 40), ("bad", 30)):
+        ctp = torch.randn(n, 768, generator=g).half()
+        vir = torch.randn(n, 2560, generator=g).half()
+        cells = torch.randperm(400, generator=g)[:n]
+        coords = torch.stack([(cells % 20).float(), (cells // 20).float()], -1).numpy() * 256.0
+        perm = torch.randperm(n, generator=g)                      # the Virchow2 file lists the tiles in another order
+        features.write_tile_features(ctp_dir / f"{name}.h5", ctp, coords, extractor="chief-ctranspath", tile_size_um=256.0,
+                                     tile_size_px=224)
+        features.write_tile_features(vir_dir / f"{name}.h5", vir[perm], coords[perm.numpy()],
+                                     extractor="uni" if name == "bad" else "virchow2-0a1b2c3d", tile_size_um=256.0, tile_size_px=224)
+        data[name] = (ctp, vir)
+    enc.encode_slides_(tmp_path / "out", ctp_dir, cuda_device, agg_feat_dir=vir_dir)
+    out = tmp_path / "out" / "eagle-slide"
+    assert sorted(p.name for p in out.iterdir()) == ["s1.h5", "s2.h5"]             # "bad": wrong aggregation extractor
+    for name in ("s1", "s2"):
+        ctp, vir = data[name]
+        want = enc._generate_slide_embedding(ctp, cuda_device, vir)
+        with h5lite.File(out / f"{name}.h5") as h5:
+            assert np.array_equal(h5["feats"][()], want) and h5.attrs["encoder"] == "eagle"
+    (tmp_path / "slides.csv").write_text("PATIENT,FILENAME\np1,s1.h5\np1,s2.h5\np2,missing.h5\n")
+    enc.encode_patients_(tmp_path / "out", ctp_dir, tmp_path / "slides.csv", "PATIENT", "FILENAME", cuda_device,
+                         agg_feat_dir=vir_dir)
+    pat = tmp_path / "out" / "eagle-pat"
+    assert [p.name for p in pat.iterdir()] == ["p1.h5"]
+    want = enc._generate_patient_embedding([data["s1"][0], data["s2"][0]], cuda_device, [data["s1"][1], data["s2"][1]])
+    with h5lite.File(pat / "p1.h5") as h5:
+        assert np.array_equal(h5["feats"][()], want) and h5.attrs["feat_type"] == "patient"
+    with pytest.raises(ValueError):
+        enc.encode_slides_(tmp_path / "out2", ctp_dir, cuda_device)
