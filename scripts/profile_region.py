@@ -16,7 +16,7 @@ torch.manual_seed(0)
 if what in ("vit_l16", "virchow2"):
     from stamp_b200.vit import UNI_ARCH, VIRCHOW2_ARCH, TileEncoder, random_state_dict
 
-    arch, B = (UNI_ARCH, 192) if what == "vit_l16" else (VIRCHOW2_ARCH, 96)
+    arch, B = (UNI_ARCH, 384) if what == "vit_l16" else (VIRCHOW2_ARCH, 96)   # the batches bench.py runs
     enc = TileEncoder(arch, random_state_dict(arch), max_batch=B).to(dev).eval()
     tiles = torch.randint(0, 255, (B, 224, 224, 3), dtype=torch.uint8, device=dev)
     unit = lambda: enc(tiles)

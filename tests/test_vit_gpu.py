@@ -118,6 +118,15 @@ def test_uni_vit_l16_at_benched_batch_192(cuda_device):
     assert err < 1e-3, err
 
 
+def test_uni_vit_l16_at_benched_batch_384(cuda_device):
+    """The batch bench.py runs by default (296 row tiles of 256: four per CTA pair)."""
+    from oracle import vit_oracle as vo
+
+    err = _run_in_full_batch(vo.UNI, 4, 384, cuda_device)
+    print("ViT-L/16 @ batch 384, max per-tile relative error:", err)
+    assert err < 1e-3, err
+
+
 def test_virchow2_vit_h14_at_benched_batch_96(cuda_device):
     from oracle import vit_oracle as vo
 
