@@ -140,6 +140,8 @@ typedef struct {
     int kpad;         /* patch vector length 3*patch^2 rounded up to a multiple of 8 */
     float ln_eps;
     float mean[3], std[3];
+    int pool;         /* 0: class token (feats [B, dim]); 1: class token | mean of all other tokens after the final norm
+                         (feats [B, 2*dim]; VirchowConcatenated, src/stamp/preprocessing/extractor/virchow_full.py:24-35) */
 } StampVitConfig;
 
 typedef struct {
@@ -168,7 +170,7 @@ size_t stamp_vit_workspace_bytes(const StampVitConfig* cfg, int B);
 
 int stamp_vit_forward(const StampVitConfig* cfg, const StampVitWeights* w,
                       const StampVitBlock* blocks /* [depth] */, const uint8_t* tiles /* [B,img,img,3] */,
-                      void* feats16 /* [B, dim] */, int B, void* workspace, size_t workspace_bytes,
+                      void* feats16 /* [B, dim] (pool 0) or [B, 2*dim] (pool 1) */, int B, void* workspace, size_t workspace_bytes,
                       void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -21,6 +21,20 @@
 
 namespace {
 
+// feats[b] = [ normalised class token | mean over the other T-1 normalised tokens ]  (fp32 tokens [B, T, D] -> fp16)
+// grid (D / 256 rounded up, B): a thread owns one channel and walks the tile's tokens (coalesced across the warp)
+__global__ void __launch_bounds__(256)
+cls_mean_pool_kernel(const float* __restrict__ tok, int T, int D, __half* __restrict__ feats) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= D) return;
+    const float* t = tok + static_cast<long long>(blockIdx.y) * T * D + c;
+    float acc = 0.f;
+    for (int r = 1; r < T; ++r) acc += t[static_cast<long long>(r) * D];
+    __half* o = feats + static_cast<long long>(blockIdx.y) * 2 * D;
+    o[c] = __float2half_rn(t[0]);
+    o[D + c] = __float2half_rn(acc / static_cast<float>(T - 1));
+}
+
 struct Layout {
     long long M, T, D, hid_out, big_cols;
     size_t off_x, off_xn, off_big, total;
@@ -31,7 +45,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 bool make_layout(const StampVitConfig* c, int B, Layout* L) {
     if (c == nullptr || B <= 0 || c->patch <= 0 || c->img % c->patch != 0 || c->heads <= 0 ||
         c->dim % c->heads != 0 || c->dim % 8 != 0 || c->mlp_hidden % 8 != 0 || c->kpad % 8 != 0 ||
-        c->kpad < 3 * c->patch * c->patch)
+        c->kpad < 3 * c->patch * c->patch || c->pool < 0 || c->pool > 1)
         return false;
     const long long np = static_cast<long long>(c->img / c->patch) * (c->img / c->patch);
     L->T = np + 1 + c->reg_tokens;
@@ -102,7 +116,7 @@ int stamp_vit_forward(const StampVitConfig* cfg, const StampVitWeights* w,
         // global_pool = 'token' (uni.py:26-31, virchow2.py:24-30 take x[:, 0]): the last block's outputs are only
         // read at the class-token rows, so after its K / V projections everything runs on those B rows alone
         // (row b*T of x and xn addressed with a row pitch of T*D; same arithmetic for the rows that are kept)
-        const bool cls_only = (l == cfg->depth - 1);
+        const bool cls_only = (l == cfg->depth - 1) && cfg->pool == 0;
         const int Mr = cls_only ? B : M;                                  // rows from the attention output on
         const long long ldr = cls_only ? static_cast<long long>(T) * D : D;  // their pitch in x / xn
         rc = layernorm(x, D, b.ln1_w, b.ln1_b, xn, nullptr, D, M, D, cfg->ln_eps, 0, stream);
@@ -152,6 +166,16 @@ int stamp_vit_forward(const StampVitConfig* cfg, const StampVitWeights* w,
             rc = gemm_tn(big, L.hid_out, b.fc2_w, L.hid_out, p, stream);
             if (rc != SB_OK) return rc;
         }
+    }
+    if (cfg->pool == 1) {
+        // every token through the final norm (fp32, into the big scratch: M x D x 4 <= M x 3D x 2 bytes), then the
+        // class token and the mean of the rest side by side
+        float* tok = reinterpret_cast<float*>(big);
+        rc = layernorm(x, D, w->norm_w, w->norm_b, tok, nullptr, D, M, D, cfg->ln_eps, 2, stream);
+        if (rc != SB_OK) return rc;
+        cls_mean_pool_kernel<<<dim3((D + 255) / 256, B), 256, 0, stream>>>(tok, T, D, static_cast<__half*>(feats16));
+        count_launch();
+        return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
     }
     // final norm on the class-token rows only (global_pool='token'): row b*T of x
     return layernorm(x, static_cast<long long>(D) * T, w->norm_w, w->norm_b, feats16, nullptr, D, B, D,

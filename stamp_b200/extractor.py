@@ -6,7 +6,7 @@ accepts an instance directly (src/stamp/preprocessing/__init__.py:117,237-238), 
 the device, calls ``model(batch)`` under ``inference_mode`` and stores ``.half().cpu()``
 (:243,322-327).  ``identifier`` is what lands in the output folder name and the ``extractor`` h5
 attribute, so the factories below keep the reference's identifiers (the ``ExtractorName`` values
-"uni", "virchow2", "uni2", "h-optimus-0", "h-optimus-1", "gigapath"; src/stamp/preprocessing/config.py:13-33).
+"uni", "virchow", "virchow-full", "virchow2", "uni2", "h-optimus-0", "h-optimus-1", "gigapath"; src/stamp/preprocessing/config.py:13-33).
 When ``stamp`` is importable the factories return instances of the reference's own ``Extractor``.
 
 The transform returns the tile as a uint8 HWC tensor (legal: the reference's ``empty`` extractor
@@ -25,7 +25,8 @@ import numpy as np
 import torch
 from torch import Tensor, nn
 
-from .vit import (GIGAPATH_ARCH, H_OPTIMUS_ARCH, UNI2_ARCH, UNI_ARCH, VIRCHOW2_ARCH, TileEncoder, VitArch,
+from .vit import (GIGAPATH_ARCH, H_OPTIMUS_ARCH, UNI2_ARCH, UNI_ARCH, VIRCHOW2_ARCH, VIRCHOW_ARCH, VIRCHOW_FULL_ARCH,
+                  TileEncoder, VitArch,
                   random_state_dict)
 
 ExtractorModel = TypeVar("ExtractorModel", bound=nn.Module)
@@ -103,6 +104,25 @@ def virchow2(weights=None, max_batch: int = 96) -> Extractor[TileEncoder]:
     return _make(VIRCHOW2_ARCH, "virchow2", weights, "hf-hub:paige-ai/Virchow2", hub_kwargs, max_batch)
 
 
+def _virchow_hub_kwargs(weights) -> dict:
+    if weights is not None:
+        return {}
+    from timm.layers.mlp import SwiGLUPacked  # same constructor arguments as the reference
+
+    return dict(mlp_layer=SwiGLUPacked, act_layer=torch.nn.SiLU)
+
+
+def virchow(weights=None, max_batch: int = 96) -> Extractor[TileEncoder]:
+    """Virchow (v1) ViT-H/14, class token only, 1280 values (reference: .../extractor/virchow.py:24-57)."""
+    return _make(VIRCHOW_ARCH, "virchow", weights, "hf-hub:paige-ai/Virchow", _virchow_hub_kwargs(weights), max_batch)
+
+
+def virchow_full(weights=None, max_batch: int = 96) -> Extractor[TileEncoder]:
+    """Virchow (v1) with the class token and the mean patch token concatenated, 2560 values (reference:
+    .../extractor/virchow_full.py:24-62); the pooling runs on the GPU after the final norm over all tokens."""
+    return _make(VIRCHOW_FULL_ARCH, "virchow-full", weights, "hf-hub:paige-ai/Virchow", _virchow_hub_kwargs(weights), max_batch)
+
+
 def uni2(weights=None, max_batch: int = 96) -> Extractor[TileEncoder]:
     """UNI2-h ViT-H/14 with 8 register tokens (reference: .../extractor/uni2.py:16-46)."""
     hub_kwargs: dict = {}
@@ -144,10 +164,10 @@ def extract_slide_features(extractor: Extractor, tiles_u8: Tensor, device: torch
     device = torch.device(device)
     model = extractor.model
     n = tiles_u8.shape[0]
-    feats_host = torch.empty((n, model.arch.dim), dtype=torch.float16).pin_memory()
+    feats_host = torch.empty((n, model.arch.out_dim), dtype=torch.float16).pin_memory()
     if tiles_u8.is_cuda:
         # tiles already in HBM (decoded there: tiling.tiles_from_cache_file_gpu): nothing to stream in
-        feats_dev = torch.empty((n, model.arch.dim), dtype=torch.float16, device=tiles_u8.device)
+        feats_dev = torch.empty((n, model.arch.out_dim), dtype=torch.float16, device=tiles_u8.device)
         for s in range(0, n, batch_size):
             feats_dev[s:s + batch_size] = model(tiles_u8[s:s + batch_size])
         feats_host.copy_(feats_dev, non_blocking=True)
@@ -173,7 +193,7 @@ def extract_slide_features(extractor: Extractor, tiles_u8: Tensor, device: torch
 
     if starts:
         issue_copy(0)
-    feats_dev = torch.empty((n, model.arch.dim), dtype=torch.float16, device=device)
+    feats_dev = torch.empty((n, model.arch.out_dim), dtype=torch.float16, device=device)
     for i, s in enumerate(starts):
         if i + 1 < len(starts):
             issue_copy(i + 1)
@@ -291,7 +311,7 @@ def extract_cache_features(extractor: Extractor, cache_file_path: str | Path, de
     coords_t = torch.tensor(coords, dtype=torch.float32).reshape(-1, 2)
     if not names:
         zf.close()
-        return torch.empty((0, model.arch.dim), dtype=torch.float16), coords_t, params
+        return torch.empty((0, model.arch.out_dim), dtype=torch.float16), coords_t, params
     info = jpeg.read_header(zf.read(names[0]))
     n_coef = jpeg.coef_count(info)
     starts = list(range(0, len(names), batch_size))
@@ -350,5 +370,5 @@ def extract_cache_features(extractor: Extractor, cache_file_path: str | Path, de
         host.copy_(feats, non_blocking=True)
         main.synchronize()
     else:
-        host = torch.empty((0, model.arch.dim), dtype=torch.float16)
+        host = torch.empty((0, model.arch.out_dim), dtype=torch.float16)
     return host, coords_t[idx], params

@@ -39,6 +39,7 @@ class VitArch:
     mean: tuple = IMAGENET_MEAN
     std: tuple = IMAGENET_STD
     no_embed_class: bool = False  # timm: pos_embed has n_patches rows, prefix tokens get no position
+    pool: str = "cls"    # "cls": class token; "cls_mean": class token | mean of the other tokens (virchow_full.py:24-35)
     pre_resize: int = 0  # > 0: transforms.Resize(pre_resize, BICUBIC) + CenterCrop(img) ahead of the model (GigaPath)
 
     @property
@@ -52,6 +53,10 @@ class VitArch:
     @property
     def n_tokens(self) -> int:
         return self.n_patches + self.n_prefix
+
+    @property
+    def out_dim(self) -> int:
+        return 2 * self.dim if self.pool == "cls_mean" else self.dim
 
     @property
     def kpad(self) -> int:
@@ -83,6 +88,11 @@ UNI2_ARCH = VitArch("uni2", patch=14, dim=1536, depth=24, heads=24, mlp_hidden=8
 H_OPTIMUS_ARCH = VitArch("h_optimus", patch=14, dim=1536, depth=40, heads=24, mlp_hidden=8192, mlp="swiglu",
                          reg_tokens=4, no_embed_class=True, mean=(0.707223, 0.578729, 0.703617),
                          std=(0.211883, 0.230117, 0.177517))
+# virchow.py:33-57 / virchow_full.py:38-62: Virchow (v1), ViT-H/14 without register tokens, SwiGLUPacked; the "full"
+# variant returns class token | mean patch token (2560 values)
+VIRCHOW_ARCH = VitArch("virchow", patch=14, dim=1280, depth=32, heads=16, mlp_hidden=6832, mlp="swiglu")
+VIRCHOW_FULL_ARCH = VitArch("virchow_full", patch=14, dim=1280, depth=32, heads=16, mlp_hidden=6832, mlp="swiglu",
+                            pool="cls_mean")
 # gigapath.py:14-35: timm vit_giant_patch14_dinov2 with patch 16 at 224 px (embed 1536, depth 40, 24 heads, SwiGLUPacked
 # 8192, class token inside the position table); the transform's Resize(256, BICUBIC) + CenterCrop(224) runs on the GPU
 GIGAPATH_ARCH = VitArch("gigapath", patch=16, dim=1536, depth=40, heads=24, mlp_hidden=8192, mlp="swiglu",
@@ -93,7 +103,7 @@ class StampVitConfig(C.Structure):
     _fields_ = [("img", C.c_int), ("patch", C.c_int), ("dim", C.c_int), ("depth", C.c_int),
                 ("heads", C.c_int), ("mlp_hidden", C.c_int), ("mlp_kind", C.c_int),
                 ("reg_tokens", C.c_int), ("kpad", C.c_int), ("ln_eps", C.c_float),
-                ("mean", C.c_float * 3), ("std", C.c_float * 3)]
+                ("mean", C.c_float * 3), ("std", C.c_float * 3), ("pool", C.c_int)]
 
 
 class StampVitWeights(C.Structure):
@@ -219,7 +229,7 @@ class TileEncoder(nn.Module):
         a = self.arch
         cfg = StampVitConfig(a.img, a.patch, a.dim, a.depth, a.heads, a.mlp_hidden,
                              1 if a.mlp == "swiglu" else 0, a.reg_tokens, a.kpad, a.ln_eps,
-                             (C.c_float * 3)(*a.mean), (C.c_float * 3)(*a.std))
+                             (C.c_float * 3)(*a.mean), (C.c_float * 3)(*a.std), {"cls": 0, "cls_mean": 1}[a.pool])
         g = lambda n: getattr(self, n).data_ptr()
         w = StampVitWeights(g("patch_w"), g("patch_b"), g("prefix"), g("pos"), g("norm_w"), g("norm_b"))
         blocks = (StampVitBlock * a.depth)()
@@ -230,7 +240,7 @@ class TileEncoder(nn.Module):
         self._structs = (cfg, w, blocks)
 
     def launches_per_batch(self) -> int:
-        return 3 + 7 * self.arch.depth + 1 + (1 if self.arch.pre_resize else 0)
+        return 3 + 7 * self.arch.depth + 1 + (1 if self.arch.pre_resize else 0) + (1 if self.arch.pool == "cls_mean" else 0)
 
     @torch.no_grad()
     def forward(self, tiles: Tensor) -> Tensor:
@@ -254,7 +264,7 @@ class TileEncoder(nn.Module):
             self._build_structs()
         cfg, w, blocks = self._structs
         n = tiles.shape[0]
-        out = torch.empty((n, a.dim), dtype=torch.float16, device=tiles.device)
+        out = torch.empty((n, a.out_dim), dtype=torch.float16, device=tiles.device)
         stream = torch.cuda.current_stream().cuda_stream
         for s in range(0, n, self.max_batch):
             b = min(self.max_batch, n - s)

@@ -135,6 +135,32 @@ def test_virchow2_vit_h14_at_benched_batch_96(cuda_device):
     assert err < 1e-3, err
 
 
+def test_virchow_full_cls_and_mean_patch_token(cuda_device):
+    """virchow_full.py:24-35: [class token | mean of the other tokens] after the final norm (2 x dim values), Virchow-v1
+    shaped blocks (patch 14, SwiGLU, no register tokens) three deep at full width; and the class-token half equals the
+    plain class-token extractor's output of the same weights."""
+    from dataclasses import replace
+
+    from oracle import vit_oracle as vo
+    from stamp_b200.vit import VIRCHOW_ARCH, VIRCHOW_FULL_ARCH, TileEncoder
+
+    cfg = vo.VitConfig("virchow-d3", patch=14, dim=1280, depth=3, heads=16, mlp_hidden=6832, mlp="swiglu")
+    w = vo.make_weights(cfg, seed=1234)
+    tiles = vo.synthetic_tiles(5, seed=8)
+    with torch.no_grad():
+        tok = vo.forward_tokens(w, cfg, vo.transform_u8(tiles, torch.float32, cfg.mean, cfg.std))
+        ref = torch.cat([tok[:, 0], tok[:, 1:].mean(1)], dim=-1)
+    full = TileEncoder(replace(VIRCHOW_FULL_ARCH, depth=3), w, max_batch=3).to(cuda_device).eval()
+    out = full(tiles.to(cuda_device))
+    assert out.shape == (5, 2560) and out.dtype == torch.float16 and torch.isfinite(out).all()
+    assert _per_tile_rel(out[:, :1280].float(), ref[:, :1280]) < 1e-3
+    assert _per_tile_rel(out[:, 1280:].float(), ref[:, 1280:]) < 1e-3
+    cls = TileEncoder(replace(VIRCHOW_ARCH, depth=3), w, max_batch=8).to(cuda_device).eval()(tiles.to(cuda_device))
+    # (the class-token-only encoder skips the other tokens in its last block: same arithmetic on the rows it keeps)
+    assert _per_tile_rel(cls.float(), out[:, :1280].float()) < 2e-4
+    assert full.launches_per_batch() == 3 + 7 * 3 + 1 + 1
+
+
 def test_tile_encoder_refuses_cpu():
     from oracle import vit_oracle as vo
     from stamp_b200.vit import TileEncoder, VitArch
