@@ -6,7 +6,7 @@ accepts an instance directly (src/stamp/preprocessing/__init__.py:117,237-238), 
 the device, calls ``model(batch)`` under ``inference_mode`` and stores ``.half().cpu()``
 (:243,322-327).  ``identifier`` is what lands in the output folder name and the ``extractor`` h5
 attribute, so the factories below keep the reference's identifiers (the ``ExtractorName`` values
-"uni", "virchow", "virchow-full", "virchow2", "uni2", "h-optimus-0", "h-optimus-1", "gigapath"; src/stamp/preprocessing/config.py:13-33).
+"uni", "virchow", "virchow-full", "virchow2", "uni2", "h-optimus-0", "h-optimus-1", "gigapath", "dino-bloom"; src/stamp/preprocessing/config.py:13-33).
 When ``stamp`` is importable the factories return instances of the reference's own ``Extractor``.
 
 The transform returns the tile as a uint8 HWC tensor (legal: the reference's ``empty`` extractor
@@ -25,7 +25,7 @@ import numpy as np
 import torch
 from torch import Tensor, nn
 
-from .vit import (GIGAPATH_ARCH, H_OPTIMUS_ARCH, UNI2_ARCH, UNI_ARCH, VIRCHOW2_ARCH, VIRCHOW_ARCH, VIRCHOW_FULL_ARCH,
+from .vit import (DINOBLOOM_ARCH, GIGAPATH_ARCH, H_OPTIMUS_ARCH, UNI2_ARCH, UNI_ARCH, VIRCHOW2_ARCH, VIRCHOW_ARCH, VIRCHOW_FULL_ARCH,
                   TileEncoder, VitArch,
                   random_state_dict)
 
@@ -146,6 +146,15 @@ def h_optimus_1(weights=None, max_batch: int = 64) -> Extractor[TileEncoder]:
     """H-optimus-1, same architecture and preprocessing (reference: .../extractor/h_optimus_1.py)."""
     return _make(H_OPTIMUS_ARCH, "h-optimus-1", weights, "hf-hub:bioptimus/H-optimus-1",
                  dict(init_values=1e-5, dynamic_img_size=False), max_batch)
+
+
+def dino_bloom(weights, max_batch: int = 384) -> Extractor[TileEncoder]:
+    """DinoBloom-S (reference: .../extractor/dinobloom.py:30-78).  ``weights``: the ``teacher`` state dict of
+    DinoBloom-S.pth with the ``backbone.`` prefix removed (what the reference loads into the hub model), a path to a
+    checkpoint in that layout, or "random"; the Zenodo download of the reference is the caller's business."""
+    if isinstance(weights, Mapping) and any(k.startswith("backbone.") for k in weights):
+        weights = {k.removeprefix("backbone."): v for k, v in weights.items() if "dino_head" not in k and "ibot_head" not in k}
+    return _make(DINOBLOOM_ARCH, "dino-bloom", weights, None, {}, max_batch)
 
 
 def gigapath(weights=None, max_batch: int = 64) -> Extractor[TileEncoder]:

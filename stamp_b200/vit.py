@@ -93,6 +93,10 @@ H_OPTIMUS_ARCH = VitArch("h_optimus", patch=14, dim=1536, depth=40, heads=24, ml
 VIRCHOW_ARCH = VitArch("virchow", patch=14, dim=1280, depth=32, heads=16, mlp_hidden=6832, mlp="swiglu")
 VIRCHOW_FULL_ARCH = VitArch("virchow_full", patch=14, dim=1280, depth=32, heads=16, mlp_hidden=6832, mlp="swiglu",
                             pool="cls_mean")
+# dinobloom.py:30-78: DinoBloom-S = facebookresearch/dinov2 ViT-S/14 (embed 384, depth 12, 6 heads, LayerScale, GELU MLP
+# 1536) with a 257-row position table (16 x 16 patches of a 224 px tile + class token: no resampling); returns the
+# normalised class token.  The DINOv2 state-dict keys are timm's (plus an unused mask_token).
+DINOBLOOM_ARCH = VitArch("dinobloom", patch=14, dim=384, depth=12, heads=6, mlp_hidden=1536)
 # gigapath.py:14-35: timm vit_giant_patch14_dinov2 with patch 16 at 224 px (embed 1536, depth 40, 24 heads, SwiGLUPacked
 # 8192, class token inside the position table); the transform's Resize(256, BICUBIC) + CenterCrop(224) runs on the GPU
 GIGAPATH_ARCH = VitArch("gigapath", patch=16, dim=1536, depth=40, heads=24, mlp_hidden=8192, mlp="swiglu",

@@ -161,6 +161,25 @@ def test_virchow_full_cls_and_mean_patch_token(cuda_device):
     assert full.launches_per_batch() == 3 + 7 * 3 + 1 + 1
 
 
+def test_dinobloom_vit_s14_matches_oracle(cuda_device):
+    """dinobloom.py:30-78: DINOv2 ViT-S/14 at full depth (dim 384 = one and a half 256-column GEMM tiles, 6 heads of 64,
+    257 tokens), weights handed over with the checkpoint's ``backbone.`` prefix."""
+    from oracle import vit_oracle as vo
+    from stamp_b200.extractor import dino_bloom
+
+    cfg = vo.VitConfig("dinobloom", patch=14, dim=384, depth=12, heads=6, mlp_hidden=1536)
+    w = vo.make_weights(cfg, seed=1234)
+    tiles = vo.synthetic_tiles(6, seed=12)
+    with torch.no_grad():
+        ref = vo.forward(w, cfg, tiles)
+    teacher = {f"backbone.{k}": v for k, v in w.items()}
+    teacher["dino_head.mlp.0.weight"] = torch.zeros(4, 4)
+    ext = dino_bloom(teacher, max_batch=4)
+    assert ext.identifier == "dino-bloom"
+    out = ext.model.to(cuda_device).eval()(tiles.to(cuda_device))
+    assert out.shape == (6, 384) and _per_tile_rel(out.float(), ref) < 1e-3
+
+
 def test_tile_encoder_refuses_cpu():
     from oracle import vit_oracle as vo
     from stamp_b200.vit import TileEncoder, VitArch
