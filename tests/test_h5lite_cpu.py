@@ -354,3 +354,41 @@ def test_reader_survives_corrupt_files():
         except OSError:
             outcomes["rejected"] += 1
     assert outcomes["ok"] > 100 and outcomes["rejected"] > 100, outcomes
+
+
+def test_roundtrip_property():
+    """Random datasets (dtype, rank 0-3, empty dimensions) and attributes (strings incl. non-ASCII, scalars, arrays)
+    survive write -> read unchanged, whatever their number and order."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    dtypes = ["f2", "f4", "f8", "i1", "i4", "i8", "u1", "u2", "u8"]
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(specs=st.lists(st.tuples(st.sampled_from(dtypes), st.lists(st.integers(0, 7), min_size=1, max_size=3)),
+                          min_size=0, max_size=12),
+           texts=st.lists(st.text(min_size=0, max_size=40).filter(lambda s: "\\x00" not in s), max_size=6),
+           numbers=st.lists(st.one_of(st.integers(-2**62, 2**62), st.floats(allow_nan=False, width=64)), max_size=6),
+           seed=st.integers(0, 1000))
+    def check(specs, texts, numbers, seed):
+        rng = np.random.default_rng(seed)
+        datasets = {f"ds_{i}_{dt}": (rng.standard_normal(shape) * 100).astype(dt) for i, (dt, shape) in enumerate(specs)}
+        attrs = {f"t{i}": t for i, t in enumerate(texts)}
+        attrs.update({f"n{i}": n for i, n in enumerate(numbers)})
+        attrs["arr"] = rng.integers(-5, 5, size=(3, 2)).astype(np.int16)
+        blob = _write(datasets, attrs)
+        with h5lite.File(io.BytesIO(blob)) as f:
+            assert sorted(f.keys()) == sorted(datasets)
+            for k, v in datasets.items():
+                got = f[k][()]
+                assert got.dtype == v.dtype and got.shape == v.shape and np.array_equal(got, v)
+            for k, v in attrs.items():
+                got = f.attrs[k]
+                if isinstance(v, str):
+                    assert got == v and isinstance(got, str)
+                elif isinstance(v, np.ndarray):
+                    assert np.array_equal(got, v) and got.dtype == v.dtype
+                else:
+                    assert got == v and got.shape == ()
+
+    check()

@@ -115,3 +115,40 @@ def test_host_decoder_survives_corrupt_files():
             except _lib.StampB200Error:
                 bad += 1
     assert ok > 100 and bad > 100, (ok, bad)
+
+
+def test_host_decoder_plus_oracle_arithmetic_is_pillow_on_random_images():
+    """The product's host half (marker parsing + Huffman decoding) followed by the oracle's integer arithmetic equals
+    Pillow for random sizes, qualities and chroma layouts -- the CPU-side pin of everything the GPU kernels are fed."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+    from PIL import Image
+
+    from stamp_b200 import jpeg
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(h=st.integers(1, 70), w=st.integers(2, 70), quality=st.integers(5, 100), sub=st.sampled_from([0, 2]),
+           seed=st.integers(0, 10_000), smooth=st.booleans())
+    def check(h, w, quality, sub, seed, smooth):
+        rng = np.random.default_rng(seed)
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if smooth:
+            img = (np.cumsum(np.cumsum(img.astype(np.int64), 0), 1) // (np.arange(1, h + 1)[:, None, None] * np.arange(1, w + 1)[None, :, None])).astype(np.uint8)
+        data = _jpeg(np.ascontiguousarray(img), quality=quality, subsampling=sub)
+        want = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+        info, coef, quant = jpeg.entropy_decode([data], max_workers=1)
+        c = coef[0].numpy()
+        planes, off = [], 0
+        for i in range(3):
+            by, bx = info.mcus_y * info.v[i], info.mcus_x * info.h[i]
+            n = by * bx * 64
+            planes.append(jo.idct_islow(c[off:off + n].reshape(by, bx, 64), quant[0, i].numpy().astype(np.uint16).astype(np.int32)))
+            off += n
+        if info.h[0] == 2:
+            cb, cr = (jo.h2v2_fancy_upsample(p, -(-h // 2), -(-w // 2)) for p in planes[1:])
+        else:
+            cb, cr = planes[1], planes[2]
+        got = jo.ycc_to_rgb(planes[0][:h, :w], cb[:h, :w], cr[:h, :w])
+        assert np.array_equal(got, want)
+
+    check()
