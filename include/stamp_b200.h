@@ -341,6 +341,34 @@ int stamp_tile_texture_u8(const uint8_t* tiles, int n_tiles, int H, int W, int l
                           int* edge_count, uint8_t* edges_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * fp32 building blocks of the TransMIL aggregator (inference): the small-matrix side of its Nystrom attention and its
+ * position layer; the dense layers around them use stamp_gemm_tn.
+ * replaces: NystromAttention.forward / moore_penrose_iter_pinv, src/stamp/modeling/models/trans_mil.py:25-160, and
+ *   PPEG.forward :253-273.  Token-major fp32 matrices [rows, ld]; head h = columns h*64 .. h*64+63.
+ *   stamp_landmark_mean_f32   out[j, c] = mean of `group` consecutive rows of x             (:113-127, reduce "(n l) d -> n d")
+ *   stamp_sgemm_batched_f32   C[b] (+)= alpha * A[b] @ op(B[b]) + bias; op = B^T (trans_b), B, or (eye_minus_b * I - B) for the
+ *                             Newton-Schulz steps z <- 1/4 z (13 I - xz (15 I - xz (7 I - xz)))   (:25-42)
+ *   stamp_softmax_rows_f32    in-place row softmax of [batch][rows, cols]
+ *   stamp_pinv_init_f32       z0 = x^T / (max row abs-sum * max column abs-sum over the WHOLE batch); scratch2: 2 uint32
+ *   stamp_attention_f32       O = softmax(scale * Q K^T) V per 64-wide head, any nq / nk (attn1 @ W and attn3 @ v)
+ *   stamp_dwconv1d_add_f32    out += depth-wise convolution of v along the tokens, one `taps`-vector per head  (res_conv, :82-90,153)
+ *   stamp_dwconv2d_f32        depth-wise ksize x ksize convolution of tokens laid out on an H x W grid, zero padded  (PPEG)
+ * ------------------------------------------------------------------------------------------- */
+int stamp_landmark_mean_f32(const float* x, long long ldx, int group, float* out, long long ldo, int n_landmarks, int cols,
+                            void* stream);
+int stamp_sgemm_batched_f32(const float* A, long long lda, long long stride_a, const float* B, long long ldb, long long stride_b,
+                            float* C, long long ldc, long long stride_c, int M, int N, int K, int batch, int trans_b, float alpha,
+                            float eye_minus_b, const float* bias /* [N] or NULL */, int mode /* bit 0: C +=, bit 1: ReLU */, void* stream);
+int stamp_softmax_rows_f32(float* x, long long ld, long long stride, int rows, int cols, int batch, void* stream);
+int stamp_pinv_init_f32(const float* x, float* z, int n, int batch, unsigned int* scratch2, void* stream);
+int stamp_attention_f32(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O,
+                        long long ldo, int nq, int nk, int heads, float scale, void* stream);
+int stamp_dwconv1d_add_f32(const float* v, long long ldv, const float* w, float* out, long long ldo, int n, int heads, int taps,
+                           void* stream);
+int stamp_dwconv2d_f32(const float* in, long long ldi, const float* k, const float* bias, float* out, long long ldo, int H, int W,
+                       int C, int ksize, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Decode of cached JPEG tiles, bit-exact with Pillow (libjpeg-turbo defaults: islow inverse DCT, fancy chroma
  * up-sampling, fixed-point YCbCr -> RGB).
  * replaces: Image.open(tile_fp) + img.load() per cached tile in _tiles_from_cache_file,

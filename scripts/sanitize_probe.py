@@ -5,7 +5,8 @@
 MIL training step and inference forward at a ragged bag length (333 tiles: tcgen05 long-bag attention forward v3,
 backward, weight gradients, row ops, fused AdamW), the ViT tile encoder for head dimensions 64 and 80 (GEMM epilogues
 incl. GELU / SwiGLU / residual reduce-add, streaming attention, LayerNorm, patch kernel) on a ragged batch, Macenko,
-the tissue-texture filter, the bicubic resampling, CHIEF pooling + top-k."""
+the tissue-texture filter, the bicubic resampling, CHIEF pooling + top-k, the JPEG tile decode, a ragged MIL batch, the
+TransMIL and barspoon aggregators."""
 import sys
 from pathlib import Path
 
@@ -60,3 +61,27 @@ pooled = GatedAttentionPool(sd).to(dev)(torch.randn(777, 768, device=dev))
 vals, idx = topk(pooled["attention_raw"].squeeze(0).contiguous(), 25)
 torch.cuda.synchronize()
 print("side kernels ok", norm.shape, cnt.tolist(), rs.shape, idx[:3].tolist())
+
+import io
+
+from PIL import Image
+
+from stamp_b200.barspoon import EncDecTransformer
+from stamp_b200.jpeg import decode_jpeg_tiles
+from stamp_b200.transmil import TransMIL
+
+blobs = []
+for t in tiles[:3].cpu().numpy():
+    b = io.BytesIO()
+    Image.fromarray(t[:100, :77]).save(b, format="jpeg")
+    blobs.append(b.getvalue())
+dec = decode_jpeg_tiles(blobs, dev, max_workers=1)
+rag = [(torch.randn(n, 64).half(), torch.rand(n, 2) * 5000) for n in (300, 1, 77, 515)]
+tok, crd, seq, smax = m.pack_ragged(rag, pin=False)
+with torch.inference_mode():
+    lr = m.forward_ragged(tok.to(dev), crd.to(dev), seq.to(dev), smax)
+    tm = TransMIL(3, 64, 512).to(dev).eval()(torch.randn(2, 333, 64, device=dev))
+    bs = EncDecTransformer(64, {"a": 2, "b": 3}, d_model=128, num_encoder_heads=2, num_decoder_heads=2,
+                           dim_feedforward=256).to(dev).eval()(torch.randn(1, 200, 64, device=dev), torch.rand(1, 200, 2, device=dev) * 1e4)
+torch.cuda.synchronize()
+print("new paths ok", dec.shape, lr.shape, tm.shape, {k: v.shape for k, v in bs.items()})

@@ -54,13 +54,17 @@ class EncDecTransformer(nn.Module):
             if d_model % h or d_model // h not in (32, 64) or d_features % 8 or d_model % 8 or dim_feedforward % 8:
                 raise ValueError("unsupported barspoon configuration for the sm_100a kernels (head dimension 32 / 64, "
                                  "widths in multiples of 8)")
-        self._half: dict[int, tuple[int, Tensor]] = {}
+        self._half: dict[int, tuple[tuple, Tensor]] = {}
 
     def _w16(self, p: Tensor) -> Tensor:
         """fp16 copy of a weight matrix, refreshed when the parameter changes."""
+        try:
+            key = (p._version, p.data_ptr())
+        except RuntimeError:            # parameters created under inference_mode do not track versions
+            key = (-1, p.data_ptr())
         hit = self._half.get(id(p))
-        if hit is None or hit[0] != p._version or hit[1].device != p.device:
-            hit = (p._version, p.detach().half().contiguous())
+        if hit is None or hit[0] != key or hit[1].device != p.device:
+            hit = (key, p.detach().half().contiguous())
             self._half[id(p)] = hit
         return hit[1]
 
