@@ -599,13 +599,18 @@ def run_b200(args) -> None:
         encoding_out = encoding_block(dev, rank, world)
 
     # ---- the other tile encoders of the reference on the same kernels (rank 0, N = 1)
-    extractors_out = cache_out = None
+    extractors_out = cache_out = aggregators_out = None
     if rank == 0 and world == 1 and not args.skip_configs:
         from bench_extra import cache_to_features_block, extractors_block
 
         extractors_out = extractors_block(dev, peak_tf)
         torch.cuda.empty_cache()
         cache_out = cache_to_features_block(dev)
+        torch.cuda.empty_cache()
+        from bench_extra import aggregators_block
+
+        aggregators_out = aggregators_block(dev, float(peaks.get("hbm_gbs", 6650.0)))
+        torch.cuda.empty_cache()
 
     # ---- the reference's own GPU path (eager torch on this GPU) for the same three stages (rank 0, N = 1)
     torch_gpu = None
@@ -637,7 +642,8 @@ def run_b200(args) -> None:
             "cpu_baseline": cpu, "mil": mil_out, "mil_train": train_out,
             "other_configs": {"virchow2_cohort": cohort_out, "crossval": crossval_out, "slide_encoding": encoding_out,
                               **(extra_out or {}),
-                              "other_extractors": extractors_out, "cache_to_features": cache_out},
+                              "other_extractors": extractors_out, "cache_to_features": cache_out,
+                              "other_aggregators": aggregators_out},
             "torch_gpu_baseline": torch_gpu, "hbm_kernels": hbm_out,
         }
         print(json.dumps(line), flush=True)

@@ -446,3 +446,33 @@ def extractors_block(dev, peak_tf: float, batch: int = 96) -> dict:
                   "blocks, incl. its Resize(256, bicubic) + CenterCrop(224) on the GPU): SwiGLU, 8 / 4 / 0 register " \
                   "tokens, head dimension 64, same GEMM / attention / LayerNorm kernels as UNI and Virchow2"
     return out
+
+
+def aggregators_block(dev, hbm_gbs: float) -> dict:
+    """the reference's other aggregators (models/mlp.py, models/trans_mil.py) on device-resident bags.
+    The bag mean of MLP / Linear is the HBM-bound kernel: 64 bags x 4096 tiles x 1024 fp16 features = 537 MB per call
+    (larger than L2), every byte read once."""
+    from stamp_b200.mlp import MLP, bag_mean
+    from stamp_b200.transmil import TransMIL
+
+    out = {}
+    try:
+        bags = torch.randn(64, 4096, 1024, device=dev).half()
+        t = _timed(lambda: bag_mean(bags), reps=20, warm=3)
+        gbs = bags.numel() * 2 / t / 1e9
+        out["bag_mean"] = {"shape": list(bags.shape), "dtype": "f16", "us_per_call": t * 1e6, "achieved_GBps": gbs,
+                           "peak_GBps": hbm_gbs, "frac": gbs / hbm_gbs, "algorithmic_bytes": bags.numel() * 2}
+        mlp = MLP(1024, 512, 2, 3, 0.25).to(dev).eval()
+        with torch.inference_mode():
+            t = _timed(lambda: mlp(bags), reps=20, warm=3)
+        out["mlp"] = {"slides_per_s": bags.shape[0] / t, "tiles_per_slide": 4096, "dim_input": 1024,
+                      "note": "bag mean + three fp32 Linear layers, 64 bags per call"}
+        one = bags[:1].float()
+        tm = TransMIL(2, 1024, 512).to(dev).eval()
+        with torch.inference_mode():
+            t = _timed(lambda: tm(one), reps=5, warm=2)
+        out["transmil"] = {"slides_per_s": 1.0 / t, "tiles_per_slide": 4096, "dim_input": 1024,
+                           "note": "_fc1 on the tcgen05 GEMM, Nystrom attention / pseudo-inverse / PPEG in fp32 on the CUDA cores, one bag per call"}
+    except Exception as e:  # noqa: BLE001 -- an auxiliary block must not take the bench line down
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out

@@ -369,6 +369,20 @@ int stamp_dwconv2d_f32(const float* in, long long ldi, const float* k, const flo
                        int C, int ksize, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Mean over the tiles of a bag: the pooling step of the MLP / Linear aggregators (the layers after it are
+ * stamp_sgemm_batched_f32 calls on [B, F] rows).
+ * replaces: `x.mean(dim=1)` in MLP.forward / Linear.forward, src/stamp/modeling/models/mlp.py:40-43, :57-60.
+ *   x        [B][n_tiles, ldx] fp32 or fp16 (is_half), bag b at x + b * stride_bag (elements)
+ *   out      [B, ldo] fp32 means
+ *   splits   CTAs sharing the rows of one bag (stamp_bag_mean_splits' suggestion fills 148 SMs); scratch holds
+ *            splits * B * F floats when splits > 1 (two deterministic stages, no atomics), may be NULL otherwise
+ * HBM-bound: B * n_tiles * F * sizeof(element) bytes read once.
+ * ------------------------------------------------------------------------------------------- */
+int stamp_bag_mean_splits(int B, int n_tiles, int F, int is_half);
+int stamp_bag_mean(const void* x, int is_half, long long ldx, long long stride_bag, int B, int n_tiles, int F, float* out,
+                   long long ldo, float* scratch, int splits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Decode of cached JPEG tiles, bit-exact with Pillow (libjpeg-turbo defaults: islow inverse DCT, fancy chroma
  * up-sampling, fixed-point YCbCr -> RGB).
  * replaces: Image.open(tile_fp) + img.load() per cached tile in _tiles_from_cache_file,
