@@ -350,7 +350,9 @@ int stamp_tile_texture_u8(const uint8_t* tiles, int n_tiles, int H, int W, int l
  *                             Newton-Schulz steps z <- 1/4 z (13 I - xz (15 I - xz (7 I - xz)))   (:25-42)
  *   stamp_softmax_rows_f32    in-place row softmax of [batch][rows, cols]
  *   stamp_pinv_init_f32       z0 = x^T / (max row abs-sum * max column abs-sum over the WHOLE batch); scratch2: 2 uint32
- *   stamp_attention_f32       O = softmax(scale * Q K^T) V per 64-wide head, any nq / nk (attn1 @ W and attn3 @ v)
+ *   stamp_attention_f32       O = softmax(scale * Q K^T) V per 64-wide head, any nq / nk (attn1 @ W and attn3 @ v); splits > 1
+ *                             shares the keys among `splits` CTAs per query block (few landmark queries over many keys) through
+ *                             scratch [splits * heads * nq * 66] floats, merged by a second kernel; splits = 1: scratch may be NULL
  *   stamp_dwconv1d_add_f32    out += depth-wise convolution of v along the tokens, one `taps`-vector per head  (res_conv, :82-90,153)
  *   stamp_dwconv2d_f32        depth-wise ksize x ksize convolution of tokens laid out on an H x W grid, zero padded  (PPEG)
  * ------------------------------------------------------------------------------------------- */
@@ -362,7 +364,7 @@ int stamp_sgemm_batched_f32(const float* A, long long lda, long long stride_a, c
 int stamp_softmax_rows_f32(float* x, long long ld, long long stride, int rows, int cols, int batch, void* stream);
 int stamp_pinv_init_f32(const float* x, float* z, int n, int batch, unsigned int* scratch2, void* stream);
 int stamp_attention_f32(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O,
-                        long long ldo, int nq, int nk, int heads, float scale, void* stream);
+                        long long ldo, int nq, int nk, int heads, float scale, float* scratch, int splits, void* stream);
 int stamp_dwconv1d_add_f32(const float* v, long long ldv, const float* w, float* out, long long ldo, int n, int heads, int taps,
                            void* stream);
 int stamp_dwconv2d_f32(const float* in, long long ldi, const float* k, const float* bias, float* out, long long ldo, int H, int W,

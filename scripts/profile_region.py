@@ -1,7 +1,7 @@
 """One warm unit of work between cudaProfilerStart/Stop, for ncu launch lists:
 
     ncu --profile-from-start off --metrics gpu__time_duration.sum,... --csv --log-file out.csv \\
-        python scripts/profile_region.py {vit_l16|virchow2|gigapath|resize|jpeg|mil_deploy|mil_train|macenko}
+        python scripts/profile_region.py {vit_l16|virchow2|gigapath|resize|jpeg|mil_deploy|mil_train|macenko|transmil}
 """
 import sys
 from pathlib import Path
@@ -83,6 +83,15 @@ elif what == "macenko":
     tiles = synthetic_he_tiles(768, 3, dev)
     out = torch.empty_like(tiles)
     unit = lambda: macenko_normalize(tiles, out=out)
+elif what == "transmil":
+    from stamp_b200.transmil import TransMIL
+
+    tm = TransMIL(2, 1024, 512).to(dev).eval()
+    bag = torch.randn(1, 4096, 1024, device=dev)
+
+    def unit():
+        with torch.inference_mode():
+            tm(bag)
 else:
     raise SystemExit(__doc__)
 

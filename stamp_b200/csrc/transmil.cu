@@ -34,38 +34,62 @@ landmark_mean_kernel(const float* __restrict__ x, long long ldx, int group, floa
 }
 
 // C[b] (+)= alpha * A[b] @ op(B[b]) + bias,  op(B) = B^T (trans_b) or B or (eye * I - B); 64 x 64 tile, 256 threads, 4 x 4 per thread
-constexpr int SG_T = 64, SG_K = 16;
+constexpr int SG_T = 64, SG_K = 16, SG_LD = SG_T + 4;       // row stride 272 B: 128-bit shared-memory reads stay aligned
+// The next K-slice is fetched into registers while the current one is multiplied out of shared memory: the small products
+// of the pseudo-inverse run one CTA per SM (8 heads x 16 tiles), where nothing else hides the load latency.
+template <bool TRANS_B>
 __global__ void __launch_bounds__(256)
 sgemm_batched_kernel(const float* __restrict__ A, long long lda, long long sa, const float* __restrict__ B, long long ldb,
-                     long long sb_, float* __restrict__ C, long long ldc, long long sc, int M, int N, int K, int trans_b,
+                     long long sb_, float* __restrict__ C, long long ldc, long long sc, int M, int N, int K,
                      float alpha, float eye, const float* __restrict__ bias, int accumulate) {
-    __shared__ float As[SG_K][SG_T + 1];
-    __shared__ float Bs[SG_K][SG_T + 1];
+    __shared__ __align__(16) float As[SG_K][SG_LD];
+    __shared__ __align__(16) float Bs[SG_K][SG_LD];
     const float* a = A + blockIdx.z * sa;
     const float* b = B + blockIdx.z * sb_;
     float* c = C + blockIdx.z * sc;
     const int m0 = blockIdx.y * SG_T, n0 = blockIdx.x * SG_T;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += SG_K) {
-        for (int i = threadIdx.x; i < SG_T * SG_K; i += 256) {
-            const int r = i / SG_K, kk = i % SG_K;       // A tile: row r of the tile, column kk
-            const int m = m0 + r, k = k0 + kk;
-            As[kk][r] = (m < M && k < K) ? a[static_cast<long long>(m) * lda + k] : 0.f;
-            const int n = n0 + r;                        // B tile: output column r, contraction index kk
-            float v = 0.f;
-            if (n < N && k < K) {
-                v = trans_b ? b[static_cast<long long>(n) * ldb + k] : b[static_cast<long long>(k) * ldb + n];
-                if (eye != 0.f) v = (k == n ? eye : 0.f) - v;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    // row-major operands (A, and B when the product is A B^T): thread -> 16 consecutive k of one row (64-byte segments);
+    // B of A B: thread -> 64 consecutive columns of one row of B (coalesced)
+    const int a_kk = tid & 15, a_r = tid >> 4;           // + 16 j
+    const int b_kk = TRANS_B ? a_kk : tid >> 6;          // + 4 j when not transposed
+    const int b_r = TRANS_B ? a_r : tid & 63;
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + a_r + 16 * j, k = k0 + a_kk;
+            ra[j] = (m < M && k < K) ? a[static_cast<long long>(m) * lda + k] : 0.f;
+            if (TRANS_B) {
+                const int n = n0 + b_r + 16 * j;
+                rb[j] = (n < N && k < K) ? b[static_cast<long long>(n) * ldb + k] : 0.f;
+            } else {
+                const int n = n0 + b_r, kb = k0 + b_kk + 4 * j;
+                float v = 0.f;
+                if (n < N && kb < K) {
+                    v = b[static_cast<long long>(kb) * ldb + n];
+                    if (eye != 0.f) v = (kb == n ? eye : 0.f) - v;
+                }
+                rb[j] = v;
             }
-            Bs[kk][r] = v;
+        }
+    };
+    float acc[4][4] = {};
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += SG_K) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            As[a_kk][a_r + 16 * j] = ra[j];
+            if (TRANS_B) Bs[b_kk][b_r + 16 * j] = rb[j];
+            else Bs[b_kk + 4 * j][b_r] = rb[j];
         }
         __syncthreads();
+        if (k0 + SG_K < K) fetch(k0 + SG_K);
 #pragma unroll
         for (int kk = 0; kk < SG_K; ++kk) {
-            float av[4], bv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { av[i] = As[kk][ty * 4 + i]; bv[i] = Bs[kk][tx * 4 + i]; }
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -132,12 +156,14 @@ pinv_init_kernel(const float* __restrict__ x, float* __restrict__ z, int n, int 
 }
 
 // O = softmax(scale * Q K^T) V per head (head dimension 64), fp32, online softmax: one thread per query row, 64 rows per CTA,
-// key tiles of 32 rows staged in shared memory
-constexpr int FA_Q = 64, FA_K = 32;
+// key tiles of 32 rows staged in shared memory.  gridDim.z > 1 splits the keys (few queries over many keys: the landmark
+// rows of attn3 @ v): CTA z takes `keys_per_split` keys and leaves its unnormalised accumulator, row maximum and row sum
+// in part[((z * heads + h) * nq + row) * 66 ..], attention_f32_combine_kernel merges them.
+constexpr int FA_Q = 64, FA_K = 32, FA_PART = 66;
 __global__ void __launch_bounds__(FA_Q)
 attention_f32_kernel(const float* __restrict__ Q, long long ldq, const float* __restrict__ K, long long ldk,
-                     const float* __restrict__ V, long long ldv, float* __restrict__ O, long long ldo, int nq, int nk,
-                     float scale) {
+                     const float* __restrict__ V, long long ldv, float* __restrict__ O, long long ldo, int nq, int nk_all,
+                     float scale, int keys_per_split, float* __restrict__ part) {
     __shared__ float Ks[FA_K][64];
     __shared__ float Vs[FA_K][64];
     const int h = blockIdx.y;
@@ -147,7 +173,8 @@ attention_f32_kernel(const float* __restrict__ Q, long long ldq, const float* __
 #pragma unroll
     for (int d = 0; d < 64; ++d) { q[d] = qp[d] * scale; o[d] = 0.f; }
     float mx = -INFINITY, l = 0.f;
-    for (int k0 = 0; k0 < nk; k0 += FA_K) {
+    const int nk = min(nk_all, static_cast<int>(blockIdx.z + 1) * keys_per_split);
+    for (int k0 = blockIdx.z * keys_per_split; k0 < nk; k0 += FA_K) {
         for (int i = threadIdx.x; i < FA_K * 64; i += FA_Q) {
             const int r = i >> 6, d = i & 63;
             const bool ok = k0 + r < nk;
@@ -180,12 +207,41 @@ attention_f32_kernel(const float* __restrict__ Q, long long ldq, const float* __
         mx = tmx;
         __syncthreads();
     }
-    if (row < nq) {
+    if (row >= nq) return;
+    if (gridDim.z == 1) {
         const float inv = 1.0f / l;
         float* op = O + static_cast<long long>(row) * ldo + h * 64;
 #pragma unroll
         for (int d = 0; d < 64; ++d) op[d] = o[d] * inv;
+    } else {
+        float* pp = part + ((static_cast<long long>(blockIdx.z) * gridDim.y + h) * nq + row) * FA_PART;
+#pragma unroll
+        for (int d = 0; d < 64; ++d) pp[d] = o[d];
+        pp[64] = mx;
+        pp[65] = l;
     }
+}
+
+// one warp per (head, query row): O = sum_z o_z e^(m_z - M) / sum_z l_z e^(m_z - M), M = max_z m_z
+__global__ void __launch_bounds__(256)
+attention_f32_combine_kernel(const float* __restrict__ part, int splits, int heads, int nq, float* __restrict__ O, long long ldo) {
+    const long long w = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= static_cast<long long>(heads) * nq) return;
+    const int h = static_cast<int>(w / nq), row = static_cast<int>(w % nq);
+    float M = -INFINITY;
+    for (int z = 0; z < splits; ++z) M = fmaxf(M, part[((static_cast<long long>(z) * heads + h) * nq + row) * FA_PART + 64]);
+    float L = 0.f, o0 = 0.f, o1 = 0.f;
+    for (int z = 0; z < splits; ++z) {
+        const float* pp = part + ((static_cast<long long>(z) * heads + h) * nq + row) * FA_PART;
+        const float f = (pp[64] == -INFINITY) ? 0.f : expf(pp[64] - M);
+        L = fmaf(pp[65], f, L);
+        o0 = fmaf(pp[lane], f, o0);
+        o1 = fmaf(pp[lane + 32], f, o1);
+    }
+    float* op = O + static_cast<long long>(row) * ldo + h * 64;
+    op[lane] = o0 / L;
+    op[lane + 32] = o1 / L;
 }
 
 // out[i, h*64 + d] += sum_t w[h, t] * v[i + t - taps/2, h*64 + d]   (zero padding; nn.Conv2d(heads, heads, (taps, 1), groups=heads))
@@ -254,8 +310,12 @@ int stamp_sgemm_batched_f32(const float* A, long long lda, long long stride_a, c
         (eye_minus_b != 0.f && (trans_b || K != N)))
         return SB_ERR_BAD_ARG;
     const dim3 grid((N + SG_T - 1) / SG_T, (M + SG_T - 1) / SG_T, batch);
-    sgemm_batched_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, lda, stride_a, B, ldb, stride_b, C, ldc, stride_c,
-                                                                             M, N, K, trans_b, alpha, eye_minus_b, bias, accumulate);
+    if (trans_b)
+        sgemm_batched_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, lda, stride_a, B, ldb, stride_b, C, ldc, stride_c,
+                                                                                       M, N, K, alpha, eye_minus_b, bias, accumulate);
+    else
+        sgemm_batched_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(A, lda, stride_a, B, ldb, stride_b, C, ldc, stride_c,
+                                                                                        M, N, K, alpha, eye_minus_b, bias, accumulate);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
@@ -281,13 +341,24 @@ int stamp_pinv_init_f32(const float* x, float* z, int n, int batch, unsigned int
 }
 
 int stamp_attention_f32(const float* Q, long long ldq, const float* K, long long ldk, const float* V, long long ldv, float* O,
-                        long long ldo, int nq, int nk, int heads, float scale, void* stream) {
+                        long long ldo, int nq, int nk, int heads, float scale, float* scratch, int splits, void* stream_) {
     using namespace sb;
-    if (Q == nullptr || K == nullptr || V == nullptr || O == nullptr || nq <= 0 || nk <= 0 || heads <= 0 || heads > 65535)
+    if (Q == nullptr || K == nullptr || V == nullptr || O == nullptr || nq <= 0 || nk <= 0 || heads <= 0 || heads > 65535 ||
+        splits <= 0 || splits > 65535 || (splits > 1 && scratch == nullptr))
         return SB_ERR_BAD_ARG;
-    const dim3 grid((nq + FA_Q - 1) / FA_Q, heads);
-    attention_f32_kernel<<<grid, FA_Q, 0, static_cast<cudaStream_t>(stream)>>>(Q, ldq, K, ldk, V, ldv, O, ldo, nq, nk, scale);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int tiles = (nk + FA_K - 1) / FA_K;
+    if (splits > tiles) splits = tiles;
+    const int keys_per_split = ((tiles + splits - 1) / splits) * FA_K;
+    splits = (nk + keys_per_split - 1) / keys_per_split;             // no empty split
+    const dim3 grid((nq + FA_Q - 1) / FA_Q, heads, splits);
+    attention_f32_kernel<<<grid, FA_Q, 0, stream>>>(Q, ldq, K, ldk, V, ldv, O, ldo, nq, nk, scale, keys_per_split, scratch);
     count_launch();
+    if (splits > 1) {
+        attention_f32_combine_kernel<<<blocks_for(static_cast<long long>(heads) * nq * 32, 256), 256, 0, stream>>>(scratch, splits, heads,
+                                                                                                                  nq, O, ldo);
+        count_launch();
+    }
     return cudaGetLastError() == cudaSuccess ? SB_OK : SB_ERR_CUDA;
 }
 

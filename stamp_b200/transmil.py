@@ -39,7 +39,7 @@ def _bind() -> C.CDLL:
         lib.stamp_sgemm_batched_f32.argtypes = [vp, ll, ll, vp, ll, ll, vp, ll, ll, i, i, i, i, i, f, f, vp, i, vp]
         lib.stamp_softmax_rows_f32.argtypes = [vp, ll, ll, i, i, i, vp]
         lib.stamp_pinv_init_f32.argtypes = [vp, vp, i, i, vp, vp]
-        lib.stamp_attention_f32.argtypes = [vp, ll, vp, ll, vp, ll, vp, ll, i, i, i, f, vp]
+        lib.stamp_attention_f32.argtypes = [vp, ll, vp, ll, vp, ll, vp, ll, i, i, i, f, vp, i, vp]
         lib.stamp_dwconv1d_add_f32.argtypes = [vp, ll, vp, vp, ll, i, i, i, vp]
         lib.stamp_dwconv2d_f32.argtypes = [vp, ll, vp, vp, vp, ll, i, i, i, i, vp]
         for name in ("stamp_landmark_mean_f32", "stamp_sgemm_batched_f32", "stamp_softmax_rows_f32", "stamp_pinv_init_f32",
@@ -159,7 +159,15 @@ class TransMIL(nn.Module):
             sq(xz, t1, t2, 1.0, 15.0)
             sq(z, t2, t1, 0.25, 13.0)
             z, t1 = t1, z
-        att = lib.stamp_attention_f32
+
+        def att(q_, ldq, k_, ldk, v_, ldv, o_, nq, nk):
+            """softmax(scale q k^T) v per head; few query blocks over many keys (the landmark rows) share the keys among CTAs"""
+            ctas = -(-nq // 64) * H
+            splits = max(1, min(-(-148 * 4 // ctas), nk // 128)) if ctas < 148 else 1
+            part = torch.empty(splits * H * nq * 66, dtype=torch.float32, device=dev) if splits > 1 else None
+            _lib.check(lib.stamp_attention_f32(q_.data_ptr(), ldq, k_.data_ptr(), ldk, v_.data_ptr(), ldv, o_.data_ptr(), Cd, nq, nk, H,
+                                               scale, part.data_ptr() if part is not None else None, splits, st), "attention_f32")
+
         taps = a.res_conv.weight.shape[2]
         wconv = a.res_conv.weight.detach().float().reshape(H, taps).contiguous()
         lin = a.to_out[0]
@@ -169,12 +177,12 @@ class TransMIL(nn.Module):
             q, k, v = qkv[:, :Cd], qkv[:, Cd:2 * Cd], qkv[:, 2 * Cd:]
             # attn3 @ v (landmark queries over all keys), W = pinv @ that, out = attn1 @ W (all queries over the landmarks)
             a3v = torch.empty((m, Cd), dtype=torch.float32, device=dev)
-            _lib.check(att(ql.data_ptr(), Cd, k.data_ptr(), ld, v.data_ptr(), ld, a3v.data_ptr(), Cd, m, n_p, H, scale, st), "attention_f32")
+            att(ql, Cd, k, ld, v, ld, a3v, m, n_p)
             w = torch.empty((m, Cd), dtype=torch.float32, device=dev)
             _lib.check(mm(z[b * H:].data_ptr(), m, m * m, a3v.data_ptr(), Cd, hd, w.data_ptr(), Cd, hd, m, hd, m, H, 0, 1.0, 0.0,
                           None, 0, st), "sgemm")
             out = torch.empty((n_p, Cd), dtype=torch.float32, device=dev)
-            _lib.check(att(q.data_ptr(), ld, kl.data_ptr(), Cd, w.data_ptr(), Cd, out.data_ptr(), Cd, n_p, m, H, scale, st), "attention_f32")
+            att(q, ld, kl, Cd, w, Cd, out, n_p, m)
             _lib.check(lib.stamp_dwconv1d_add_f32(v.data_ptr(), ld, wconv.data_ptr(), out.data_ptr(), Cd, n_p, H, taps, st),
                        "stamp_dwconv1d_add_f32")
             # x += to_out(out[-n:])

@@ -57,3 +57,55 @@ def test_transmil_matches_reference_golden(cuda_device):
         with torch.inference_mode():
             alone = model(bags[1:].to(cuda_device)).float().cpu()
         assert (alone - got[1:]).abs().max() > 1e-5 or n == 300
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,batch", [(70, 33, 19, 3), (256, 256, 256, 8), (5, 130, 64, 1), (129, 64, 300, 2)])
+def test_sgemm_batched_f32_all_modes(cuda_device, M, N, K, batch):
+    """stamp_sgemm_batched_f32 at ragged shapes: A B^T and A B, the (eye * I - B) operand of the Newton-Schulz steps, bias,
+    ReLU and accumulation, against fp64."""
+    from stamp_b200 import _lib
+    from stamp_b200.transmil import _bind
+
+    lib = _bind()
+    g = torch.Generator().manual_seed(M * 1000 + N)
+    st = torch.cuda.current_stream().cuda_stream
+    A = torch.randn(batch, M, K, generator=g).to(cuda_device)
+    bias = torch.randn(N, generator=g).to(cuda_device)
+    for trans_b, eye, mode, use_bias in ((1, 0.0, 0, True), (0, 0.0, 0, False), (1, 0.0, 3, True), (0, 0.0, 1, True)) + \
+            (((0, 7.0, 0, False),) if N == K else ()):
+        B = torch.randn(batch, *((N, K) if trans_b else (K, N)), generator=g).to(cuda_device)
+        C0 = torch.randn(batch, M, N, generator=g).to(cuda_device)
+        C = C0.clone()
+        _lib.check(lib.stamp_sgemm_batched_f32(A.data_ptr(), K, M * K, B.data_ptr(), B.shape[2], B.shape[1] * B.shape[2], C.data_ptr(), N,
+                                               M * N, M, N, K, batch, trans_b, 0.5, eye, bias.data_ptr() if use_bias else None, mode, st),
+                   "sgemm")
+        Bd = B.double().transpose(1, 2) if trans_b else B.double()
+        if eye:
+            Bd = eye * torch.eye(N, device=cuda_device, dtype=torch.float64) - Bd
+        want = 0.5 * A.double() @ Bd + (bias.double() if use_bias else 0.0)
+        if mode & 2:
+            want = want.clamp_min(0.0)
+        if mode & 1:
+            want = want + C0.double()
+        assert ((C.double() - want).norm() / want.norm()).item() < 1e-6, (trans_b, eye, mode)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nq,nk,splits", [(256, 4352, 17), (100, 77, 1), (64, 1000, 5), (300, 256, 1), (7, 33, 9)])
+def test_attention_f32_key_splits(cuda_device, nq, nk, splits):
+    """stamp_attention_f32 with the keys shared among several CTAs equals softmax(scale Q K^T) V in fp64."""
+    from stamp_b200 import _lib
+    from stamp_b200.transmil import _bind
+
+    lib = _bind()
+    H = 2
+    g = torch.Generator().manual_seed(nq + nk)
+    q, k, v = (torch.randn(n, H * 64, generator=g).to(cuda_device) for n in (nq, nk, nk))
+    out = torch.empty(nq, H * 64, device=cuda_device)
+    part = torch.empty(splits * H * nq * 66, device=cuda_device)
+    _lib.check(lib.stamp_attention_f32(q.data_ptr(), H * 64, k.data_ptr(), H * 64, v.data_ptr(), H * 64, out.data_ptr(), H * 64, nq, nk,
+                                       H, 0.125, part.data_ptr(), splits, torch.cuda.current_stream().cuda_stream), "attention_f32")
+    sp = lambda t: t.double().reshape(-1, H, 64).transpose(0, 1)      # noqa: E731
+    want = ((sp(q) @ sp(k).transpose(1, 2) * 0.125).softmax(-1) @ sp(v)).transpose(0, 1).reshape(nq, H * 64)
+    assert ((out.double() - want).norm() / want.norm()).item() < 1e-6
