@@ -309,6 +309,17 @@ int stamp_pairwise_dist_mean(const float* coords, int B, int N, float* mean_out 
 int stamp_cross_entropy(const float* logits, const float* targets, const float* class_weights /* or NULL */,
                         int B, int C, float grad_scale, float* loss_out /* device scalar */,
                         float* dlogits_out, void* stream);
+/* Losses of the regression and survival tasks with their gradients, one launch each, no host synchronisation.
+ * replaces: nn.functional.l1_loss in LitBaseRegressor._compute_loss, src/stamp/modeling/models/__init__.py:420-422, and
+ *   neg_partial_log_likelihood(log_hz, time, event), src/stamp/modeling/models/cox.py:107-268 (ties: Efron by default,
+ *   Breslow when `breslow`; reduction "mean": over the distinct event times for Efron / no ties, over the events for
+ *   Breslow).  No events: loss 0, gradient 0.  n <= STAMP_COX_MAX_SAMPLES (one CTA, O(n^2) compares in shared memory).
+ *   d*_out (may be NULL) = grad_scale * dloss/dinput. */
+#define STAMP_COX_MAX_SAMPLES 8192
+int stamp_cox_loss(const float* log_hz, const float* time, const uint8_t* event, int n, int breslow, float grad_scale,
+                   float* loss_out /* device scalar */, float* dlog_hz_out, void* stream);
+int stamp_l1_loss(const float* pred, const float* target, long long n, float grad_scale, float* loss_out /* device scalar */,
+                  float* dpred_out, void* stream);
 /* torch.optim.AdamW step t (1-based) over flat fp32 buffers; grads are multiplied by grad_scale first */
 int stamp_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                      float lr, float beta1, float beta2, float eps, float weight_decay, int step,

@@ -69,6 +69,10 @@ def _bind() -> C.CDLL:
     lib.stamp_pairwise_dist_mean.argtypes = [vp, i32, i32, vp, vp, sz, vp]
     lib.stamp_cross_entropy.restype = i32
     lib.stamp_cross_entropy.argtypes = [vp, vp, vp, i32, i32, f32, vp, vp, vp]
+    lib.stamp_cox_loss.restype = i32
+    lib.stamp_cox_loss.argtypes = [vp, vp, vp, i32, i32, f32, vp, vp, vp]
+    lib.stamp_l1_loss.restype = i32
+    lib.stamp_l1_loss.argtypes = [vp, vp, ll, f32, vp, vp, vp]
     lib.stamp_adamw_step.restype = i32
     lib.stamp_adamw_step.argtypes = [vp, vp, vp, vp, ll, f32, f32, f32, f32, f32, i32, f32, vp]
     lib._train_bound = True
@@ -371,6 +375,87 @@ def training_step(model: VisionTransformer, batch, class_weights: Tensor | None 
     bags, coords, _bag_sizes, targets = batch
     logits = model(bags, coords=coords, mask=None)
     return cross_entropy(logits, targets.to(logits.dtype), class_weights)
+
+
+class _L1LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred: Tensor, target: Tensor) -> Tensor:
+        lib = _bind()
+        _need_cuda(pred, "pred")
+        p32 = pred.detach().float().contiguous()
+        t32 = target.detach().to(p32.device).float().expand_as(p32).contiguous()
+        loss = torch.empty((), dtype=torch.float32, device=p32.device)
+        dp = torch.empty_like(p32)
+        _lib.check(lib.stamp_l1_loss(p32.data_ptr(), t32.data_ptr(), p32.numel(), 1.0, loss.data_ptr(), dp.data_ptr(), _stream()),
+                   "stamp_l1_loss")
+        ctx.save_for_backward(dp)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        (dp,) = ctx.saved_tensors
+        return dp * g, None
+
+
+def l1_loss(pred: Tensor, target: Tensor) -> Tensor:
+    """``nn.functional.l1_loss`` as ``LitBaseRegressor._compute_loss`` calls it (models/__init__.py:420-422); the gradient
+    goes to ``pred`` (the reference passes its arguments in the order (preds, y), the loss is symmetric)."""
+    return _L1LossFn.apply(pred, target)
+
+
+class _CoxLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, log_hz: Tensor, time: Tensor, event: Tensor, breslow: bool) -> Tensor:
+        lib = _bind()
+        _need_cuda(log_hz, "log_hz")
+        s32 = log_hz.detach().float().contiguous()
+        t32 = time.detach().to(s32.device).float().contiguous()
+        e8 = (event.detach().to(s32.device) != 0).to(torch.uint8).contiguous()
+        if not (s32.ndim == 1 and t32.shape == s32.shape and e8.shape == s32.shape):
+            raise ValueError(f"log_hz, time and event must be vectors of one length, got {tuple(log_hz.shape)}, "
+                             f"{tuple(time.shape)}, {tuple(event.shape)}")
+        loss = torch.empty((), dtype=torch.float32, device=s32.device)
+        ds = torch.empty_like(s32)
+        _lib.check(lib.stamp_cox_loss(s32.data_ptr(), t32.data_ptr(), e8.data_ptr(), s32.numel(), int(breslow), 1.0, loss.data_ptr(),
+                                      ds.data_ptr(), _stream()), "stamp_cox_loss")
+        ctx.save_for_backward(ds)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        (ds,) = ctx.saved_tensors
+        return ds * g, None, None, None
+
+
+def neg_partial_log_likelihood(log_hz: Tensor, time: Tensor, event: Tensor, ties_method: str = "efron",
+                               reduction: str = "mean") -> Tensor:
+    """``neg_partial_log_likelihood`` of the reference (models/cox.py:107-268) in one launch, no host synchronisation:
+    Cox partial likelihood, Efron's (default) or Breslow's handling of tied times, reduction "mean".  Where the reference
+    returns a fresh zero leaf (no events in the batch) this returns a zero that is still connected to ``log_hz`` (zero
+    gradient); NaN inputs are not filtered (the reference's ``nanmean``)."""
+    if ties_method not in ("efron", "breslow"):
+        raise ValueError(f'Ties method {ties_method} should be one of ["efron", "breslow"]')
+    if reduction.lower() != "mean":
+        raise ValueError(f"Reduction {reduction} is not implemented, only 'mean' (what the reference's steps use)")
+    if log_hz.ndim == 0:
+        return log_hz * 0.0
+    return _CoxLossFn.apply(log_hz, time, event, ties_method == "breslow")
+
+
+def regression_step(model: VisionTransformer, batch) -> Tensor:
+    """``LitTileRegressor._step(step_name='training', use_mask=False)`` (models/__init__.py:444-462): dim_output = 1,
+    batch = (bags, coords, bag_sizes, targets [B, 1])."""
+    bags, coords, _bag_sizes, targets = batch
+    preds = model(bags, coords=coords, mask=None)
+    return l1_loss(preds, targets.to(preds.device).float())
+
+
+def survival_step(model: VisionTransformer, batch) -> Tensor:
+    """``LitTileSurvival.training_step`` (models/__init__.py:751-776): dim_output = 1, targets [B, 2] = (time, event)."""
+    bags, coords, _bag_sizes, targets = batch
+    preds = model(bags, coords=coords, mask=None)
+    y = targets.to(preds.device, dtype=torch.float32)
+    return neg_partial_log_likelihood(preds.squeeze(-1), y[:, 0], y[:, 1])
 
 
 # ---- optimiser -----------------------------------------------------------------------------------------

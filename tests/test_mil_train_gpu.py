@@ -42,7 +42,9 @@ def _model(sd, n_heads, device, dropout=0.0, p_ff=0.0):
     return m.to(device).train()
 
 
-def _check_grads(model, ref_grads, what, grad_tol=GRAD_TOL):
+def _check_grads(model, ref_grads, what, grad_tol=GRAD_TOL, term_scale=None):
+    """term_scale: per-tensor magnitude of the per-bag terms a gradient is the sum of -- the floor of the relative error for
+    losses whose per-bag cotangents cancel (the Cox loss: they sum to zero)."""
     worst = (0.0, None)
     named = {k: p.grad for k, p in model.named_parameters()}
     assert set(named) == set(ref_grads)
@@ -63,6 +65,8 @@ def _check_grads(model, ref_grads, what, grad_tol=GRAD_TOL):
         g, ref = torch.cat(ours[k]), torch.cat(refs[k])
         err = float((g - ref).norm())
         floor = 1e-5 * scale
+        if term_scale is not None and k in term_scale:
+            floor = max(floor, term_scale[k])
         if ".key_encoders." in k and k.endswith(".bias"):
             # analytically zero (softmax is invariant to the per-query shift a key bias adds): both sides
             # hold round-off only; bound it by the same head's key-weight gradient
