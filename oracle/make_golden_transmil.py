@@ -32,6 +32,13 @@ def main() -> None:
             bags = torch.randn(2, n, 64, generator=g).half().float()
             arrays[f"bags_checksum_{n}"] = np.array(bags.double().sum().item())
             arrays[f"logits_{n}"] = model(bags).numpy()
+    # the shape of the reference's own unit test (tests/test_model.py:135-166): 7 bags of 76 tiles, 457 input features, 4 classes
+    model = mod.TransMIL(dim_output=4, dim_input=457, dim_hidden=512).eval()
+    model.load_state_dict(transmil_state_dict(4, 457, 512), strict=True)
+    with torch.no_grad():
+        bags = torch.rand(7, 76, 457, generator=g).half().float()
+        arrays["bags_checksum_odd"] = np.array(bags.double().sum().item())
+        arrays["logits_odd"] = model(bags, coords=torch.rand(7, 76, 2), mask=torch.rand(7, 76) > 0.5).numpy()
     dst = Path(__file__).resolve().parent.parent / "tests" / "golden" / "transmil.npz"
     np.savez_compressed(dst, **arrays)
     print(dst, dst.stat().st_size, arrays["logits_300"], arrays["logits_1100"])

@@ -1,6 +1,7 @@
 """Patient-level inference loop: whole-bag forwards, one bag at a time, with the host->device copies hidden.
 
-Mirrors ``_predict`` (src/stamp/modeling/deploy.py:390-456) for the single-target classification case:
+Mirrors ``_predict`` (src/stamp/modeling/deploy.py:390-456) for the single-target case (classification below;
+``task="regression"`` / ``"survival"`` keep the raw outputs as :440-449 does):
 ``trainer.predict`` feeds ``LitTileClassifier.predict_step`` one patient per batch (batch size 1, all tiles;
 src/stamp/modeling/models/__init__.py:302-313), the logits are concatenated and ``softmax(dim=1)`` gives
 ``{patient_id: probabilities}``.
@@ -23,6 +24,14 @@ from .mil import VisionTransformer
 
 
 _STREAMS: dict[tuple[int, int], list[torch.cuda.Stream]] = {}
+TASKS = ("classification", "regression", "survival")
+
+
+def _finish(logits: Tensor, task: str) -> Tensor:
+    """What ``_predict`` does with the concatenated outputs (deploy.py:440-449): class probabilities for classification,
+    the raw [n, 1] predictions for regression, the risk scores (squeezed by the caller) for survival."""
+    logits = logits.float()
+    return torch.softmax(logits, dim=1) if task == "classification" else logits
 
 
 def _stream_pool(device: torch.device, n: int) -> list[torch.cuda.Stream]:
@@ -38,7 +47,9 @@ class _GraphedForward:
     input buffers the bag is copied into (straight from pinned host memory when it comes from the host), static
     output.  Valid for the packed weights it was captured with (``model._packed`` identity)."""
 
-    def __init__(self, model: VisionTransformer, stream: torch.cuda.Stream, feats: Tensor, coords: Tensor, device):
+    def __init__(self, model: VisionTransformer, stream: torch.cuda.Stream, feats: Tensor, coords: Tensor, device,
+                 task: str = "classification"):
+        self.task = task
         self.feats = torch.empty((1, *feats.shape), dtype=feats.dtype, device=device)
         self.coords = torch.empty((1, *coords.shape), dtype=torch.float32, device=device)
         self.feats.copy_(feats, non_blocking=True)
@@ -51,7 +62,7 @@ class _GraphedForward:
             self.probs = self._run(model)
 
     def _run(self, model: VisionTransformer) -> Tensor:
-        return torch.softmax(model(self.feats, coords=self.coords, mask=None).float(), dim=1)
+        return _finish(model(self.feats, coords=self.coords, mask=None), self.task)
 
     def __call__(self, feats: Tensor, coords: Tensor) -> Tensor:
         self.feats[0].copy_(feats, non_blocking=True)
@@ -67,9 +78,11 @@ _MAX_GRAPHS = 24
 
 @torch.inference_mode()
 def predict_bags(model: VisionTransformer, bags: Iterable[tuple[Tensor, Tensor]],
-                 device: torch.device | str = "cuda", n_streams: int = 3, graphs: bool = True) -> Tensor:
+                 device: torch.device | str = "cuda", n_streams: int = 3, graphs: bool = True,
+                 task: str = "classification") -> Tensor:
     """``bags`` yields ``(feats [N, F] fp16 | fp32, coords [N, 2])`` tensors (one patient each, on the host or already
-    on the device); returns the class probabilities ``[n_patients, C]`` on the host.
+    on the device); returns the class probabilities ``[n_patients, C]`` on the host (``task`` "regression" /
+    "survival": the raw ``[n_patients, 1]`` outputs, as ``_predict`` keeps them).
 
     Bags are independent batch-1 forwards (as in the reference's predict loop); they are issued round-robin on
     ``n_streams`` CUDA streams, each with its own workspace, so the host->device copy of one bag and the short,
@@ -81,6 +94,8 @@ def predict_bags(model: VisionTransformer, bags: Iterable[tuple[Tensor, Tensor]]
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("predict_bags runs on a CUDA device only (no CPU fallback)")
+    if task not in TASKS:
+        raise ValueError(f"task must be one of {TASKS}, got {task!r}")
     model = model.eval()
     main = torch.cuda.current_stream(device)
     streams = _stream_pool(device, max(1, n_streams))
@@ -92,7 +107,7 @@ def predict_bags(model: VisionTransformer, bags: Iterable[tuple[Tensor, Tensor]]
         si = i % len(streams)
         s = streams[si]
         with torch.cuda.stream(s):
-            key = (id(model), device.index, si, len(streams), tuple(feats.shape), feats.dtype)
+            key = (id(model), device.index, si, len(streams), tuple(feats.shape), feats.dtype, task)
             # (device-resident bags run eagerly: measured 3 % faster than replaying through the static input buffer)
             if graphs and not feats.is_cuda and feats.dtype in (torch.float16, torch.float32):
                 g = _GRAPHS.get(key)
@@ -104,7 +119,7 @@ def predict_bags(model: VisionTransformer, bags: Iterable[tuple[Tensor, Tensor]]
                         _GRAPHS.clear()
                         _SEEN.clear()
                     src_f = feats if feats.is_cuda or feats.is_pinned() else feats.pin_memory()
-                    g = _GRAPHS[key] = _GraphedForward(model, s, src_f, coords.float(), device)
+                    g = _GRAPHS[key] = _GraphedForward(model, s, src_f, coords.float(), device, task)
                 if len(_SEEN) > 4096:
                     _SEEN.clear()
                 _SEEN.add(key)
@@ -125,7 +140,7 @@ def predict_bags(model: VisionTransformer, bags: Iterable[tuple[Tensor, Tensor]]
                 feats = feats.float()
             # fp16 features are the aggregator's GEMM operand as they are: no fp32 round trip anywhere
             logits = model(feats.unsqueeze(0), coords=coords.unsqueeze(0).float(), mask=None)
-            out.append(torch.softmax(logits.float(), dim=1))
+            out.append(_finish(logits, task))
     if not out:
         return torch.empty((0, model._cfg["dim_output"]))
     for s in streams:
@@ -138,18 +153,23 @@ def predict_bags(model: VisionTransformer, bags: Iterable[tuple[Tensor, Tensor]]
 
 
 def predict_patients(model: VisionTransformer, patient_ids: Sequence[str], bags: Iterable[tuple[Tensor, Tensor]],
-                     device: torch.device | str = "cuda") -> dict[str, Tensor]:
-    """``_predict``'s result type: ``{patient_id: probabilities [C]}``.  Real cohorts are bags of different lengths:
+                     device: torch.device | str = "cuda", task: str = "classification") -> dict[str, Tensor]:
+    """``_predict``'s result type: ``{patient_id: probabilities [C]}`` (regression: ``[1]`` predictions; survival: scalar
+    risk scores, the reference's ``squeeze(-1)``).  Real cohorts are bags of different lengths:
     they go through ragged batches when the model allows it (measured on 64 host bags of 2 000 .. 10 000 tiles: 1 916
     vs 701 slides/s for per-bag forwards, whose ever-changing shapes defeat the graph replay and churn the allocator;
     for equal 4096-tile bags the two paths are within 10 % of each other)."""
-    probs = predict_bags_ragged(model, bags, device) if model.supports_ragged() else predict_bags(model, bags, device)
+    probs = (predict_bags_ragged(model, bags, device, task=task) if model.supports_ragged()
+             else predict_bags(model, bags, device, task=task))
+    if task == "survival":
+        probs = probs.squeeze(-1)
     return {pid: probs[i] for i, pid in enumerate(patient_ids)}
 
 
 @torch.inference_mode()
 def predict_bags_ragged(model: VisionTransformer, bags: Iterable[tuple[Tensor, Tensor]],
-                        device: torch.device | str = "cuda", max_rows: int = 36_000, max_bags: int = 32) -> Tensor:
+                        device: torch.device | str = "cuda", max_rows: int = 36_000, max_bags: int = 32,
+                        task: str = "classification") -> Tensor:
     """``predict_bags`` with bags of DIFFERENT lengths sharing one forward: consecutive bags are packed into ragged
     batches of up to ``max_rows`` tokens (``VisionTransformer.pack_ragged``), so that the dense layers see tens of
     thousands of rows per launch instead of one bag's few thousand (a batch-1 forward leaves most of its 22 launches
@@ -159,9 +179,11 @@ def predict_bags_ragged(model: VisionTransformer, bags: Iterable[tuple[Tensor, T
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError("predict_bags_ragged runs on a CUDA device only (no CPU fallback)")
+    if task not in TASKS:
+        raise ValueError(f"task must be one of {TASKS}, got {task!r}")
     model = model.eval()
     if not model.supports_ragged():
-        return predict_bags(model, bags, device)
+        return predict_bags(model, bags, device, task=task)
     main = torch.cuda.current_stream(device)
     copy = torch.cuda.Stream(device=device)
     out: list[Tensor] = []
@@ -200,7 +222,7 @@ def predict_bags_ragged(model: VisionTransformer, bags: Iterable[tuple[Tensor, T
         main.wait_event(ev)
         for t in (td, cd, sd):
             t.record_stream(main)
-        out.append(torch.softmax(model.forward_ragged(td, cd, sd, s_max), dim=1))
+        out.append(_finish(model.forward_ragged(td, cd, sd, s_max), task))
 
     group: list[tuple[Tensor, Tensor]] = []
     rows = 0

@@ -85,9 +85,9 @@ class _PPEG(nn.Module):
 class TransMIL(nn.Module):
     def __init__(self, dim_output: int, dim_input: int, dim_hidden: int) -> None:
         super().__init__()
-        if dim_hidden % 8 or dim_hidden // 8 != 64 or dim_input % 8:
-            raise ValueError("unsupported TransMIL configuration for the sm_100a kernels (dim_hidden 512 = 8 heads of 64, "
-                             "dim_input a multiple of 8)")
+        if dim_hidden % 8 or dim_hidden // 8 != 64:
+            raise ValueError("unsupported TransMIL configuration for the sm_100a kernels (dim_hidden 512 = 8 heads of 64; "
+                             "any dim_input: widths that are not a multiple of 8 run zero-padded)")
         self.pos_layer = _PPEG(dim_hidden)
         self._fc1 = nn.Sequential(nn.Linear(dim_input, dim_hidden), nn.ReLU())
         self.cls_token = nn.Parameter(torch.randn(1, 1, dim_hidden))
@@ -100,13 +100,18 @@ class TransMIL(nn.Module):
         self.fc1_fp32 = False   # True: _fc1 on the fp32 path too (1e-6 instead of 6e-4 against the reference module)
 
     def _w16(self, p: Tensor) -> Tensor:
+        """fp16 copy of a weight matrix (columns zero-padded to a multiple of 8, the GEMM's K granularity), refreshed when
+        the parameter changes."""
         try:
             key = (p._version, p.data_ptr())
         except RuntimeError:            # parameters created under inference_mode do not track versions
             key = (-1, p.data_ptr())
         hit = self._half.get(id(p))
         if hit is None or hit[0] != key or hit[1].device != p.device:
-            hit = (key, p.detach().half().contiguous())
+            w = p.detach().half()
+            if w.shape[1] % 8:
+                w = torch.nn.functional.pad(w, (0, 8 - w.shape[1] % 8))
+            hit = (key, w.contiguous())
             self._half[id(p)] = hit
         return hit[1]
 
@@ -227,7 +232,10 @@ class TransMIL(nn.Module):
                 _lib.check(_bind().stamp_sgemm_batched_f32(hb.data_ptr(), F, 0, w1.data_ptr(), F, 0, feats.data_ptr(), Cd, 0, n, Cd, F,
                                                            1, 1, 1.0, 0.0, b1.data_ptr(), 2, _stream()), "sgemm")
             else:
-                ops.gemm_tn(h[b].detach().half().contiguous(), self._w16(fc1.weight), out=feats, bias=fc1.bias,
+                hb = h[b].detach().half()
+                if F % 8:                                               # zero columns against the zero-padded weight columns
+                    hb = torch.nn.functional.pad(hb, (0, 8 - F % 8))
+                ops.gemm_tn(hb.contiguous(), self._w16(fc1.weight), out=feats, bias=fc1.bias.detach().float(),
                             act=ops.ACT_RELU, store=ops.ST_32)
             xs.append(torch.cat([self.cls_token.detach().float().reshape(1, Cd), feats, feats[:add]], dim=0).contiguous())
         self._nystrom_layer(xs, self.layer1)

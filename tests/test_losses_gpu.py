@@ -143,3 +143,84 @@ def test_task_training_step_matches_reference_golden(cuda_device, task):
         for k, p in model.named_parameters():
             p.grad = saved[k]
     _check_grads(model, g["grads"], task, term_scale=term_scale)
+
+
+def test_concordance_index_pair_rules():
+    """c-index of the survival validation (models/__init__.py:662-694, lifelines' pair rules): against a brute-force loop
+    over the pairs, ties in time and score included."""
+    import math
+
+    from stamp_b200.crossval import concordance_index
+
+    g = torch.Generator().manual_seed(0)
+    for n in (1, 2, 7, 40, 200):
+        s = torch.randint(0, 5, (n,), generator=g).float()
+        t = torch.randint(0, 6, (n,), generator=g).float()
+        e = torch.rand(n, generator=g) < 0.6
+        pairs = good = 0.0
+        for i in range(n):
+            for j in range(n):
+                if i != j and e[j] and (t[j] < t[i] or (t[j] == t[i] and not e[i])):     # j died before i left the study
+                    pairs += 1
+                    good += 1.0 if s[j] > s[i] else (0.5 if s[j] == s[i] else 0.0)
+        got = concordance_index(s, t, e)
+        assert (pairs == 0 and math.isnan(got)) or abs(got - good / pairs) < 1e-12
+    assert concordance_index(torch.tensor([3.0, 2.0, 1.0]), torch.tensor([1.0, 2.0, 3.0]), torch.ones(3)) == 1.0
+    assert concordance_index(torch.tensor([1.0, 2.0, 3.0]), torch.tensor([1.0, 2.0, 3.0]), torch.ones(3)) == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["regression", "survival"])
+def test_crossval_and_deploy_of_the_other_tasks(cuda_device, task):
+    """Cross-validation (crossval.py:48-370) and deployment (deploy.py:390-456) of the regression and survival tasks at
+    small scale: a planted signal (the share of shifted tiles sets the target / the hazard) is learnt on held-out folds,
+    the monitored metric picks the checkpoint, predictions come back as the reference's ``_predict`` shapes them."""
+    from stamp_b200.crossval import Patient, concordance_index, crossval
+    from stamp_b200.deploy import predict_patients
+    from stamp_b200.mil import VisionTransformer
+
+    g = torch.Generator().manual_seed(1)
+    pats, truth = [], {}
+    for i in range(36):
+        n = 90 + int(torch.randint(0, 30, (1,), generator=g))
+        level = (i % 6) / 5.0                                                 # 0 .. 1
+        f = torch.randn(n, 64, generator=g)
+        f[: int(n * 0.4 * level)] += 1.5
+        cells = torch.randperm(400, generator=g)[:n]
+        c = torch.stack([(cells % 20).float(), (cells // 20).float()], dim=-1) * 256.0
+        label = 2.0 * level - 1.0 if task == "regression" else (10.0 - 8.0 * level + 0.01 * i, float(i % 4 != 0))
+        truth[f"p{i:02d}"] = level
+        pats.append(Patient(f"p{i:02d}", f.half().to(cuda_device), c.to(cuda_device), label))
+    res = crossval(pats, n_splits=3, dim_input=64, mode="fold_per_gpu", task=task,
+                   model_params=dict(dim_model=128, n_heads=2, dim_feedforward=128, dropout=0.0, use_alibi=False),
+                   bag_size=64, batch_size=12, max_epochs=12, patience=4, max_lr=3e-3, seed=1)
+    assert [r.fold for r in res] == [0, 1, 2]
+    seen, preds, levels = [], [], []
+    for r in res:
+        assert r.probs.shape == ((len(r.test_patients), 1) if task == "regression" else (len(r.test_patients),))
+        best = min(h["validation_loss"] for h in r.history)
+        assert abs(r.history[r.best_epoch]["validation_loss"] - best) < 1e-12
+        seen += r.test_patients
+        preds += r.probs.flatten().tolist()
+        levels += [truth[p] for p in r.test_patients]
+    assert sorted(seen) == sorted(p.pid for p in pats)
+    corr = torch.corrcoef(torch.tensor([preds, levels]))[0, 1].item()
+    print(f"{task}: held-out correlation of the prediction with the planted level {corr:.3f}; "
+          f"validation metric per fold {[round(min(h['validation_loss'] for h in r.history), 3) for r in res]}")
+    assert corr > 0.5, corr
+    with pytest.raises(ValueError):
+        crossval(pats, n_splits=3, dim_input=64, mode="dp_in_fold", task=task)
+
+    # deployment: raw [1] predictions per patient for regression, scalar risk scores for survival
+    model = VisionTransformer(dim_output=1, dim_input=64, dim_model=128, n_layers=2, n_heads=2, dim_feedforward=128,
+                              dropout=0.0, use_alibi=False).to(cuda_device).eval()
+    out = predict_patients(model, [p.pid for p in pats[:5]], [(p.feats.cpu(), p.coords.cpu()) for p in pats[:5]], cuda_device,
+                           task=task)
+    with torch.inference_mode():
+        want = torch.cat([model(p.feats[None], coords=p.coords[None], mask=None).float() for p in pats[:5]]).cpu()
+    for i, p in enumerate(pats[:5]):
+        assert out[p.pid].shape == (() if task == "survival" else (1,))
+        assert abs(out[p.pid].flatten()[0].item() - want[i, 0].item()) < 2e-3 * max(1.0, abs(want[i, 0].item()))
+    if task == "survival":
+        y = torch.tensor([p.label for p in pats])
+        assert 0.0 <= concordance_index(torch.tensor(preds), y[:, 0][[int(s[1:]) for s in seen]], y[:, 1][[int(s[1:]) for s in seen]]) <= 1.0

@@ -109,3 +109,47 @@ def test_attention_f32_key_splits(cuda_device, nq, nk, splits):
     sp = lambda t: t.double().reshape(-1, H, 64).transpose(0, 1)      # noqa: E731
     want = ((sp(q) @ sp(k).transpose(1, 2) * 0.125).softmax(-1) @ sp(v)).transpose(0, 1).reshape(nq, H * 64)
     assert ((out.double() - want).norm() / want.norm()).item() < 1e-6
+
+
+@pytest.mark.gpu
+def test_reference_unit_test_shapes(cuda_device):
+    """The reference's own model tests (tests/test_model.py:77-166): MLP on [7, 33] vectors, TransMIL on 7 bags of 76 tiles
+    with 457 input features (not a multiple of the GEMM's K granularity: runs zero-padded), coords / mask keywords accepted
+    and ignored, two forwards identical; the TransMIL logits against the reference module's (golden `logits_odd`)."""
+    from oracle.transmil_weights import transmil_state_dict
+    from stamp_b200.mlp import MLP
+    from stamp_b200.transmil import TransMIL
+
+    z = np.load(GOLD)
+    g = torch.Generator().manual_seed(9)
+    for n in (300, 1100):
+        _bags(n, g)                                                   # advance the generator as the golden's script did
+    bags = torch.rand(7, 76, 457, generator=g).half().float()
+    assert abs(bags.double().sum().item() - float(z["bags_checksum_odd"])) < 1e-9
+    model = TransMIL(dim_output=4, dim_input=457, dim_hidden=512)
+    model.load_state_dict(transmil_state_dict(4, 457, 512), strict=True)
+    model = model.to(cuda_device).eval()
+    mask = torch.arange(76)[None, :].repeat(7, 1) >= torch.randint(1, 76, (7, 1))
+    with torch.inference_mode():
+        a = model.forward(bags.to(cuda_device), coords=torch.rand(7, 76, 2, device=cuda_device), mask=mask.to(cuda_device))
+        b = model.forward(bags.to(cuda_device), coords=torch.rand(7, 76, 2, device=cuda_device), mask=mask.to(cuda_device))
+    assert a.shape == (7, 4) and torch.equal(a, b)
+    want = torch.from_numpy(z["logits_odd"])
+    err = ((a.float().cpu() - want).norm(dim=1) / want.norm(dim=1)).max().item()
+    model.fc1_fp32 = True
+    with torch.inference_mode():
+        a32 = model.forward(bags.to(cuda_device))
+    model.fc1_fp32 = False
+    err32 = ((a32.float().cpu() - want).norm(dim=1) / want.norm(dim=1)).max().item()
+    print(f"TransMIL, reference test shape (76 tiles = one token per landmark, 457 features): max per-bag relative error "
+          f"{err:.2e} (_fc1 fp16 operands), {err32:.2e} (all fp32)")
+    # one token per landmark: the pseudo-inverse is of the full 256 x 256 attention matrix, the worst-conditioned case
+    assert err32 < 1e-4 and err < 2e-3, (err, err32)              # measured 2.9e-6 / 5.2e-4
+
+    mlp = MLP(dim_output=4, dim_input=33, dim_hidden=64, num_layers=3, dropout=0.1).to(cuda_device).eval()
+    feats = torch.rand(7, 33, device=cuda_device)
+    with torch.inference_mode():
+        l1, l2 = mlp.forward(feats), mlp.forward(feats)
+        want = mlp.mlp(feats)                                          # the same nn.Sequential in eager torch on the GPU
+    assert l1.shape == (7, 4) and torch.equal(l1, l2)
+    assert ((l1 - want).norm() / want.norm()).item() < 1e-5            # eager torch may use TF32-free fp32: same arithmetic
