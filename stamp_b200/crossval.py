@@ -109,6 +109,18 @@ def concordance_index(scores: Tensor, times: Tensor, events: Tensor) -> float:
     return float(good / pairs.double())
 
 
+def stratification_labels(labels: Sequence, task: str) -> list | None:
+    """``_get_splits`` (crossval.py:373-423) with the splitter ``categorical_crossval_`` picks (:90-96): folds stratified by
+    class, by event status for survival, plain ``KFold`` (None) for regression."""
+    if task == "classification":
+        return list(labels)
+    if task == "survival":
+        return [int(v[1]) for v in labels]
+    if task == "regression":
+        return None
+    raise ValueError(f"unknown task {task!r}")
+
+
 def _targets(labels: Sequence, task: str, n_classes: int, device) -> Tensor:
     if task == "classification":
         return _one_hot(labels, n_classes, device)
@@ -220,10 +232,7 @@ def crossval(patients: Sequence[Patient], *, n_splits: int = 5, n_classes: int =
         raise ValueError(mode)
     rank, ws = world()
     by_id = {p.pid: p for p in patients}
-    # _get_splits (crossval.py:373-423): stratified by class, by event status for survival, plain KFold for regression
-    strat = {"classification": lambda: [p.label for p in patients], "survival": lambda: [int(p.label[1]) for p in patients],
-             "regression": lambda: None}[task]()
-    splits = crossval_splits([p.pid for p in patients], strat, n_splits)
+    splits = crossval_splits([p.pid for p in patients], stratification_labels([p.label for p in patients], task), n_splits)
     mine = folds_for_rank(n_splits, rank, ws) if mode == "fold_per_gpu" else list(range(n_splits))
     out = []
     for f in mine:

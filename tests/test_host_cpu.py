@@ -375,3 +375,39 @@ def test_vals_to_im_matches_the_reference_function():
         from stamp_b200.heatmaps import ranked_tiles
 
         ranked_tiles(torch.rand(5), 2, 2)
+
+
+def test_task_aware_folds_match_the_reference_get_splits():
+    """crossval.stratification_labels + sharding.crossval_splits against the reference's own ``_get_splits``
+    (src/stamp/modeling/crossval.py:373-423, executed from its source with the splitter ``categorical_crossval_`` picks,
+    :90-96) for the three tasks: identical train / test patient sets per fold."""
+    ref_file = Path("/root/reference/src/stamp/modeling/crossval.py")
+    if not ref_file.exists():
+        pytest.skip("reference checkout not present on this machine")
+    from collections import namedtuple
+    from typing import Any, cast
+
+    import numpy as np
+    from sklearn.model_selection import KFold, StratifiedKFold
+
+    from stamp_b200.crossval import stratification_labels
+    from stamp_b200.sharding import crossval_splits
+
+    ns = _reference_functions(ref_file, ["_get_splits"])
+    Split = namedtuple("Split", "train_patients test_patients")
+    Splits = namedtuple("Splits", "splits")
+    ns.update(np=np, cast=cast, Any=Any, _Split=Split, _Splits=Splits)
+    Data = namedtuple("Data", "ground_truth")
+    ids = [f"pat{i:03d}" for i in range(53)]
+    cases = {"classification": ["MSI" if i % 3 == 0 else "MSS" for i in range(53)],
+             "survival": [(float(100 - i), int(i % 4 != 0)) for i in range(53)],
+             "regression": [float(i) * 0.1 for i in range(53)]}
+    for task, labels in cases.items():
+        spliter = KFold if task == "regression" else StratifiedKFold
+        ref = ns["_get_splits"](patient_to_data={p: Data(l) for p, l in zip(ids, labels)}, n_splits=4, spliter=spliter, task=task)
+        ours = crossval_splits(ids, stratification_labels(labels, task), 4)
+        assert len(ref.splits) == len(ours) == 4
+        for r, (tr, te) in zip(ref.splits, ours):
+            assert set(tr) == r.train_patients and set(te) == r.test_patients, task
+    with pytest.raises(ValueError):
+        stratification_labels([1, 2], "ranking")
