@@ -207,7 +207,9 @@ def test_crossval_and_deploy_of_the_other_tasks(cuda_device, task):
     corr = torch.corrcoef(torch.tensor([preds, levels]))[0, 1].item()
     print(f"{task}: held-out correlation of the prediction with the planted level {corr:.3f}; "
           f"validation metric per fold {[round(min(h['validation_loss'] for h in r.history), 3) for r in res]}")
-    assert corr > 0.5, corr
+    # measured 0.92 (regression) / 0.70 (survival); the reference module trained the same way on the CPU: 0.96 / 0.79;
+    # chance level for 36 patients is 0 +- 0.17
+    assert corr > (0.6 if task == "regression" else 0.35), corr
     with pytest.raises(ValueError):
         crossval(pats, n_splits=3, dim_input=64, mode="dp_in_fold", task=task)
 
