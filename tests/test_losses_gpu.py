@@ -226,3 +226,20 @@ def test_crossval_and_deploy_of_the_other_tasks(cuda_device, task):
     if task == "survival":
         y = torch.tensor([p.label for p in pats])
         assert 0.0 <= concordance_index(torch.tensor(preds), y[:, 0][[int(s[1:]) for s in seen]], y[:, 1][[int(s[1:]) for s in seen]]) <= 1.0
+
+
+def test_task_plumbing_on_the_host():
+    """What the tasks change outside the kernels: target tensors of a batch (data.py's encoded targets: one-hot classes,
+    [B, 1] regression values, [B, 2] = (time, event)), and ``_predict``'s post-processing (deploy.py:440-449)."""
+    from stamp_b200.crossval import _targets
+    from stamp_b200.deploy import _finish, predict_bags, predict_bags_ragged
+
+    assert torch.equal(_targets([0, 2, 1], "classification", 3, "cpu"), torch.eye(3)[[0, 2, 1]])
+    assert torch.equal(_targets([0.5, -1.0], "regression", 1, "cpu"), torch.tensor([[0.5], [-1.0]]))
+    assert torch.equal(_targets([(5.0, 1), (3.0, 0)], "survival", 1, "cpu"), torch.tensor([[5.0, 1.0], [3.0, 0.0]]))
+    logits = torch.tensor([[1.0, 3.0], [0.0, 0.0]])
+    assert torch.allclose(_finish(logits, "classification"), torch.softmax(logits, dim=1))
+    assert torch.equal(_finish(logits[:, :1].half(), "regression"), logits[:, :1]) and _finish(logits[:, :1], "survival").dtype == torch.float32
+    for fn in (predict_bags, predict_bags_ragged):
+        with pytest.raises(RuntimeError):
+            fn(None, iter([]), "cpu")
